@@ -1,0 +1,363 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's heatmap hot path.
+
+Nothing in ``simple_pose_b200/`` imports this module. It exists so that the CUDA
+path can be checked (``tests/``, ``__graft_entry__.smoke()``) and so that
+``bench.py`` can time the reference's CPU algorithm next to the GPU numbers
+(``cpu_baseline`` and ``--impl reference``). It is never the thing shipped.
+
+Parity status: **pinned**. The reference has no tests of its own (SURVEY.md
+section 4), so the pin is (a) ``tests/test_oracle_vs_reference.py`` which, in
+the build container where ``/root/reference`` is mounted, runs the reference's
+own functions (through ``oracle/ref_loader.py``) against every function below
+and demands bit equality, and (b) the fixtures in ``tests/golden/`` generated
+from the reference by ``oracle/make_golden.py`` which travel to the GPU box.
+
+Each function cites the reference lines it restates (paths relative to the
+reference root). The arithmetic (dtype promotions, operation order, library
+calls) follows the reference so that results are bit-identical on CPU; the
+code itself is written independently.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+COCO_JOINT_PAIRS = ((1, 2), (3, 4), (5, 6), (7, 8), (9, 10), (11, 12), (13, 14), (15, 16))
+COCO_OKS_SIGMAS = np.array(
+    [.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89]) / 10.0
+
+
+# --------------------------------------------------------------------------- encode
+def encode_person(joints, sigma=2.0, shape=(48, 64)):
+    """DarkPose-style unbiased target encoder for one person.
+
+    Restates ``RefineSimpleTransform.get_heat_map`` (commons/transforms.py:167-191).
+    ``joints`` is [K,3] float32 (x, y, vis) in heatmap pixels, ``shape`` is (W, H).
+    Returns (targets [K,H,W] float32, weights [K] float32).
+
+    Arithmetic notes that matter for bit parity:
+      * the cull test uses ``int()`` (truncation toward zero) of float32 expressions
+        ``mu - 3*sigma`` and ``mu + 3*sigma + 1`` (transforms.py:181-182). With NumPy 2
+        scalar promotion a float32 scalar combined with a Python float stays float32.
+      * the Gaussian is evaluated in float64 over the *whole* map (int64 grid minus a
+        float32 centre promotes to float64, transforms.py:188-190) and rounded to
+        float32 on assignment.
+    """
+    joints = np.asarray(joints)
+    width, height = int(shape[0]), int(shape[1])
+    n = joints.shape[0]
+    weights = np.array(joints[:, 2], copy=True)
+    targets = np.zeros((n, height, width), dtype=np.float32)
+    reach = sigma * 3
+    cols = np.arange(width)
+    rows = np.arange(height)
+    for j in range(n):
+        cx, cy = joints[j, 0], joints[j, 1]
+        lo_x, lo_y = int(cx - reach), int(cy - reach)
+        hi_x, hi_y = int(cx + reach + 1), int(cy + reach + 1)
+        if lo_x >= width or lo_y >= height or hi_x < 0 or hi_y < 0:
+            weights[j] = 0.
+            continue
+        if weights[j] > 0.5:
+            gx, gy = np.meshgrid(cols, rows)
+            grid = np.stack([gx, gy], axis=-1)
+            centre = np.array([cx, cy])
+            targets[j] = np.exp(-np.sum((grid - centre) ** 2, axis=-1) / (2 * sigma ** 2))
+    return targets, weights
+
+
+def encode_batch(joints, sigma=2.0, shape=(48, 64)):
+    """[B,K,3] -> ([B,K,H,W], [B,K]); the stacking done by ``MSCOCO.collate_fn``
+    (datasets/coco.py:138-146)."""
+    joints = np.asarray(joints)
+    maps, wts = [], []
+    for b in range(joints.shape[0]):
+        t, w = encode_person(joints[b], sigma, shape)
+        maps.append(t)
+        wts.append(w)
+    return np.stack(maps), np.stack(wts)
+
+
+def encode_person_basic(joints, sigma=2.0, shape=(48, 64), stride=4):
+    """Quantised 13x13 encoder: ``BasicSimpleTransform.get_heat_map``
+    (commons/transforms.py:80-116). ``joints`` are in *input* pixels."""
+    joints = np.asarray(joints)
+    width, height = int(shape[0]), int(shape[1])
+    n = joints.shape[0]
+    weights = np.array(joints[:, 2], copy=True)
+    targets = np.zeros((n, height, width), dtype=np.float32)
+    reach = sigma * 3
+    side = 2 * reach + 1
+    ax = np.arange(0, side, 1, np.float32)
+    mid = side // 2
+    patch = np.exp(-((ax[None, :] - mid) ** 2 + (ax[:, None] - mid) ** 2) / (2 * (sigma ** 2)))
+    for j in range(n):
+        mx = int(joints[j, 0] / stride + 0.5)
+        my = int(joints[j, 1] / stride + 0.5)
+        lo = (int(mx - reach), int(my - reach))
+        hi = (int(mx + reach + 1), int(my + reach + 1))
+        if lo[0] >= width or lo[1] >= height or hi[0] < 0 or hi[1] < 0:
+            weights[j] = 0.
+            continue
+        px = (max(0, -lo[0]), min(hi[0], width) - lo[0])
+        py = (max(0, -lo[1]), min(hi[1], height) - lo[1])
+        ix = (max(0, lo[0]), min(hi[0], width))
+        iy = (max(0, lo[1]), min(hi[1], height))
+        if weights[j] > 0.5:
+            targets[j, iy[0]:iy[1], ix[0]:ix[1]] = patch[py[0]:py[1], px[0]:px[1]]
+    return targets, weights
+
+
+# --------------------------------------------------------------------------- loss
+def masked_mse_loss(pred, target, mask):
+    """``0.5 * nn.MSELoss()(pred.mul(mask[..., None, None]), target.mul(mask[..., None, None]))``
+    -- the inline expression of processors/dp_pose_hrnet_solver.py:86,106 (same in
+    dp_pose_resnet_solver.py:107 and ddp_pose_resnet_solver.py:117). Mean over *all*
+    B*K*H*W elements. Returns a 0-d tensor attached to ``pred``'s graph."""
+    m = mask[..., None, None]
+    return 0.5 * torch.nn.MSELoss()(pred.mul(m), target.mul(m))
+
+
+def masked_mse_loss_and_grad(pred, target, mask):
+    """Loss value and d loss / d pred via autograd of the expression above."""
+    p = pred.detach().clone().requires_grad_(True)
+    loss = masked_mse_loss(p, target, mask)
+    loss.backward()
+    return loss.detach(), p.grad.detach()
+
+
+# --------------------------------------------------------------------------- decode
+def argmax_coords(heat_map):
+    """``BasicKeyPointDecoder.heat_map_to_axis`` (metrics/pose_metrics.py:11-24).
+
+    [B,K,H,W] -> (coords [B,K,2] float32 as (x, y), max_val [B,K,1]). First maximal
+    index on ties, NaN propagates (``torch.max`` semantics); x = idx % W and
+    y = floor(idx / W) are computed in float32; both are zeroed when max_val <= 0."""
+    b, k, h, w = heat_map.shape
+    flat = heat_map.reshape(b, k, h * w)
+    peak, where = flat.max(dim=-1, keepdim=True)
+    xy = where.repeat(1, 1, 2).float()
+    xy[..., 0] = xy[..., 0] % w
+    xy[..., 1] = (xy[..., 1] / w).floor()
+    xy = xy * (peak > 0.).repeat(1, 1, 2).float()
+    return xy, peak
+
+
+def argmax_index(heat_map):
+    """Flat argmax index per (b,k) as int64 [B,K] (the integer the float coords of
+    ``argmax_coords`` are derived from; used for the bit-exact index gate)."""
+    b, k, h, w = heat_map.shape
+    return heat_map.reshape(b, k, h * w).max(dim=-1)[1]
+
+
+def gaussian_taps(kernel_size=11):
+    """1-D taps of ``cv.getGaussianKernel(kernel_size, 0)`` for kernel_size >= 9
+    (metrics/pose_metrics.py:57): sigma = 0.3*((n-1)*0.5-1)+0.8, normalised
+    ``exp(-x^2/(2 sigma^2))`` in float64. For n = 11 (sigma = 2.0) the float32 outer
+    product is bit-equal to OpenCV 4.13's (checked in tests when cv2 is importable).
+    OpenCV uses fixed tables for n <= 7; the reference only ever uses 11."""
+    n = int(kernel_size)
+    sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8
+    x = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
+    g = np.exp(-(x * x) / (2.0 * sigma * sigma))
+    return g / g.sum()
+
+
+def blur_weights(kernel_size=11):
+    """float32 [n,n] = float32(k64 k64^T) (metrics/pose_metrics.py:57-60)."""
+    k = gaussian_taps(kernel_size).reshape(-1, 1)
+    return (k * k.T).astype(np.float32)
+
+
+def gauss_taylor_decode(heat_map, trans_inv, kernel_size=11, return_heatmap_space=False):
+    """``GaussTaylorKeyPointDecoder.__call__`` (metrics/pose_metrics.py:62-107), CPU.
+
+    heat_map [B,K,H,W] float32, trans_inv [B,2,3] float32 ->
+    (coords [B,K,2] float32 in image px, max_val [B,K,1] float32).
+    Steps: argmax on the original map (:66); depthwise kxk blur with zero padding (:68);
+    rescale by ori_max / blur_max, clamp at 1e-10, log (:71-73); for peaks with
+    1 < x < W-2 and 1 < y < H-2 (:78) central differences of the log map (:80-93);
+    keep those with dxx*dyy - dxy^2 != 0 (:94); offset = -H^-1 g through
+    ``torch.inverse`` (:95-100); coords = clamp(coords + offset, min=0) for those
+    joints only (:101-103); affine back-projection (:105-106)."""
+    heat_map = heat_map.detach()
+    b, k, h, w = heat_map.shape
+    wts = torch.from_numpy(blur_weights(kernel_size))[None, None].repeat(k, 1, 1, 1)
+    coords, peak = argmax_coords(heat_map)
+    blurred = F.conv2d(heat_map, wts, bias=None, stride=1, padding=(kernel_size - 1) // 2, groups=k)
+    ori_max = heat_map.reshape(b, k, -1).max(dim=-1)[0]
+    blur_max = blurred.reshape(b, k, -1).max(dim=-1)[0]
+    logmap = (blurred * ori_max[..., None, None] / blur_max[..., None, None]).clamp(min=1e-10).log()
+
+    flat = logmap.reshape(b * k, h * w)
+    xi = coords[..., 0].long().reshape(-1)
+    yi = coords[..., 1].long().reshape(-1)
+    inner = (xi > 1) & (xi < w - 2) & (yi > 1) & (yi < h - 2)
+    rows = torch.nonzero(inner).reshape(-1)
+    vx, vy = xi[rows], yi[rows]
+
+    def at(dy, dx):
+        return flat[rows, (vy + dy) * w + (vx + dx)]
+
+    c = at(0, 0)
+    dx = 0.5 * (at(0, 1) - at(0, -1))
+    dy = 0.5 * (at(1, 0) - at(-1, 0))
+    dxx = 0.25 * (at(0, 2) - 2 * c + at(0, -2))
+    dxy = 0.25 * (at(1, 1) - at(-1, 1) - at(1, -1) + at(-1, -1))
+    dyy = 0.25 * (at(2, 0) - 2 * c + at(-2, 0))
+    solvable = dxx * dyy - dxy ** 2 != 0
+    hess = torch.stack([torch.stack([dxx, dxy], dim=-1), torch.stack([dxy, dyy], dim=-1)], dim=-2)[solvable]
+    grad = torch.stack([dx, dy], dim=-1).unsqueeze(-1)[solvable]
+    step = (-hess.inverse() @ grad).transpose(1, 2).squeeze(1)
+    out = coords.reshape(-1, 2).clone()
+    refine_rows = rows[solvable]
+    out[refine_rows] = (out[refine_rows] + step).clamp(min=0.)
+    out = out.reshape(b, k, 2)
+    if return_heatmap_space:
+        return out, peak
+    return back_project(out, trans_inv), peak
+
+
+def back_project(coords, trans_inv):
+    """Last two lines of both decoders (metrics/pose_metrics.py:50-51,105-106):
+    out[b,c,a] = sum_d [x, y, 1][d] * trans_inv[b,a,d] via ``torch.einsum``."""
+    homog = torch.cat([coords, torch.ones_like(coords[..., [0]])], dim=-1)
+    return torch.einsum("bcd,bad->bca", homog, trans_inv)
+
+
+def basic_decode(heat_map, trans_inv):
+    """``BasicKeyPointDecoder.__call__`` (metrics/pose_metrics.py:26-52): argmax, then a
+    quarter-pixel shift toward the larger neighbour for 1 < x < W-1, 1 < y < H-1."""
+    heat_map = heat_map.detach()
+    b, k, h, w = heat_map.shape
+    coords, peak = argmax_coords(heat_map)
+    flat = heat_map.reshape(b * k, h * w)
+    xi = coords[..., 0].long().reshape(-1)
+    yi = coords[..., 1].long().reshape(-1)
+    inner = (xi > 1) & (xi < w - 1) & (yi > 1) & (yi < h - 1)
+    rows = torch.nonzero(inner).reshape(-1)
+    vx, vy = xi[rows], yi[rows]
+    sx = (flat[rows, vy * w + vx + 1] - flat[rows, vy * w + vx - 1]).sign()
+    sy = (flat[rows, (vy + 1) * w + vx] - flat[rows, (vy - 1) * w + vx]).sign()
+    out = coords.reshape(-1, 2).clone()
+    out[rows] = out[rows] + torch.stack([sx, sy], dim=-1) * 0.25
+    return back_project(out.reshape(b, k, 2), trans_inv), peak
+
+
+# --------------------------------------------------------------------------- flip test
+def swap_permutation(num_joints=17, joint_pairs=COCO_JOINT_PAIRS):
+    """Channel permutation equivalent to the pair swap in ``flip_joints``
+    (commons/joint_utils.py:109-111) with ``joint_pairs`` of datasets/coco.py:26."""
+    perm = list(range(num_joints))
+    for a, b in joint_pairs:
+        perm[a], perm[b] = perm[b], perm[a]
+    return perm
+
+
+def flip_average(heat_map, heat_map_flip, joint_pairs=COCO_JOINT_PAIRS):
+    """NOT IN THE REFERENCE -- composed from its primitives:
+    avg[b,k,y,x] = 0.5 * (hm[b,k,y,x] + hm_flip[b,perm[k],y,W-1-x]); pure mirror
+    ``x -> W-1-x`` and pair swap as in ``flip_joints`` (commons/joint_utils.py:102-112),
+    no 1-px shift."""
+    perm = swap_permutation(heat_map.shape[1], joint_pairs)
+    return 0.5 * (heat_map + heat_map_flip.flip(-1)[:, perm])
+
+
+def flip_decode(heat_map, heat_map_flip, trans_inv, joint_pairs=COCO_JOINT_PAIRS, kernel_size=11,
+                return_heatmap_space=False):
+    return gauss_taylor_decode(flip_average(heat_map, heat_map_flip, joint_pairs), trans_inv,
+                               kernel_size, return_heatmap_space)
+
+
+# --------------------------------------------------------------------------- OKS / NMS
+def oks_similarity(pick_kps, cand_kps, pick_area, cand_area, sigmas=None, in_vis_thresh=None):
+    """``oks_iou`` (datasets/naive_data.py:120-150). pick [K,3], cand [n,K,3] -> [n] float64.
+    e = (dx^2+dy^2)/var/((a_p+a_c)/2 + 1e-12)/2 ; oks = sum(exp(-e)*vis)/(sum(vis)+1e-12);
+    vis is float32 ones unless a visibility threshold is given."""
+    if not isinstance(sigmas, np.ndarray):
+        sigmas = COCO_OKS_SIGMAS
+    var = (sigmas * 2) ** 2
+    dx = cand_kps[..., 0] - pick_kps[:, 0]
+    dy = cand_kps[..., 1] - pick_kps[:, 1]
+    e = (dx ** 2 + dy ** 2) / var / ((pick_area + cand_area)[:, None] / 2 + 1e-12) / 2
+    vis = np.ones_like(cand_kps[..., 2], dtype=np.float32)
+    if in_vis_thresh is not None:
+        pick_vis = np.tile((pick_kps[:, 2] > in_vis_thresh)[None, :], (cand_kps.shape[0], 1))
+        vis = ((cand_kps[..., 2] > in_vis_thresh) & pick_vis).astype(np.float32)
+    return (np.exp(-e) * vis).sum(-1) / (vis.sum(-1) + 1e-12)
+
+
+def oks_greedy_nms(kps, scores, areas, thresh, sigmas=None, in_vis_thresh=None):
+    """``oks_nms`` (datasets/naive_data.py:153-173): visit persons by descending score
+    (``argsort()[::-1]``), keep the head, drop every remaining one whose OKS with it is
+    > thresh. Returns the kept indices in pick order."""
+    pending = scores.argsort()[::-1]
+    kept = []
+    while pending.size > 0:
+        head = pending[0]
+        kept.append(head)
+        pending = pending[1:]
+        if pending.size == 0:
+            break
+        sim = oks_similarity(kps[head], kps[pending], areas[head], areas[pending], sigmas, in_vis_thresh)
+        pending = pending[sim <= thresh]
+    return kept
+
+
+def rescore_person(box_score, kps, in_vis_thre=0.2):
+    """eval.py:168-175: score = box_score * mean(joint_score[joint_score > thr]) (0 if none)."""
+    js = np.asarray(kps, dtype=np.float64).reshape(-1, 3)[:, -1]
+    sel = js > in_vis_thre
+    mean = js[sel].mean() if sel.sum() > 0 else 0.
+    return box_score * mean
+
+
+def rescore_and_nms(kps, box_scores, areas, seg_offsets, in_vis_thre=0.2, oks_thre=0.9):
+    """eval.py:153-197 without the JSON round trip: per image (segment) rescore, run
+    ``oks_nms`` and return (keep mask [N] bool, scores [N] float64, kept index lists)."""
+    kps = np.asarray(kps, dtype=np.float64)
+    n = kps.shape[0]
+    scores = np.array([rescore_person(box_scores[i], kps[i], in_vis_thre) for i in range(n)], dtype=np.float64)
+    keep = np.zeros(n, dtype=bool)
+    picks = []
+    for s in range(len(seg_offsets) - 1):
+        lo, hi = int(seg_offsets[s]), int(seg_offsets[s + 1])
+        if hi <= lo:
+            picks.append([])
+            continue
+        sel = oks_greedy_nms(kps[lo:hi], scores[lo:hi], np.asarray(areas[lo:hi], dtype=np.float64), oks_thre)
+        sel = [int(i) + lo for i in sel]
+        keep[sel] = True
+        picks.append(sel)
+    return keep, scores, picks
+
+
+# --------------------------------------------------------------------------- accuracy metric
+def heat_map_acc(predicts, targets, distance_thresh=0.5, norm_frac=10.):
+    """``HeatMapAcc.__call__`` (metrics/pose_metrics.py:212-245): per-joint fraction of
+    persons whose argmax lies within ``distance_thresh`` (in units of (W,H)/norm_frac) of the
+    target argmax, over persons whose target argmax has x > 1 and y > 1; averaged over joints
+    that have at least one such person."""
+    p, _ = argmax_coords(predicts)
+    t, _ = argmax_coords(targets)
+    norm = torch.tensor([predicts.shape[-1], predicts.shape[-2]], dtype=torch.float) / norm_frac
+    ok = (t[..., 0] > 1) & (t[..., 1] > 1)
+    dist = torch.norm(p / norm - t / norm, dim=-1)
+    dist[~ok] = -1.
+    total, used = 0., 0.
+    for j in range(dist.shape[1]):
+        dj, oj = dist.T[j], ok.T[j]
+        if oj.sum().item() < 1:
+            continue
+        total = total + (dj[oj] < distance_thresh).sum().float() / (oj.sum())
+        used += 1
+    if used > 0:
+        return total / used
+    return torch.tensor(0.)
+
+
+def kps_score(max_val):
+    """Person score of ``kps_to_dict_`` (metrics/pose_metrics.py:176): mean + max of the
+    joint peak values. max_val [B,K,1] -> [B]."""
+    return max_val.mean(dim=(1, 2)) + max_val.amax(dim=(1, 2))

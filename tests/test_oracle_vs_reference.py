@@ -1,0 +1,77 @@
+"""CPU, build container only: pins the oracle restatement against the unmodified reference
+imported from /root/reference (skipped where the tree is absent, e.g. on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import heatmap_oracle as O
+from oracle import ref_loader
+from simple_pose_b200 import synth
+from conftest import bits
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (72, 96), (20, 12)])
+def test_encode(ref, shape):
+    w, h = shape
+    joints = synth.joints(24, height=h, width=w, seed=101).numpy()
+    t, wt = O.encode_batch(joints, 2.0, shape)
+    for b in range(joints.shape[0]):
+        rt, rw = ref.get_heat_map(joints[b], 2.0, shape)
+        assert np.array_equal(bits(rt), bits(t[b])) and np.array_equal(rw, wt[b])
+
+
+@pytest.mark.parametrize("hw,noise", [((64, 48), 0.01), ((96, 72), 0.01), ((64, 48), 0.05), ((32, 24), 0.02)])
+def test_decode(ref, hw, noise):
+    h, w = hw
+    hm = synth.heatmaps(16, height=h, width=w, seed=202, noise=noise)
+    tinv = synth.inverse_affines(16, height=h, width=w, seed=202)[0]
+    rc, rm = ref.GaussTaylorKeyPointDecoder()(hm.clone(), tinv)
+    oc, om = O.gauss_taylor_decode(hm, tinv)
+    assert torch.equal(rc, oc) and torch.equal(rm, om)
+    rb, _ = ref.BasicKeyPointDecoder()(hm.clone(), tinv)
+    ob, _ = O.basic_decode(hm, tinv)
+    assert torch.equal(rb, ob)
+
+
+def test_decode_does_not_mutate_input(ref):
+    hm = synth.heatmaps(2, seed=5)
+    keep = hm.clone()
+    O.gauss_taylor_decode(hm, synth.identity_affines(2))
+    assert torch.equal(hm, keep)
+
+
+def test_loss(ref):
+    tgt = torch.from_numpy(O.encode_batch(synth.joints(8, seed=7).numpy())[0])
+    msk = torch.from_numpy(O.encode_batch(synth.joints(8, seed=7).numpy())[1])
+    pred = synth.predictions_like(tgt, seed=8)
+    p = pred.clone().requires_grad_(True)
+    ref_loss = 0.5 * torch.nn.MSELoss()(p.mul(msk[[..., None, None]]), tgt.mul(msk[[..., None, None]]))
+    ref_loss.backward()
+    loss, grad = O.masked_mse_loss_and_grad(pred, tgt, msk)
+    assert torch.equal(loss, ref_loss.detach()) and torch.equal(grad, p.grad)
+
+
+def test_oks_and_nms(ref):
+    kps, box, area, seg = synth.nms_groups(40, seed=9)
+    kps, box, area, seg = kps.numpy(), box.numpy(), area.numpy(), seg.numpy()
+    for s in range(40):
+        lo, hi = seg[s], seg[s + 1]
+        r = ref.oks_nms(kps[lo:hi], box[lo:hi], area[lo:hi], 0.9)
+        o = O.oks_greedy_nms(kps[lo:hi], box[lo:hi], area[lo:hi], 0.9)
+        assert [int(i) for i in r] == [int(i) for i in o]
+        a = ref.oks_iou(kps[lo], kps[lo:hi], area[lo], area[lo:hi])
+        b = O.oks_similarity(kps[lo], kps[lo:hi], area[lo], area[lo:hi])
+        assert np.array_equal(bits(a), bits(b))
+
+
+def test_heat_map_acc(ref):
+    tgt = torch.from_numpy(O.encode_batch(synth.joints(8, seed=17).numpy())[0])
+    pred = synth.predictions_like(tgt, seed=18, noise=0.3)
+    assert float(ref.HeatMapAcc()(pred, tgt)) == float(O.heat_map_acc(pred, tgt))
