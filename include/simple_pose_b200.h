@@ -1,0 +1,148 @@
+/*
+ * simple_pose_b200 -- C ABI of the B200 (sm_100a) heatmap hot path.
+ *
+ * The reference (liangheming/simple_pose) is 100 % Python: it has no plugin, operator or FFI
+ * layer. Its "interface" for this path is a set of Python call signatures; each entry point
+ * below names the reference function it replaces (paths relative to the reference root).
+ * The Python mirror of those signatures lives in simple_pose_b200/{commons,metrics,datasets,
+ * processors}/ and reaches this library through ctypes (simple_pose_b200/_abi.py).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every buffer is allocated and owned by the caller;
+ *     the library never allocates or frees persistent device memory;
+ *   - pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *     tensors are dense, row-major ("C-contiguous"), base addresses 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is
+ *     enqueued on it and the call returns without synchronising;
+ *   - return value: 0 on success, a cudaError_t (> 0) for CUDA failures, or one of the
+ *     SP_ERR_* codes (< 0) for argument errors; sp_error_string() names any of them.
+ *     No exception crosses the boundary;
+ *   - stateless and re-entrant; the only per-call scratch is the workspace the caller hands
+ *     to sp_mse_fwd_bwd_f32.
+ */
+#ifndef SIMPLE_POSE_B200_H
+#define SIMPLE_POSE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_ABI_VERSION 1
+
+#define SP_ERR_BAD_ARGUMENT  (-1)   /* null pointer, non-positive size, unsupported value  */
+#define SP_ERR_BAD_ALIGNMENT (-2)   /* a base pointer is not 16-byte aligned                */
+#define SP_ERR_WORKSPACE     (-3)   /* workspace too small                                  */
+#define SP_ERR_UNSUPPORTED   (-4)   /* shape outside what the kernels handle                */
+
+/* decode modes of sp_decode_f32 */
+#define SP_DECODE_GAUSS_TAYLOR 0    /* GaussTaylorKeyPointDecoder.__call__                  */
+#define SP_DECODE_ARGMAX       1    /* BasicKeyPointDecoder.heat_map_to_axis (no affine)    */
+#define SP_DECODE_BASIC        2    /* BasicKeyPointDecoder.__call__ (quarter-pixel shift)  */
+
+/* flags of sp_mse_fwd_bwd_f32 */
+#define SP_MSE_SKIP_MASKED 1        /* do not read pred/target of joints whose mask is 0    */
+
+int sp_abi_version(void);
+const char* sp_error_string(int code);
+/* SM count and compute capability of the current device (host-side query). */
+int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  RefineSimpleTransform.get_heat_map(joints, sigma=2.0, shape=(48, 64))
+ *     commons/transforms.py:167-191, batched as MSCOCO.collate_fn does (datasets/coco.py:138-146).
+ *
+ * joints  [B,K,3] f32  (x, y, vis) in heatmap pixels
+ * targets [B,K,H,W] f32 out; weights [B,K] f32 out
+ * A joint is culled (weight 0, zero map) when int(x-3s) >= W or int(y-3s) >= H or
+ * int(x+3s+1) < 0 or int(y+3s+1) < 0 (float32 arithmetic, truncation toward zero); a kept
+ * joint with vis > 0.5 gets exp(-((px-x)^2+(py-y)^2)/(2 s^2)) over the whole map, evaluated
+ * in float64 and rounded once to float32; otherwise a zero map. `sigma` is a double because
+ * the reference uses a Python float.
+ */
+int sp_encode_f32(const float* joints, float* targets, float* weights,
+                  int B, int K, int H, int W, double sigma, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2  0.5 * nn.MSELoss()(pred.mul(mask[..., None, None]), target.mul(mask[..., None, None]))
+ *     and its backward; processors/dp_pose_hrnet_solver.py:86,106-107 (same expression in
+ *     dp_pose_resnet_solver.py:107 and ddp_pose_resnet_solver.py:117).
+ *
+ * pred, target [B,K,HW] f32; mask [B,K] f32; grad [B,K,HW] f32 out (NULL = forward only);
+ * loss: 1 f32 out = 0.5/(B*K*HW) * sum((m*p - m*t)^2);
+ * grad = grad_scale * m * (m*p - m*t) / (B*K*HW)   (d loss / d pred).
+ * One pass over pred/target; deterministic two-stage reduction in float64.
+ * workspace: sp_mse_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED ONCE by the caller
+ * before first use (the kernel restores the zero state before it finishes, so the same
+ * buffer can be reused by later calls on the same stream without re-zeroing).
+ */
+size_t sp_mse_workspace_bytes(void);
+int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const float* mask,
+                       float* grad, float* loss, void* workspace, size_t workspace_bytes,
+                       int B, int K, int HW, float grad_scale, int flags, void* stream);
+
+/* grad[i] *= *scale_dev, skipped entirely (no memory traffic) when *scale_dev == 1.0f.
+ * Used by the autograd wrapper when the upstream gradient is not 1 (e.g. GradScaler). */
+int sp_scale_inplace_f32(float* data, long long n, const float* scale_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A3/A4/A5/A6  decoders of metrics/pose_metrics.py.
+ *   mode SP_DECODE_GAUSS_TAYLOR: GaussTaylorKeyPointDecoder.__call__ (:62-107)
+ *   mode SP_DECODE_ARGMAX:       BasicKeyPointDecoder.heat_map_to_axis (:11-24); trans_inv unused
+ *   mode SP_DECODE_BASIC:        BasicKeyPointDecoder.__call__ (:26-52)
+ *
+ * hm        [B,K,H,W] f32 (not modified)
+ * hm_flip   NULL, or [B,K,H,W] f32: the network output for the horizontally mirrored image.
+ *           Then the decoded map is 0.5*(hm[b,k,y,x] + hm_flip[b,perm[k],y,W-1-x]) -- the
+ *           flip-test average composed from flip_joints (commons/joint_utils.py:102-112) and
+ *           joint_pairs (datasets/coco.py:26); perm [K] i32 is required in that case.
+ * trans_inv [B,2,3] f32 (NULL = identity, i.e. heatmap-space output)
+ * blur_w    [ksize*ksize] f32 = float32(k k^T), k = cv.getGaussianKernel(ksize, 0)
+ *           (:57-60); only read in GAUSS_TAYLOR mode; ksize odd, 3 <= ksize <= 15
+ * coords    [B,K,2] f32 out (x, y); maxval [B,K] f32 out (un-blurred peak value)
+ * argmax    NULL or [B,K] i32 out: flat index of the peak (first maximal index, NaN wins)
+ */
+int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
+                  const float* trans_inv, const float* blur_w,
+                  float* coords, float* maxval, int* argmax,
+                  int B, int K, int H, int W, int ksize, int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A7  oks_iou(pick_kps, candi_kps, pick_area, candi_area, sigmas=None, in_vis_thresh=None)
+ *     datasets/naive_data.py:120-150.  All float64.
+ * pick_kps [K,3]; cand_kps [n,K,3]; pick_area: 1 f64 (device); cand_area [n]; sigmas [K]
+ * (NULL = COCO 17-joint table, requires K == 17); use_vis_thresh 0 -> in_vis_thresh=None.
+ */
+int sp_oks_iou_f64(const double* pick_kps, const double* cand_kps, const double* pick_area,
+                   const double* cand_area, const double* sigmas, double* out,
+                   int n, int K, int use_vis_thresh, double vis_thresh, void* stream);
+
+/* A8  oks_nms(kps, scores, areas, thresh, sigmas=None, in_vis_thresh=None)
+ *     datasets/naive_data.py:153-173, segmented: one independent greedy NMS per image.
+ * kps [N,K,3] f64; scores [N]; areas [N]; seg [I+1] i32 offsets (seg[0]=0, seg[I]=N);
+ * keep [N] u8 out (1 = kept); rank [N] i32 out: position of each person in its image's
+ * descending-score visiting order (ties: higher index first, as argsort()[::-1] of a stable
+ * sort) so that the reference's pick-order list can be rebuilt without sorting again.
+ * max_seg >= the largest seg[i+1]-seg[i] (sizes the per-image scratch in shared memory;
+ * the caller builds seg on the host and knows it). Scores must not be NaN.
+ */
+int sp_oks_nms_f64(const double* kps, const double* scores, const double* areas, const int* seg,
+                   const double* sigmas, unsigned char* keep, int* rank,
+                   int N, int I, int K, int max_seg, double thresh,
+                   int use_vis_thresh, double vis_thresh, void* stream);
+
+/* A9  rescoring of eval.py:168-175: scores[i] = box_scores[i] * mean(conf[conf > thr]) (0 if none). */
+int sp_rescore_f64(const double* kps, const double* box_scores, double* scores,
+                   int N, int K, double in_vis_thre, void* stream);
+
+/* Packs decoder output for the NMS stage without a host round trip: out_kps[n,k,:] =
+ * (coords[n,k,0], coords[n,k,1], maxval[n,k]) widened to float64 (the JSON round trip of
+ * eval.py:138-160 yields exactly these doubles). */
+int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps,
+                    int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLE_POSE_B200_H */

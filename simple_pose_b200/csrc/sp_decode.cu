@@ -1,0 +1,495 @@
+// A3/A4/A5/A6: heatmap decoders of the reference's metrics/pose_metrics.py, one fused kernel.
+//
+//   GAUSS_TAYLOR  GaussTaylorKeyPointDecoder.__call__ (:62-107): argmax on the raw map, 11x11
+//                 Gaussian blur, rescale by ori_max/blur_max, clamp 1e-10, log, second-order
+//                 Taylor step at the peak, clamp(min=0), affine back-projection.
+//   ARGMAX        BasicKeyPointDecoder.heat_map_to_axis (:11-24).
+//   BASIC         BasicKeyPointDecoder.__call__ (:26-52): quarter-pixel shift toward the larger
+//                 neighbour.
+//   flip-test     optional second input: the decoded map is 0.5*(hm + mirror/swap(hm_flip)).
+//
+// HBM-bound: K*H*W*4 bytes read per person (twice that with the flip input), 12 bytes written
+// per joint. Design (persistent, one CTA per SM):
+//   * every warp owns a private ring of shared-memory stages and streams whole (person, joint)
+//     maps into it with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); lane 0
+//     re-arms the stage for the warp's next map as soon as the warp is done with it, so the
+//     copy of map i+1 overlaps the arithmetic on map i and a full SM keeps ~100-200 KB in flight;
+//   * argmax: one 16-byte shared load per lane per step, per-quad NaN-propagating max, a
+//     (value, quad) warp butterfly with torch.max tie rules (first index wins), and an exact
+//     scalar rescan only if a NaN/Inf was seen;
+//   * the blur is NOT applied to the whole map. The Taylor step reads the log-blurred map at 13
+//     stencil points only, so the 11x11 window is evaluated at those 13 points from a
+//     zero-padded 15x15 patch (1573 FMAs per joint instead of 371 712). The reference's
+//     ori_max/blur_max factor multiplies every stencil value by the same constant, which
+//     cancels in every finite difference of the logs, *provided the 1e-10 clamp does not fire*.
+//     Since blur_max <= ori_max * sum(w) up to float32 rounding the factor is >= 1 - 1e-5, so when all 13 blurred
+//     values are >= 2e-10 the clamp provably cannot fire and the factor is dropped; if they are
+//     all <= 0 every stencil value is clamped to the same constant and the Hessian test
+//     (det != 0) rejects the joint, as in the reference; the remaining (mixed) case takes an
+//     exact slow path that blurs the whole map of that joint to obtain blur_max;
+//   * no tensor cores: nothing here is a dense contraction.
+#include "sp_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int kMaxKsize = 15;
+constexpr int kStencil = 13;
+constexpr int kPatchMax = kMaxKsize + 4;               // 19
+constexpr int kPatchFloats = kPatchMax * kPatchMax;    // 361
+
+struct DecodeArgs {
+    const float* hm;
+    const float* hm_flip;
+    const int* perm;
+    const float* trans_inv;
+    const float* blur_w;
+    float* coords;
+    float* maxval;
+    int* argmax;
+    int nmaps, K, H, W, ksize, mode;
+};
+
+// 13 stencil points (dy, dx): centre, x+-1, y+-1, x+-2, y+-2, four diagonals.
+#define SP_STENCIL_DY {0, 0, 0, 1, -1, 0, 0, 2, -2, 1, -1, 1, -1}
+#define SP_STENCIL_DX {0, 1, -1, 0, 0, 2, -2, 0, 0, 1, 1, -1, -1}
+enum { S_C = 0, S_XP1, S_XM1, S_YP1, S_YM1, S_XP2, S_XM2, S_YP2, S_YM2, S_PP, S_MP, S_PM, S_MM };
+// S_PP = (y+1,x+1), S_MP = (y-1,x+1), S_PM = (y+1,x-1), S_MM = (y-1,x-1)
+
+struct Peak {
+    float value;
+    int index;
+};
+
+// ---------------------------------------------------------------------------------------------
+// argmax of a map that is resident in shared (fast path) or global (generic path) memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Peak warp_best(float v, int i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(SP_FULL, v, o);
+        const int oi = __shfl_xor_sync(SP_FULL, i, o);
+        if (sp::better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+    Peak p;
+    p.value = v;
+    p.index = i;
+    return p;
+}
+
+// exact scalar scan (torch.max semantics incl. NaN); used by the generic path and as the
+// fallback of the vector scan
+template <typename View>
+__device__ __forceinline__ Peak argmax_exact(const View& map, int hw, int lane) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < hw; i += 32) {
+        const float v = map.at(i);
+        if (sp::better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    return warp_best(bv, bi);
+}
+
+struct DirectView {
+    const float* p;
+    __device__ __forceinline__ float at(int i) const { return p[i]; }
+};
+
+// 0.5*(a[y,x] + b[y,W-1-x]) evaluated on the fly (generic path of the flip test)
+struct FlipAvgView {
+    const float* a;
+    const float* b;
+    int W;
+    __device__ __forceinline__ float at(int i) const {
+        const int y = i / W, x = i - y * W;
+        return __fmul_rn(0.5f, __fadd_rn(a[i], b[y * W + (W - 1 - x)]));
+    }
+};
+
+// Vector scan over a shared-memory map (hw % 4 == 0). If FLIP, first folds the mirrored partner
+// map into `a` in place (W % 4 == 0 so the mirror of an aligned quad is an aligned quad).
+template <bool FLIP>
+__device__ __forceinline__ Peak argmax_smem(float* a, const float* b, int hw, int W, int lane) {
+    const int nq = hw >> 2;
+    float best = -CUDART_INF_F;
+    int bq = 0x3fffffff;
+    float poison = 0.f;                 // becomes NaN if any quad max is NaN or +-Inf
+    float4* a4 = reinterpret_cast<float4*>(a);
+    const int qpr = W >> 2;
+    int y = 0, xq = 0, step_y = 0, step_x = 0;
+    if (FLIP) {
+        y = lane / qpr;
+        xq = lane - y * qpr;
+        step_y = 32 / qpr;
+        step_x = 32 - step_y * qpr;
+    }
+#pragma unroll 4
+    for (int q = lane; q < nq; q += 32) {
+        float4 v = a4[q];
+        if (FLIP) {
+            const float4 m = *reinterpret_cast<const float4*>(b + y * W + (W - 4 - 4 * xq));
+            v.x = __fmul_rn(0.5f, __fadd_rn(v.x, m.w));
+            v.y = __fmul_rn(0.5f, __fadd_rn(v.y, m.z));
+            v.z = __fmul_rn(0.5f, __fadd_rn(v.z, m.y));
+            v.w = __fmul_rn(0.5f, __fadd_rn(v.w, m.x));
+            a4[q] = v;
+            xq += step_x;
+            y += step_y;
+            if (xq >= qpr) { xq -= qpr; ++y; }
+        }
+        const float m4 = sp::fmax_nan(sp::fmax_nan(v.x, v.y), sp::fmax_nan(v.z, v.w));
+        poison = fmaf(m4, 0.f, poison);
+        if (m4 > best) { best = m4; bq = q; }
+    }
+    if (FLIP) __syncwarp();             // folded values visible to the whole warp
+    const bool weird = __any_sync(SP_FULL, poison != poison);
+    if (weird) {
+        DirectView view{a};
+        return argmax_exact(view, hw, lane);
+    }
+    // (value, quad) butterfly: larger value, then smaller quad index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(SP_FULL, best, o);
+        const int oq = __shfl_xor_sync(SP_FULL, bq, o);
+        if (ov > best || (ov == best && oq < bq)) { best = ov; bq = oq; }
+    }
+    const float4 w = a4[bq];            // broadcast read; first lane of the quad equal to the max
+    const int sub = (w.x == best) ? 0 : (w.y == best) ? 1 : (w.z == best) ? 2 : 3;
+    Peak p;
+    p.value = (sub == 0) ? w.x : (sub == 1) ? w.y : (sub == 2) ? w.z : w.w;   // keeps the sign of a zero
+    p.index = 4 * bq + sub;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Taylor refinement around an interior peak. All lanes return the same values.
+// ---------------------------------------------------------------------------------------------
+template <typename View>
+__device__ float full_blur_max(const View& map, const float* w, int H, int W, int ks, int lane) {
+    // exact slow path: max over the whole zero-padded blurred map of this joint
+    const int r = ks >> 1;
+    float best = -CUDART_INF_F;
+    bool seen_nan = false;
+    for (int i = lane; i < H * W; i += 32) {
+        const int y = i / W, x = i - y * W;
+        float acc = 0.f;
+        for (int ty = 0; ty < ks; ++ty) {
+            const int yy = y + ty - r;
+            if (yy < 0 || yy >= H) continue;
+            for (int tx = 0; tx < ks; ++tx) {
+                const int xx = x + tx - r;
+                if (xx < 0 || xx >= W) continue;
+                acc = fmaf(w[ty * ks + tx], map.at(yy * W + xx), acc);
+            }
+        }
+        if (acc != acc) seen_nan = true;
+        best = fmaxf(best, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(SP_FULL, best, o));
+    if (__any_sync(SP_FULL, seen_nan)) best = CUDART_NAN_F;   // torch.max propagates NaN
+    return best;
+}
+
+template <typename View>
+__device__ __forceinline__ void taylor_refine(const View& map, const float* wts, float* patch, int H, int W,
+                                              int ks, int px, int py, float ori_max, int lane, float& ox, float& oy,
+                                              bool& refined) {
+    const int r = ks >> 1;
+    const int P = ks + 4;               // patch side: blur radius + stencil radius 2 on each side
+    const int pr = r + 2;
+    // zero-padded patch of the raw map around the peak
+    __syncwarp();
+    for (int e = lane; e < P * P; e += 32) {
+        const int ry = e / P, rx = e - ry * P;
+        const int yy = py + ry - pr, xx = px + rx - pr;
+        patch[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? map.at(yy * W + xx) : 0.f;
+    }
+    __syncwarp();
+    // blur at the 13 stencil points: taps are split across lanes, then butterfly sums
+    constexpr int kStencilDy[kStencil] = SP_STENCIL_DY;
+    constexpr int kStencilDx[kStencil] = SP_STENCIL_DX;
+    float acc[kStencil];
+#pragma unroll
+    for (int s = 0; s < kStencil; ++s) acc[s] = 0.f;
+    for (int t = lane; t < ks * ks; t += 32) {
+        const int ty = t / ks, tx = t - ty * ks;
+        const float wv = wts[t];
+        const float* base = patch + (ty + 2) * P + (tx + 2);
+#pragma unroll
+        for (int s = 0; s < kStencil; ++s) acc[s] = fmaf(wv, base[kStencilDy[s] * P + kStencilDx[s]], acc[s]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int s = 0; s < kStencil; ++s) acc[s] += __shfl_xor_sync(SP_FULL, acc[s], o);
+    }
+    float lo = acc[0], hi = acc[0];
+#pragma unroll
+    for (int s = 1; s < kStencil; ++s) { lo = fminf(lo, acc[s]); hi = fmaxf(hi, acc[s]); }
+    bool any_nan = false;
+#pragma unroll
+    for (int s = 0; s < kStencil; ++s) any_nan |= (acc[s] != acc[s]);
+
+    float L[kStencil];
+    if (!any_nan && lo >= 2e-10f) {
+        // clamp cannot fire (scale >= 1 - 1e-5): the common factor cancels in the differences
+#pragma unroll
+        for (int s = 0; s < kStencil; ++s) L[s] = logf(acc[s]);
+    } else if (!any_nan && hi <= 0.f && ori_max > 0.f) {
+        // blur_max > 0 would be needed for a positive scale; with every stencil value <= 0 and a
+        // positive scale all 13 logs equal log(1e-10) -> det == 0 -> not refined. A non-positive
+        // blur_max flips signs, so that sub-case still goes through the exact path below.
+        const float bmax = full_blur_max(map, wts, H, W, ks, lane);
+        if (bmax > 0.f) { refined = false; return; }
+#pragma unroll
+        for (int s = 0; s < kStencil; ++s) L[s] = logf(fmaxf(__fdiv_rn(__fmul_rn(acc[s], ori_max), bmax), 1e-10f));
+    } else {
+        const float bmax = full_blur_max(map, wts, H, W, ks, lane);
+#pragma unroll
+        for (int s = 0; s < kStencil; ++s) {
+            const float v = __fdiv_rn(__fmul_rn(acc[s], ori_max), bmax);
+            // torch.clamp(min=) keeps NaN
+            L[s] = logf((v != v) ? v : fmaxf(v, 1e-10f));
+        }
+    }
+    // finite differences, same operation order as pose_metrics.py:80-93
+    const float dx = __fmul_rn(0.5f, __fsub_rn(L[S_XP1], L[S_XM1]));
+    const float dy = __fmul_rn(0.5f, __fsub_rn(L[S_YP1], L[S_YM1]));
+    const float c2 = __fmul_rn(2.f, L[S_C]);
+    const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_XP2], c2), L[S_XM2]));
+    const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_YP2], c2), L[S_YM2]));
+    const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(L[S_PP], L[S_MP]), L[S_PM]), L[S_MM]));
+    const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
+    if (!(det != 0.f)) { refined = false; return; }     // det == 0 -> skip; NaN != 0 is true, as in torch
+    // offset = -H^-1 g, H = [[dxx, dxy], [dxy, dyy]]
+    const float inv = __fdiv_rn(1.f, det);
+    ox = -__fmul_rn(__fsub_rn(__fmul_rn(dyy, dx), __fmul_rn(dxy, dy)), inv);
+    oy = -__fmul_rn(__fsub_rn(__fmul_rn(dxx, dy), __fmul_rn(dxy, dx)), inv);
+    refined = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// everything after the argmax: coordinates, refinement, affine, stores
+// ---------------------------------------------------------------------------------------------
+template <typename View>
+__device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map, const float* wts, float* patch,
+                                           int m, Peak pk, int lane) {
+    const int W = A.W, H = A.H;
+    const bool positive = pk.value > 0.f;                 // false for NaN, like (max_val > 0.)
+    const int ix = positive ? pk.index % W : 0;
+    const int iy = positive ? pk.index / W : 0;
+    float x = (float)ix, y = (float)iy;
+
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR) {
+        const bool inner = (ix > 1) && (ix < W - 2) && (iy > 1) && (iy < H - 2);
+        if (inner) {
+            float ox = 0.f, oy = 0.f;
+            bool refined = false;
+            taylor_refine(map, wts, patch, H, W, A.ksize, ix, iy, pk.value, lane, ox, oy, refined);
+            if (refined) {
+                const float nx = __fadd_rn(x, ox), ny = __fadd_rn(y, oy);
+                x = (nx < 0.f) ? 0.f : nx;                // clamp(min=0) that keeps NaN
+                y = (ny < 0.f) ? 0.f : ny;
+            }
+        }
+    } else if (A.mode == SP_DECODE_BASIC) {
+        const bool inner = (ix > 1) && (ix < W - 1) && (iy > 1) && (iy < H - 1);
+        if (inner) {
+            const float ddx = __fsub_rn(map.at(iy * W + ix + 1), map.at(iy * W + ix - 1));
+            const float ddy = __fsub_rn(map.at((iy + 1) * W + ix), map.at((iy - 1) * W + ix));
+            const float sx = (ddx > 0.f) ? 1.f : (ddx < 0.f) ? -1.f : ddx;   // torch.sign (NaN stays NaN)
+            const float sy = (ddy > 0.f) ? 1.f : (ddy < 0.f) ? -1.f : ddy;
+            x = __fadd_rn(x, __fmul_rn(sx, 0.25f));
+            y = __fadd_rn(y, __fmul_rn(sy, 0.25f));
+        }
+    }
+    if (lane == 0) {
+        float outx = x, outy = y;
+        if (A.mode != SP_DECODE_ARGMAX && A.trans_inv != nullptr) {
+            const float* T = A.trans_inv + 6 * (size_t)(m / A.K);
+            outx = __fadd_rn(fmaf(y, __ldg(T + 1), __fmul_rn(x, __ldg(T + 0))), __ldg(T + 2));
+            outy = __fadd_rn(fmaf(y, __ldg(T + 4), __fmul_rn(x, __ldg(T + 3))), __ldg(T + 5));
+        }
+        reinterpret_cast<float2*>(A.coords)[m] = make_float2(outx, outy);
+        A.maxval[m] = pk.value;
+        if (A.argmax) A.argmax[m] = pk.index;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast path: persistent CTAs, per-warp TMA rings
+// ---------------------------------------------------------------------------------------------
+// dynamic shared memory layout:
+//   [0, 1024)                      mbarriers (nwarps * stages * 8 B)
+//   [1024, 1024 + 1024)            blur weights (<= 225 floats)
+//   then per warp                  patch (kPatchFloats floats, padded to 1536 B)
+//   then per warp, per stage       map a (hw floats) [+ map b if FLIP]
+constexpr int kBarBytes = 1024;
+constexpr int kWtsBytes = 1024;
+constexpr int kPatchBytes = 1536;
+
+template <bool FLIP>
+__global__ void __launch_bounds__(512, 1)
+decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = A.H * A.W;
+    const uint32_t map_bytes = (uint32_t)hw * 4u;
+    const uint32_t stage_bytes = FLIP ? 2u * map_bytes : map_bytes;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * stages;
+    float* wts = reinterpret_cast<float*>(smem + kBarBytes);
+    float* patch = reinterpret_cast<float*>(smem + kBarBytes + kWtsBytes + (size_t)warp * kPatchBytes);
+    unsigned char* ring = smem + kBarBytes + kWtsBytes + (size_t)nwarps * kPatchBytes +
+                          (size_t)warp * stages * stage_bytes;
+
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) sp::mbar_init(bars + s, 1);
+        sp::mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int gw = blockIdx.x * nwarps + warp;
+    const int total = gridDim.x * nwarps;
+
+    auto issue = [&](int s, int m) {
+        float* dst = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
+        sp::mbar_expect_tx(bars + s, stage_bytes);
+        sp::bulk_g2s(dst, A.hm + (size_t)m * hw, map_bytes, bars + s);
+        if (FLIP) {
+            const int b = m / A.K, k = m - b * A.K;
+            const int src = b * A.K + __ldg(A.perm + k);
+            sp::bulk_g2s(dst + hw, A.hm_flip + (size_t)src * hw, map_bytes, bars + s);
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const int m = gw + s * total;
+            if (m < A.nmaps) issue(s, m);
+        }
+    }
+    int it = 0;
+    for (int m = gw; m < A.nmaps; m += total, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (uint32_t)(it / stages) & 1u;
+        sp::mbar_wait(bars + s, parity);
+        float* a = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
+        const Peak pk = argmax_smem<FLIP>(a, a + hw, hw, A.W, lane);
+        DirectView view{a};
+        finish_map(A, view, wts, patch, m, pk, lane);
+        __syncwarp();
+        const int next = m + stages * total;
+        if (lane == 0 && next < A.nmaps) {
+            sp::fence_proxy_async_smem();
+            issue(s, next);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic path: any H, W; reads straight from global memory (L1/L2 serve the re-reads)
+// ---------------------------------------------------------------------------------------------
+template <bool FLIP>
+__global__ void __launch_bounds__(256)
+decode_generic_kernel(const DecodeArgs A) {
+    __shared__ float wts[kMaxKsize * kMaxKsize];
+    __shared__ float patches[8][kPatchFloats];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = A.H * A.W;
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    __syncthreads();
+    const int total = gridDim.x * 8;
+    for (int m = blockIdx.x * 8 + warp; m < A.nmaps; m += total) {
+        if (FLIP) {
+            const int b = m / A.K, k = m - b * A.K;
+            FlipAvgView view{A.hm + (size_t)m * hw, A.hm_flip + (size_t)(b * A.K + __ldg(A.perm + k)) * hw, A.W};
+            const Peak pk = argmax_exact(view, hw, lane);
+            finish_map(A, view, wts, patches[warp], m, pk, lane);
+        } else {
+            DirectView view{A.hm + (size_t)m * hw};
+            const Peak pk = argmax_exact(view, hw, lane);
+            finish_map(A, view, wts, patches[warp], m, pk, lane);
+        }
+    }
+}
+
+int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    if (!v || !*v) return fallback;
+    return atoi(v);
+}
+
+}  // namespace
+
+extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
+                             const float* trans_inv, const float* blur_w,
+                             float* coords, float* maxval, int* argmax,
+                             int B, int K, int H, int W, int ksize, int mode, void* stream) {
+    SP_RETURN_IF(!hm || !coords || !maxval, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_BASIC, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(hm_flip && !perm, SP_ERR_BAD_ARGUMENT);
+    if (mode == SP_DECODE_GAUSS_TAYLOR) {
+        SP_RETURN_IF(!blur_w, SP_ERR_BAD_ARGUMENT);
+        SP_RETURN_IF(ksize < 3 || ksize > kMaxKsize || (ksize & 1) == 0, SP_ERR_UNSUPPORTED);
+    } else {
+        ksize = 0;
+    }
+    SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
+    SP_RETURN_IF(!sp_aligned16(coords), SP_ERR_BAD_ALIGNMENT);
+    if (B == 0) return 0;
+
+    DecodeArgs A;
+    A.hm = hm; A.hm_flip = hm_flip; A.perm = perm; A.trans_inv = trans_inv; A.blur_w = blur_w;
+    A.coords = coords; A.maxval = maxval; A.argmax = argmax;
+    A.nmaps = B * K; A.K = K; A.H = H; A.W = W; A.ksize = ksize; A.mode = mode;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool flip = hm_flip != nullptr;
+
+    // fast path needs 16-byte bulk copies and row-aligned quads
+    const size_t map_bytes = (size_t)H * W * 4;
+    const size_t stage_bytes = flip ? 2 * map_bytes : map_bytes;
+    const size_t budget = 227 * 1024 - kBarBytes - kWtsBytes;
+    bool fast = (W % 4 == 0) && sp_aligned16(hm) && (!flip || sp_aligned16(hm_flip)) &&
+                (stage_bytes + kPatchBytes <= budget) && !env_int("SP_DECODE_FORCE_GENERIC", 0);
+    if (fast) {
+        // as many warps as fit (<= 16), then as many stages per warp as still fit (<= 4)
+        int nwarps = (int)(budget / (stage_bytes + kPatchBytes));
+        if (nwarps > 16) nwarps = 16;
+        nwarps = env_int("SP_DECODE_WARPS", nwarps);
+        if (nwarps < 1) nwarps = 1;
+        if (nwarps > 16) nwarps = 16;
+        int stages = (int)((budget / nwarps - kPatchBytes) / stage_bytes);
+        if (stages > 4) stages = 4;
+        stages = env_int("SP_DECODE_STAGES", stages);
+        if (stages < 1) stages = 1;
+        while ((size_t)nwarps * (stages * stage_bytes + kPatchBytes) > budget && stages > 1) --stages;
+        while ((size_t)nwarps * (stages * stage_bytes + kPatchBytes) > budget && nwarps > 1) --nwarps;
+        const size_t smem = kBarBytes + kWtsBytes + (size_t)nwarps * (kPatchBytes + stages * stage_bytes);
+        int grid = sp_sm_count();
+        const int need = (A.nmaps + nwarps - 1) / nwarps;
+        if (grid > need) grid = need;
+        if (flip) {
+            SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_tma_kernel<true><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);
+        } else {
+            SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_tma_kernel<false><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);
+        }
+        return sp_launch_status();
+    }
+    int grid = sp_sm_count() * 8;
+    const int need = (A.nmaps + 7) / 8;
+    if (grid > need) grid = need;
+    if (flip) decode_generic_kernel<true><<<grid, 256, 0, st>>>(A);
+    else      decode_generic_kernel<false><<<grid, 256, 0, st>>>(A);
+    return sp_launch_status();
+}

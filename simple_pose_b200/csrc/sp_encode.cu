@@ -1,0 +1,144 @@
+// A1: DarkPose-style unbiased Gaussian target encoder (reference commons/transforms.py:167-191).
+//
+// Store-bound: K*H*W*4 bytes written per person, 12 bytes read per joint. One warp owns one
+// (person, joint) map: the lanes evaluate the W + H separable factors exp(-dx^2/(2 s^2)) and
+// exp(-dy^2/(2 s^2)) in float64 (the reference computes in float64 and rounds once to float32,
+// so the product is formed in float64 too and converted with a single cvt.rn.f32.f64), park
+// them in a private slice of shared memory, then stream the map out with coalesced 16-byte
+// stores (32 lanes x float4 = 512 contiguous bytes per instruction). No block-level barrier.
+// Denormal results are kept (no -ftz / fast-math), as in the reference.
+#include "sp_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+struct JointVerdict {
+    float weight;   // value written to weights[b,k]
+    bool draw;      // whether a Gaussian is rendered (else the map is zero)
+};
+
+// Cull test of transforms.py:180-185. NumPy 2 keeps float32 for float32-scalar (+,-) Python
+// scalar, so the bounds are float32 sums truncated toward zero by int().
+__device__ __forceinline__ JointVerdict judge_joint(float mx, float my, float vis, float reach, int H, int W) {
+    const int lo_x = (int)__fsub_rn(mx, reach);
+    const int lo_y = (int)__fsub_rn(my, reach);
+    const int hi_x = (int)__fadd_rn(__fadd_rn(mx, reach), 1.0f);
+    const int hi_y = (int)__fadd_rn(__fadd_rn(my, reach), 1.0f);
+    JointVerdict v;
+    if (lo_x >= W || lo_y >= H || hi_x < 0 || hi_y < 0) {
+        v.weight = 0.0f;
+        v.draw = false;
+    } else {
+        v.weight = vis;
+        v.draw = vis > 0.5f;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double gauss_factor(int p, float mu, double denom) {
+    const double d = (double)p - (double)mu;
+    return exp(__ddiv_rn(-__dmul_rn(d, d), denom));
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)
+encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targets, float* __restrict__ weights,
+                     int nmaps, int H, int W, float reach, double denom) {
+    extern __shared__ __align__(16) double factors[];   // per warp: ex[Wpad] then ey[H]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpad = (W + 1) & ~1;                        // keeps ey 16-byte aligned
+    double* ex = factors + (size_t)warp * (wpad + H);
+    double* ey = ex + wpad;
+    const int hw = H * W;
+    const int total_warps = gridDim.x * kWarpsPerCta;
+
+    for (int m = blockIdx.x * kWarpsPerCta + warp; m < nmaps; m += total_warps) {
+        const float mx = __ldg(joints + 3 * (size_t)m + 0);
+        const float my = __ldg(joints + 3 * (size_t)m + 1);
+        const float vis = __ldg(joints + 3 * (size_t)m + 2);
+        const JointVerdict jv = judge_joint(mx, my, vis, reach, H, W);
+        if (lane == 0) weights[m] = jv.weight;
+        float* out = targets + (size_t)m * hw;
+
+        if (!jv.draw) {
+            if (VEC4) {
+                float4* o4 = reinterpret_cast<float4*>(out);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = lane; q < (hw >> 2); q += 32) o4[q] = z;
+            } else {
+                for (int i = lane; i < hw; i += 32) out[i] = 0.f;
+            }
+            continue;
+        }
+
+        __syncwarp();   // previous map's readers are done with ex/ey
+        for (int i = lane; i < W + H; i += 32) {
+            if (i < W) ex[i] = gauss_factor(i, mx, denom);
+            else       ey[i - W] = gauss_factor(i - W, my, denom);
+        }
+        __syncwarp();
+
+        if (VEC4) {
+            // W % 4 == 0: a quad never straddles rows. Track (row, quad-in-row) incrementally.
+            const int qpr = W >> 2;
+            const int nq = hw >> 2;
+            int y = lane / qpr;
+            int xq = lane - y * qpr;
+            const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
+            float4* o4 = reinterpret_cast<float4*>(out);
+            for (int q = lane; q < nq; q += 32) {
+                const double2 a = *reinterpret_cast<const double2*>(ex + 4 * xq);
+                const double2 b = *reinterpret_cast<const double2*>(ex + 4 * xq + 2);
+                const double fy = ey[y];
+                float4 v;
+                v.x = __double2float_rn(__dmul_rn(a.x, fy));
+                v.y = __double2float_rn(__dmul_rn(a.y, fy));
+                v.z = __double2float_rn(__dmul_rn(b.x, fy));
+                v.w = __double2float_rn(__dmul_rn(b.y, fy));
+                o4[q] = v;
+                xq += step_x;
+                y += step_y;
+                if (xq >= qpr) { xq -= qpr; ++y; }
+            }
+        } else {
+            for (int i = lane; i < hw; i += 32) {
+                const int y = i / W, x = i - y * W;
+                out[i] = __double2float_rn(__dmul_rn(ex[x], ey[y]));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights,
+                             int B, int K, int H, int W, double sigma, void* stream) {
+    SP_RETURN_IF(!joints || !targets || !weights, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
+    if (B == 0) return 0;
+    const int nmaps = B * K;
+    const double reach_d = sigma * 3.0;            // tmp_size = sigma * 3 (Python float)
+    const float reach = (float)reach_d;            // weak Python scalar -> float32 in the cull test
+    const double denom = 2.0 * (sigma * sigma);    // 2 * sigma ** 2
+    const int wpad = (W + 1) & ~1;
+    const size_t smem = (size_t)kWarpsPerCta * (wpad + H) * sizeof(double);
+    SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
+    const bool vec4 = (W % 4 == 0) && sp_aligned16(targets);
+    const int ctas_needed = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int max_ctas = sp_sm_count() * 8;        // 8 resident CTAs of 8 warps per SM
+    const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec4) {
+        if (smem > 48 * 1024)
+            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_refine_kernel<true><<<grid, kWarpsPerCta * SP_WARP, smem, st>>>(joints, targets, weights, nmaps, H, W, reach, denom);
+    } else {
+        if (smem > 48 * 1024)
+            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_refine_kernel<false><<<grid, kWarpsPerCta * SP_WARP, smem, st>>>(joints, targets, weights, nmaps, H, W, reach, denom);
+    }
+    return sp_launch_status();
+}

@@ -1,0 +1,229 @@
+// A7/A8/A9: OKS similarity, greedy keypoint NMS per image, eval rescoring
+// (reference datasets/naive_data.py:120-173 and eval.py:153-197). All float64.
+//
+// Latency-bound, not bandwidth-bound (408 B per person). One CTA owns one image (segment):
+// persons are ranked by descending score with a counting rank (stable; ties -> higher index
+// first, i.e. argsort()[::-1] of a stable sort), then the greedy loop visits them in that
+// order; for each surviving pick the remaining candidates are scored in parallel, one thread
+// per candidate. The per-pair arithmetic keeps the reference's operation order, including
+// NumPy's 8-accumulator pairwise summation, so that the `oks > thresh` decisions agree.
+#include "sp_common.cuh"
+
+namespace {
+
+constexpr int kNmsThreads = 128;
+constexpr int kMaxJoints = 64;
+
+__device__ __constant__ double kCocoSigmas[17] = {.26, .25, .25, .35, .35, .79, .79, .72, .72,
+                                                  .62, .62, 1.07, 1.07, .87, .87, .89, .89};
+
+// NumPy's pairwise sum for n <= 128 fed one value at a time (numpy/core/src/umath/loops_utils:
+// 8 running accumulators, tree-combined, then the n % 8 tail added in order; for n < 8 a plain
+// running sum). The reduction starts from the identity: result = 0 + pairwise(values).
+struct NumpySum {
+    double r[8];
+    double tail;
+    int n_main, seen, n;
+    __device__ void begin(int count) {
+        n = count;
+        n_main = (count < 8) ? 0 : count - (count % 8);
+        seen = 0;
+        tail = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0.0;
+    }
+    __device__ void push(double v) {
+        if (seen < n_main) {
+            const int j = seen & 7;
+            // first round initialises the accumulator (r[j] = a[j]), later rounds add
+            double cur = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q == j) cur = r[q];
+            cur = (seen < 8) ? v : __dadd_rn(cur, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q == j) r[q] = cur;
+            if (seen + 1 == n_main)
+                tail = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                 __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        } else {
+            tail = __dadd_rn(tail, v);
+        }
+        ++seen;
+    }
+    __device__ double result() const { return __dadd_rn(0.0, tail); }
+};
+
+struct OksParams {
+    const double* sigmas;    // NULL -> COCO table
+    int K;
+    int use_vis;
+    double vis_thresh;
+};
+
+__device__ __forceinline__ double joint_var(const OksParams& P, int k) {
+    const double s = P.sigmas ? P.sigmas[k] : __ddiv_rn(kCocoSigmas[k], 10.0);
+    const double t = __dmul_rn(s, 2.0);
+    return __dmul_rn(t, t);
+}
+
+// oks_iou for one (pick, candidate) pair, naive_data.py:139-149
+__device__ double oks_pair(const OksParams& P, const double* __restrict__ pick, const double* __restrict__ cand,
+                           double pick_area, double cand_area) {
+    const double denom_area = __dadd_rn(__ddiv_rn(__dadd_rn(pick_area, cand_area), 2.0), 1e-12);
+    int nvis = P.K;
+    if (P.use_vis) {
+        nvis = 0;
+        for (int k = 0; k < P.K; ++k) nvis += (cand[3 * k + 2] > P.vis_thresh) && (pick[3 * k + 2] > P.vis_thresh);
+    }
+    NumpySum acc;
+    acc.begin(P.K);
+    for (int k = 0; k < P.K; ++k) {
+        const double dx = __dsub_rn(cand[3 * k + 0], pick[3 * k + 0]);
+        const double dy = __dsub_rn(cand[3 * k + 1], pick[3 * k + 1]);
+        double e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        e = __ddiv_rn(__ddiv_rn(__ddiv_rn(e, joint_var(P, k)), denom_area), 2.0);
+        double v = exp(-e);
+        if (P.use_vis) {
+            const bool vis = (cand[3 * k + 2] > P.vis_thresh) && (pick[3 * k + 2] > P.vis_thresh);
+            v = __dmul_rn(v, vis ? 1.0 : 0.0);
+        }
+        acc.push(v);
+    }
+    // (vd_vis.sum(-1) + 1e-12) is float32 arithmetic in the reference
+    const float cnt = __fadd_rn((float)nvis, 1e-12f);
+    return __ddiv_rn(acc.result(), (double)cnt);
+}
+
+__global__ void __launch_bounds__(128)
+oks_iou_kernel(const double* __restrict__ pick_kps, const double* __restrict__ cand_kps,
+               const double* __restrict__ pick_area, const double* __restrict__ cand_area,
+               double* __restrict__ out, int n, OksParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = oks_pair(P, pick_kps, cand_kps + (size_t)i * 3 * P.K, pick_area[0], cand_area[i]);
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores, const double* __restrict__ areas,
+               const int* __restrict__ seg, unsigned char* __restrict__ keep, int* __restrict__ rank,
+               int max_seg, double thresh, OksParams P) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    int* order = reinterpret_cast<int*>(nms_smem);
+    unsigned char* alive = nms_smem + (size_t)max_seg * sizeof(int);
+    const int lo = seg[blockIdx.x], hi = seg[blockIdx.x + 1];
+    const int n = hi - lo;
+    if (n <= 0) return;
+    const int tid = threadIdx.x;
+
+    // descending-score visiting order; ties: higher index first
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const double si = scores[lo + i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) {
+            const double sj = scores[lo + j];
+            r += (sj > si) || (sj == si && j > i);
+        }
+        order[r] = i;
+        rank[lo + i] = r;
+        alive[i] = 1;
+        keep[lo + i] = 0;
+    }
+    __syncthreads();
+
+    const size_t stride = (size_t)3 * P.K;
+    for (int p = 0; p < n; ++p) {
+        if (!alive[p]) continue;                       // uniform: everyone reads the same byte
+        const int i = order[p];
+        if (tid == 0) keep[lo + i] = 1;
+        const double* pick = kps + (size_t)(lo + i) * stride;
+        const double pick_area = areas[lo + i];
+        for (int c = p + 1 + tid; c < n; c += kNmsThreads) {
+            if (!alive[c]) continue;
+            const int j = order[c];
+            const double oks = oks_pair(P, pick, kps + (size_t)(lo + j) * stride, pick_area, areas[lo + j]);
+            if (oks > thresh) alive[c] = 0;            // survivors satisfy oks <= thresh
+        }
+        __syncthreads();
+    }
+}
+
+// eval.py:168-175
+__global__ void __launch_bounds__(128)
+rescore_kernel(const double* __restrict__ kps, const double* __restrict__ box_scores, double* __restrict__ scores,
+               int N, int K, double thr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double* k = kps + (size_t)i * 3 * K;
+    int cnt = 0;
+    for (int j = 0; j < K; ++j) cnt += (k[3 * j + 2] > thr);
+    double mean = 0.0;
+    if (cnt > 0) {
+        NumpySum acc;
+        acc.begin(cnt);
+        for (int j = 0; j < K; ++j) {
+            const double c = k[3 * j + 2];
+            if (c > thr) acc.push(c);
+        }
+        mean = __ddiv_rn(acc.result(), (double)cnt);
+    }
+    scores[i] = __dmul_rn(box_scores[i], mean);
+}
+
+__global__ void __launch_bounds__(256)
+pack_kps_kernel(const float* __restrict__ coords, const float* __restrict__ maxval, double* __restrict__ out, long long nk) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nk) return;
+    const float2 c = reinterpret_cast<const float2*>(coords)[i];
+    out[3 * i + 0] = (double)c.x;
+    out[3 * i + 1] = (double)c.y;
+    out[3 * i + 2] = (double)maxval[i];
+}
+
+}  // namespace
+
+extern "C" int sp_oks_iou_f64(const double* pick_kps, const double* cand_kps, const double* pick_area,
+                              const double* cand_area, const double* sigmas, double* out,
+                              int n, int K, int use_vis_thresh, double vis_thresh, void* stream) {
+    SP_RETURN_IF(!pick_kps || !cand_kps || !pick_area || !cand_area || !out, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(n < 0 || K <= 0 || K > kMaxJoints, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
+    if (n == 0) return 0;
+    OksParams P{sigmas, K, use_vis_thresh ? 1 : 0, vis_thresh};
+    oks_iou_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pick_kps, cand_kps, pick_area, cand_area, out, n, P);
+    return sp_launch_status();
+}
+
+extern "C" int sp_oks_nms_f64(const double* kps, const double* scores, const double* areas, const int* seg,
+                              const double* sigmas, unsigned char* keep, int* rank,
+                              int N, int I, int K, int max_seg, double thresh,
+                              int use_vis_thresh, double vis_thresh, void* stream) {
+    SP_RETURN_IF(!kps || !scores || !areas || !seg || !keep || !rank, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(N < 0 || I < 0 || K <= 0 || K > kMaxJoints || max_seg < 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
+    if (N == 0 || I == 0) return 0;
+    const size_t smem = (size_t)max_seg * (sizeof(int) + 1) + 16;
+    SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
+    if (smem > 48 * 1024)
+        SP_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OksParams P{sigmas, K, use_vis_thresh ? 1 : 0, vis_thresh};
+    oks_nms_kernel<<<I, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(kps, scores, areas, seg, keep, rank, max_seg, thresh, P);
+    return sp_launch_status();
+}
+
+extern "C" int sp_rescore_f64(const double* kps, const double* box_scores, double* scores,
+                              int N, int K, double in_vis_thre, void* stream) {
+    SP_RETURN_IF(!kps || !box_scores || !scores, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(N < 0 || K <= 0 || K > 128, SP_ERR_BAD_ARGUMENT);
+    if (N == 0) return 0;
+    rescore_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(kps, box_scores, scores, N, K, in_vis_thre);
+    return sp_launch_status();
+}
+
+extern "C" int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps, int N, int K, void* stream) {
+    SP_RETURN_IF(!coords || !maxval || !out_kps, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(N < 0 || K <= 0, SP_ERR_BAD_ARGUMENT);
+    const long long nk = (long long)N * K;
+    if (nk == 0) return 0;
+    pack_kps_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(coords, maxval, out_kps, nk);
+    return sp_launch_status();
+}

@@ -1,0 +1,134 @@
+"""Heatmap decoders: drop-ins for the reference's ``metrics/pose_metrics.py``.
+
+``BasicKeyPointDecoder`` (:10-52) and ``GaussTaylorKeyPointDecoder`` (:55-107) keep their
+constructor and call signatures; every call is one launch of the fused sm_100a kernel
+``sp_decode_f32`` (argmax + 13-point blur + log + Taylor + affine), instead of ~60 ATen ops and
+seven passes over the heatmaps. ``flip_call`` adds the flip-test average (not in the reference;
+composed from its ``flip_joints`` / ``joint_pairs`` semantics).
+"""
+import numpy as np
+import torch
+
+from .. import _abi
+from ..commons.joint_utils import swap_permutation
+
+
+def gaussian_kernel_1d(kernel_size):
+    """``cv.getGaussianKernel(kernel_size, 0)`` (float64 column). OpenCV itself when importable
+    (as the reference does, pose_metrics.py:57); otherwise its closed form for n > 7
+    (sigma = 0.3*((n-1)*0.5-1)+0.8, normalised exp(-x^2/(2 sigma^2))), which gives bit-identical
+    float32 2-D weights for the reference's kernel_size = 11."""
+    n = int(kernel_size)
+    try:
+        import cv2
+        return cv2.getGaussianKernel(n, 0)
+    except ImportError:
+        if n <= 7:
+            raise RuntimeError("kernel_size <= 7 needs OpenCV's fixed tables (cv2 not importable)")
+        sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8
+        x = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
+        g = np.exp(-(x * x) / (2.0 * sigma * sigma))
+        return (g / g.sum()).reshape(-1, 1)
+
+
+def _decode(heat_map, heat_map_flip, perm, trans_inv, blur_w, ksize, mode, want_index=False):
+    dev = _abi.require_cuda(heat_map, heat_map_flip, trans_inv)
+    if heat_map.dim() != 4:
+        raise ValueError("heat_map must be [B, K, H, W]")
+    b, k, h, w = (int(s) for s in heat_map.shape)
+    hm = _abi.dense(heat_map.detach(), torch.float32)
+    hf = None
+    if heat_map_flip is not None:
+        if tuple(heat_map_flip.shape) != tuple(heat_map.shape):
+            raise ValueError("heat_map_flip must have the shape of heat_map")
+        hf = _abi.dense(heat_map_flip.detach(), torch.float32)
+    ti = None
+    if trans_inv is not None:
+        if tuple(trans_inv.shape) != (b, 2, 3):
+            raise ValueError("trans_inv must be [B, 2, 3]")
+        ti = _abi.dense(trans_inv.detach(), torch.float32)
+    coords = torch.empty((b, k, 2), dtype=torch.float32, device=dev)
+    maxval = torch.empty((b, k, 1), dtype=torch.float32, device=dev)
+    index = torch.empty((b, k), dtype=torch.int32, device=dev) if want_index else None
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_decode_f32(hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), _abi.ptr(ti),
+                                            _abi.ptr(blur_w), coords.data_ptr(), maxval.data_ptr(),
+                                            _abi.ptr(index), b, k, h, w, int(ksize), int(mode),
+                                            _abi.stream_ptr(dev)))
+    if want_index:
+        return coords, maxval, index
+    return coords, maxval
+
+
+class BasicKeyPointDecoder(object):
+    @staticmethod
+    def heat_map_to_axis(heat_map):
+        """[B,K,H,W] -> (coords [B,K,2] (x, y) float32, max_val [B,K,1]); reference :11-24."""
+        return _decode(heat_map, None, None, None, None, 0, _abi.SP_DECODE_ARGMAX)
+
+    @staticmethod
+    def heat_map_argmax(heat_map):
+        """As ``heat_map_to_axis`` plus the flat int32 argmax [B,K] (first maximal index)."""
+        return _decode(heat_map, None, None, None, None, 0, _abi.SP_DECODE_ARGMAX, want_index=True)
+
+    @torch.no_grad()
+    def __call__(self, heat_map, trans_inv):
+        return _decode(heat_map, None, None, trans_inv, None, 0, _abi.SP_DECODE_BASIC)
+
+
+class GaussTaylorKeyPointDecoder(BasicKeyPointDecoder):
+    def __init__(self, kernel_size=11, num_joints=17):
+        kernel = gaussian_kernel_1d(kernel_size)
+        self.kernel_size = kernel_size
+        self.num_joints = num_joints
+        # float32(k k^T), as pose_metrics.py:60 (one copy; the kernel is depthwise-identical)
+        self.blur_weights = torch.from_numpy(np.ascontiguousarray((kernel * kernel.T).astype(np.float32)))
+        self._perm_cache = {}
+
+    def _weights_on(self, device):
+        if self.blur_weights.device != device:
+            self.blur_weights = self.blur_weights.to(device)
+        return self.blur_weights
+
+    def _perm_on(self, device, num_joints, joint_pairs):
+        key = (device, num_joints, None if joint_pairs is None else tuple(map(tuple, joint_pairs)))
+        perm = self._perm_cache.get(key)
+        if perm is None:
+            perm = torch.tensor(swap_permutation(num_joints, joint_pairs), dtype=torch.int32, device=device)
+            self._perm_cache[key] = perm
+        return perm
+
+    @torch.no_grad()
+    def __call__(self, heat_map, trans_inv):
+        """heat_map [B,K,H,W], trans_inv [B,2,3] -> (coords [B,K,2] image px, max_val [B,K,1])."""
+        return _decode(heat_map, None, None, trans_inv, self._weights_on(heat_map.device),
+                       self.kernel_size, _abi.SP_DECODE_GAUSS_TAYLOR)
+
+    @torch.no_grad()
+    def flip_call(self, heat_map, heat_map_flip, trans_inv, joint_pairs=None):
+        """Flip-test decode: ``heat_map_flip`` is the network output for the mirrored image.
+        Decodes 0.5*(heat_map + mirror_x(heat_map_flip)[:, swap(joint_pairs)]) without
+        materialising the average."""
+        dev = heat_map.device
+        perm = self._perm_on(dev, int(heat_map.shape[1]), joint_pairs)
+        return _decode(heat_map, heat_map_flip, perm, trans_inv, self._weights_on(dev),
+                       self.kernel_size, _abi.SP_DECODE_GAUSS_TAYLOR)
+
+    @torch.no_grad()
+    def decode_with_index(self, heat_map, trans_inv=None, heat_map_flip=None, joint_pairs=None):
+        """Same as ``__call__``/``flip_call`` but also returns the flat argmax (int32 [B,K]);
+        ``trans_inv=None`` gives heatmap-space coordinates."""
+        dev = heat_map.device
+        perm = self._perm_on(dev, int(heat_map.shape[1]), joint_pairs) if heat_map_flip is not None else None
+        return _decode(heat_map, heat_map_flip, perm, trans_inv, self._weights_on(dev),
+                       self.kernel_size, _abi.SP_DECODE_GAUSS_TAYLOR, want_index=True)
+
+
+def kps_to_dict_(predicts, scores, img_ids, set_in_list):
+    """Reference :172-179 with ONE device->host copy instead of one ``.item()`` + ``.tolist()``
+    per person: score = mean + max of the joint peaks, keypoints = [x, y, score] * K."""
+    sc = scores.reshape(scores.shape[0], -1)
+    person = (sc.mean(dim=1) + sc.max(dim=1)[0]).cpu().tolist()
+    flat = torch.cat([predicts, scores], dim=-1).reshape(predicts.shape[0], -1).cpu().tolist()
+    for kp, s, img_id in zip(flat, person, img_ids):
+        set_in_list.append({"image_id": img_id, "score": float(s), "category_id": 1, "keypoints": kp})

@@ -1,0 +1,92 @@
+"""Masked joints-MSE loss: drop-in for the expression every reference solver repeats
+(``processors/dp_pose_hrnet_solver.py:86,106-107``)::
+
+    loss = 0.5 * nn.MSELoss()(pred.mul(mask[[..., None, None]]), target.mul(mask[[..., None, None]]))
+    loss.backward()
+
+``JointsMSELoss()(pred, target, mask)`` returns the same 0-d float32 tensor with autograd
+support. Forward and backward are ONE kernel (``sp_mse_fwd_bwd_f32``): the gradient w.r.t.
+``pred`` is produced while the loss is being reduced; ``backward`` only rescales it when the
+upstream gradient is not 1 (``GradScaler``), and that rescale kernel exits without touching
+memory when the factor is exactly 1.
+"""
+import torch
+
+from .. import _abi
+
+_workspaces = {}
+
+
+def _workspace(device, stream_id):
+    """Zero-initialised scratch per (device, stream); the kernel restores the zero state."""
+    key = (device.index, stream_id)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = int(_abi.lib().sp_mse_workspace_bytes())
+        ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def mse_forward_backward(pred, target, mask, need_grad=True, grad_scale=1.0, skip_masked=False):
+    """(loss 0-d float32, grad like pred or None); everything on pred's CUDA device."""
+    dev = _abi.require_cuda(pred, target, mask)
+    if pred.dim() < 3:
+        raise ValueError("pred must be [B, K, ...]")
+    b, k = int(pred.shape[0]), int(pred.shape[1])
+    hw = 1
+    for s in pred.shape[2:]:
+        hw *= int(s)
+    if tuple(target.shape) != tuple(pred.shape) or tuple(mask.shape) != (b, k):
+        raise ValueError("shape mismatch: pred %s target %s mask %s" % (tuple(pred.shape), tuple(target.shape), tuple(mask.shape)))
+    p = _abi.dense(pred.detach(), torch.float32)
+    t = _abi.dense(target.detach(), torch.float32)
+    m = _abi.dense(mask.detach(), torch.float32)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(p) if need_grad else None
+    stream = _abi.stream_ptr(dev)
+    ws = _workspace(dev, stream)
+    flags = _abi.SP_MSE_SKIP_MASKED if skip_masked else 0
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_mse_fwd_bwd_f32(p.data_ptr(), t.data_ptr(), m.data_ptr(), _abi.ptr(grad),
+                                                 loss.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                                 b, k, hw, float(grad_scale), flags, stream))
+    return loss, grad
+
+
+class _MaskedMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, skip_masked):
+        need = pred.requires_grad
+        loss, grad = mse_forward_backward(pred, target, mask, need_grad=need, skip_masked=skip_masked)
+        ctx.pred_dtype = pred.dtype
+        ctx.save_for_backward(grad if need else None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None, None, None
+        dev = grad.device
+        g = _abi.dense(grad_out.detach().to(dev), torch.float32)
+        with torch.cuda.device(dev):
+            _abi.check(_abi.lib().sp_scale_inplace_f32(grad.data_ptr(), grad.numel(), g.data_ptr(),
+                                                       _abi.stream_ptr(dev)))
+        out = grad if ctx.pred_dtype == torch.float32 else grad.to(ctx.pred_dtype)
+        return out, None, None, None
+
+
+class JointsMSELoss(torch.nn.Module):
+    """``loss = JointsMSELoss()(pred [B,K,H,W], target [B,K,H,W], mask [B,K])``.
+
+    ``skip_masked=True`` does not read pred/target of joints whose mask is 0 (saves their HBM
+    traffic; differs from the reference only when those maps hold NaN/Inf, which the
+    reference would propagate into the loss)."""
+
+    def __init__(self, skip_masked=False):
+        super().__init__()
+        self.skip_masked = bool(skip_masked)
+
+    def forward(self, pred, target, mask):
+        return _MaskedMSE.apply(pred, target, mask, self.skip_masked)

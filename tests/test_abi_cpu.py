@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library builds, loads without a GPU and exports exactly the symbols that
+include/simple_pose_b200.h declares; host-side argument checks fire before any launch; the
+product path refuses to run without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from simple_pose_b200 import build, _abi
+    build.build()
+    return _abi.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "simple_pose_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from simple_pose_b200 import _abi, build
+    names = declared_symbols()
+    assert len(names) >= 12
+    assert sorted(_abi.SIGNATURES) == names            # ctypes table mirrors the header 1:1
+    out = subprocess.run(["nm", "-D", "--defined-only", build.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (sp_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_header_compiles_as_c():
+    src = '#include "simple_pose_b200.h"\nint main(void){return SP_ABI_VERSION-1;}\n'
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+
+
+def test_library_is_sm100a_only(lib):
+    from simple_pose_b200 import build
+    out = subprocess.run(["cuobjdump", "--list-elf", build.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, out
+
+
+def test_tma_bulk_copy_in_sass(lib):
+    from simple_pose_b200 import build
+    out = subprocess.run("cuobjdump -sass %s | grep -c UBLKCP" % build.lib_path(), shell=True, capture_output=True, text=True).stdout
+    assert int(out.strip() or 0) >= 2                  # plain and flip variants of the decode kernel
+
+
+def test_argument_errors_without_gpu(lib):
+    assert lib.sp_abi_version() == 1
+    assert lib.sp_mse_workspace_bytes() >= 16
+    assert b"aligned" in lib.sp_error_string(-2)
+    assert lib.sp_error_string(0) == b"ok"
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.sp_encode_f32(None, None, None, 1, 17, 64, 48, 2.0, None) == -1
+    assert lib.sp_encode_f32(16, 16, 16, 1, 17, 64, 48, -1.0, None) == -1
+    assert lib.sp_decode_f32(None, None, None, None, None, None, None, None, 1, 17, 64, 48, 11, 0, None) == -1
+    assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 1, 17, 64, 48, 10, 0, None) == -4   # even ksize
+    assert lib.sp_decode_f32(16, 16, None, None, 16, 16, 16, None, 1, 17, 64, 48, 11, 0, None) == -1     # flip w/o perm
+    assert lib.sp_decode_f32(16, None, None, None, 16, 24, 16, None, 1, 17, 64, 48, 11, 0, None) == -2   # misaligned coords
+    assert lib.sp_mse_fwd_bwd_f32(16, 16, 16, 16, 16, 16, 8, 1, 17, 3072, 1.0, 0, None) == -3             # workspace too small
+    assert lib.sp_oks_nms_f64(16, 16, 16, 16, None, 16, 16, 4, 1, 16, 4, 0.9, 0, 0.0, None) == -1         # K != 17 w/o sigmas
+    # empty batches are a no-op success
+    assert lib.sp_encode_f32(16, 16, 16, 0, 17, 64, 48, 2.0, None) == 0
+    assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 0, 17, 64, 48, 11, 0, None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from simple_pose_b200.commons.transforms import RefineSimpleTransform, encode_heat_maps
+    from simple_pose_b200.metrics.pose_metrics import GaussTaylorKeyPointDecoder
+    from simple_pose_b200.processors.loss import JointsMSELoss
+    from simple_pose_b200.datasets.naive_data import oks_nms
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        RefineSimpleTransform.get_heat_map(np.zeros((17, 3), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        encode_heat_maps(torch.zeros(2, 17, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        GaussTaylorKeyPointDecoder()(torch.zeros(1, 17, 64, 48), torch.zeros(1, 2, 3))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        JointsMSELoss()(torch.zeros(1, 17, 8, 8), torch.zeros(1, 17, 8, 8), torch.ones(1, 17))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        oks_nms(np.zeros((2, 17, 3)), np.array([.5, .4]), np.ones(2), 0.9)
+
+
+def test_missing_extension_is_loud(monkeypatch, tmp_path):
+    from simple_pose_b200 import _abi
+    monkeypatch.setattr(_abi, "_lib", None)
+    monkeypatch.setenv("SIMPLE_POSE_B200_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(_abi.ExtensionMissing, match="no CPU fallback"):
+        _abi.lib()
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under simple_pose_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "simple_pose_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(base, f)
+                assert "/root/reference" not in text, os.path.join(base, f)
+
+
+def test_swap_permutation():
+    from simple_pose_b200.commons.joint_utils import swap_permutation
+    assert swap_permutation(17) == [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
+    assert swap_permutation(4, [[0, 3]]) == [3, 1, 2, 0]
+    with pytest.raises(ValueError):
+        swap_permutation(4, [[0, 9]])

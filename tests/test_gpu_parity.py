@@ -1,0 +1,425 @@
+"""GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against
+(1) the fixtures frozen from the reference and (2) the oracle on seeded inputs.
+
+Gates (BASELINE.json north_star / SURVEY.md section 8d):
+  argmax indices bit-exact; max_val bit-exact; refined coordinates <= 1e-4 px in heatmap
+  space; image space <= 1e-4 px scaled by the affine magnification (plus 2 ulp at the
+  coordinate magnitude); loss <= 1e-5 relative; grad <= 1e-5 relative (floor 1e-12);
+  encoder targets <= 1 float32 ulp with < 1e-6 of elements differing at all (float64
+  separable evaluation, one rounding); weights, NMS keep sets and pick order exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits
+from oracle import heatmap_oracle as O
+from simple_pose_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def api():
+    from simple_pose_b200 import _abi
+    from simple_pose_b200.commons import transforms
+    from simple_pose_b200.datasets import naive_data
+    from simple_pose_b200.metrics import pose_metrics
+    from simple_pose_b200.processors import loss
+
+    class NS:
+        pass
+    ns = NS()
+    ns.abi, ns.transforms, ns.naive, ns.metrics, ns.loss = _abi, transforms, naive_data, pose_metrics, loss
+    _abi.lib()
+    return ns
+
+
+def ulp_diff(a, b):
+    ia = np.ascontiguousarray(a).view(np.int32).astype(np.int64)
+    ib = np.ascontiguousarray(b).view(np.int32).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+def assert_targets_match(got, want):
+    d = ulp_diff(got, want)
+    assert d.max() <= 1, "max ulp diff %d" % d.max()
+    assert (d != 0).mean() < 1e-6, "fraction differing %.3g" % (d != 0).mean()
+
+
+# ------------------------------------------------------------------------------------ encode
+def test_encode_golden(api, golden):
+    g = golden("encode")
+    for tag, shape, sigma in (("a", (48, 64), 2.0), ("b", (72, 96), 2.0), ("e", (48, 64), 2.0), ("s", (48, 64), 1.5)):
+        t, w = api.transforms.encode_heat_maps(torch.from_numpy(g["joints_" + tag]).to(DEV), sigma, shape)
+        assert np.array_equal(w.cpu().numpy(), g["weights_" + tag]), tag
+        assert_targets_match(t.cpu().numpy(), g["targets_" + tag])
+        # the hand-built vectors are few enough to demand bit equality outright
+        if tag == "e":
+            assert np.array_equal(bits(t.cpu().numpy()), bits(g["targets_e"]))
+
+
+@pytest.mark.parametrize("shape,persons", [((48, 64), 128), ((72, 96), 32), ((50, 30), 8), ((4, 4), 3), ((132, 20), 4)])
+def test_encode_vs_oracle(api, shape, persons):
+    w, h = shape
+    joints = synth.joints(persons, height=h, width=w, seed=123)
+    t, wt = api.transforms.encode_heat_maps(joints.to(DEV), 2.0, shape)
+    rt, rw = O.encode_batch(joints.numpy(), 2.0, shape)
+    assert np.array_equal(wt.cpu().numpy(), rw)
+    assert_targets_match(t.cpu().numpy(), rt)
+    assert 0 < (rw == 0).mean() < 1          # both cull branches exercised
+
+
+def test_encode_per_sample_signature_and_empty(api, golden):
+    g = golden("encode")
+    t, w = api.transforms.RefineSimpleTransform.get_heat_map(g["joints_e"][0], sigma=2.0, shape=(48, 64))
+    assert isinstance(t, np.ndarray) and t.dtype == np.float32 and t.shape == (17, 64, 48)
+    assert np.array_equal(bits(t), bits(g["targets_e"][0])) and np.array_equal(w, g["weights_e"][0])
+    t0, w0 = api.transforms.encode_heat_maps(torch.zeros(0, 17, 3, device=DEV))
+    assert t0.shape == (0, 17, 64, 48) and w0.shape == (0, 17)
+
+
+def test_encode_denormals_kept(api):
+    j = torch.tensor([[[3.0, 3.0, 1.0]]], device=DEV)
+    t, _ = api.transforms.encode_heat_maps(j, 2.0, (48, 64))
+    t = t.cpu().numpy()
+    assert ((t > 0) & (t < 1.1754944e-38)).any()
+
+
+# ------------------------------------------------------------------------------------ loss
+def test_loss_golden(api, golden):
+    g = golden("loss")
+    pred = torch.from_numpy(g["pred"]).to(DEV).requires_grad_(True)
+    loss = api.loss.JointsMSELoss()(pred, torch.from_numpy(g["target"]).to(DEV), torch.from_numpy(g["mask"]).to(DEV))
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    got = pred.grad.cpu().numpy()
+    assert np.allclose(got, g["grad"], rtol=1e-5, atol=1e-12)
+    assert np.array_equal(bits(got), bits(g["grad"]))      # same operation order as ATen
+
+
+@pytest.mark.parametrize("b,hw", [(128, (64, 48)), (16, (96, 72)), (5, (7, 9))])
+def test_loss_vs_oracle(api, b, hw):
+    h, w = hw
+    joints = synth.joints(b, height=h, width=w, seed=5)
+    tgt_np, msk_np = O.encode_batch(joints.numpy(), 2.0, (w, h))
+    tgt, msk = torch.from_numpy(tgt_np), torch.from_numpy(msk_np)
+    pred = synth.predictions_like(tgt, seed=6)
+    ref_loss, ref_grad = O.masked_mse_loss_and_grad(pred, tgt, msk)
+    p = pred.to(DEV).requires_grad_(True)
+    loss = api.loss.JointsMSELoss()(p, tgt.to(DEV), msk.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert torch.allclose(p.grad.cpu(), ref_grad, rtol=1e-5, atol=1e-12)
+    # skip_masked variant: identical on finite inputs
+    p2 = pred.to(DEV).requires_grad_(True)
+    loss2 = api.loss.JointsMSELoss(skip_masked=True)(p2, tgt.to(DEV), msk.to(DEV))
+    loss2.backward()
+    assert loss2.item() == loss.item() and torch.equal(p2.grad, p.grad)
+
+
+def test_loss_upstream_gradient_and_determinism(api):
+    tgt = synth.heatmaps(8, seed=3).to(DEV)
+    msk = (torch.rand(8, 17, device=DEV) > 0.2).float()
+    pred = synth.predictions_like(tgt, seed=4)
+    crit = api.loss.JointsMSELoss()
+    p1 = pred.clone().requires_grad_(True)
+    l1 = crit(p1, tgt, msk)
+    l1.backward()
+    p2 = pred.clone().requires_grad_(True)
+    l2 = crit(p2, tgt, msk)
+    (l2 * 1024.0).backward()                      # GradScaler-style upstream gradient
+    assert l1.item() == l2.item()                 # deterministic reduction
+    assert torch.equal(p2.grad, p1.grad * 1024.0)
+    p3 = pred.clone()                             # no grad requested -> forward only
+    assert crit(p3, tgt, msk).item() == l1.item()
+
+
+def test_loss_is_linear_in_squared_scale(api):
+    """Size-independent property at the full cfg-2 shape: scaling (pred - target) by 2 scales
+    the loss by 4 and the gradient by 2 (powers of two are exact in float32)."""
+    tgt = synth.heatmaps(128, seed=9).to(DEV)
+    msk = torch.ones(128, 17, device=DEV)
+    diff = 0.05 * torch.randn_like(tgt)
+    crit = api.loss.JointsMSELoss()
+    pa = (tgt + diff).requires_grad_(True)
+    pb = (tgt + 2 * diff).requires_grad_(True)
+    la, lb = crit(pa, tgt, msk), crit(pb, tgt, msk)
+    la.backward()
+    lb.backward()
+    assert abs(lb.item() - 4 * la.item()) <= 2e-6 * lb.item()
+    assert torch.allclose(pb.grad, 2 * pa.grad, rtol=2e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ decode
+def check_decode(api, hm, tinv, ref_img, ref_hsp, ref_max, ref_idx, dec=None):
+    dec = dec or api.metrics.GaussTaylorKeyPointDecoder()
+    hm_d = hm.to(DEV)
+    keep = hm_d.clone()
+    hsp, mx, idx = dec.decode_with_index(hm_d)
+    assert torch.equal(hm_d, keep)                                   # input not modified
+    assert np.array_equal(idx.cpu().numpy(), np.asarray(ref_idx, dtype=np.int32)), "argmax not bit-exact"
+    assert np.array_equal(bits(mx.cpu().numpy()), bits(np.asarray(ref_max))), "max_val not bit-exact"
+    err = np.abs(hsp.cpu().numpy().astype(np.float64) - np.asarray(ref_hsp, dtype=np.float64))
+    assert np.nanmax(err) <= 1e-4, "heatmap-space error %.3g px" % np.nanmax(err)
+    assert np.array_equal(np.isnan(hsp.cpu().numpy()), np.isnan(ref_hsp))
+    if tinv is not None:
+        img, mx2 = dec(hm_d, tinv.to(DEV))
+        assert img.shape == (hm.shape[0], hm.shape[1], 2) and mx2.shape == (hm.shape[0], hm.shape[1], 1)
+        mag = tinv[:, :, :2].abs().sum(-1).max(-1)[0].numpy()[:, None, None]     # px per heatmap px
+        tol = 1e-4 * mag + 2 * np.spacing(np.abs(np.asarray(ref_img)).astype(np.float32))
+        ierr = np.abs(img.cpu().numpy().astype(np.float64) - np.asarray(ref_img, dtype=np.float64))
+        assert (ierr <= tol).all(), "image-space error %.3g" % ierr.max()
+    return float(np.nanmax(err))
+
+
+def test_decode_golden(api, golden):
+    g = golden("decode")
+    for tag in ("a", "b", "e"):
+        check_decode(api, torch.from_numpy(g["hm_" + tag]), torch.from_numpy(g["tinv_" + tag]),
+                     g["img_" + tag], g["hsp_" + tag], g["max_" + tag], g["idx_" + tag])
+
+
+def test_blur_weights_are_the_reference_ones(api, golden):
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    assert np.array_equal(bits(dec.blur_weights.cpu().numpy()), bits(golden("blur_weights")["w11"]))
+
+
+@pytest.mark.parametrize("b,hw,noise", [(128, (64, 48), 0.01), (64, (96, 72), 0.01), (32, (64, 48), 0.05),
+                                        (8, (32, 24), 0.02), (6, (40, 50), 0.01), (4, (33, 31), 0.01)])
+def test_decode_vs_oracle(api, b, hw, noise):
+    h, w = hw
+    hm = synth.heatmaps(b, height=h, width=w, seed=77, noise=noise)
+    tinv = synth.inverse_affines(b, height=h, width=w, seed=77)[0]
+    ref_img, ref_max = O.gauss_taylor_decode(hm, tinv)
+    ref_hsp, _ = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
+    check_decode(api, hm, tinv, ref_img.numpy(), ref_hsp.numpy(), ref_max.numpy(), O.argmax_index(hm).numpy())
+
+
+def test_decode_generic_path_matches_fast_path(api):
+    hm = synth.heatmaps(16, seed=5).to(DEV)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    a = dec.decode_with_index(hm)
+    os.environ["SP_DECODE_FORCE_GENERIC"] = "1"
+    try:
+        b = dec.decode_with_index(hm)
+    finally:
+        del os.environ["SP_DECODE_FORCE_GENERIC"]
+    assert torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
+    assert (a[0] - b[0]).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("warps,stages", [(1, 1), (4, 2), (8, 2), (16, 1), (3, 4)])
+def test_decode_ring_configurations(api, warps, stages):
+    """Every warps x stages ring layout walks the same maps (phase/parity bookkeeping)."""
+    hm = synth.heatmaps(40, seed=6)
+    ref_hsp, ref_max = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
+    os.environ["SP_DECODE_WARPS"], os.environ["SP_DECODE_STAGES"] = str(warps), str(stages)
+    try:
+        check_decode(api, hm, None, None, ref_hsp.numpy(), ref_max.numpy(), O.argmax_index(hm).numpy())
+    finally:
+        del os.environ["SP_DECODE_WARPS"], os.environ["SP_DECODE_STAGES"]
+
+
+def test_argmax_special_values(api):
+    """torch.max semantics: first index on ties, NaN wins (first NaN), +-Inf, -0.0 == +0.0."""
+    hm = torch.zeros(1, 8, 64, 48)
+    hm[0, 0, 5, 5] = float("nan")
+    hm[0, 0, 9, 9] = 3.0
+    hm[0, 1, 7, 7] = float("inf")
+    hm[0, 1, 8, 8] = float("inf")
+    hm[0, 2] = -float("inf")
+    hm[0, 3] = float("nan")
+    hm[0, 4] = -0.0
+    hm[0, 4, 2, 3] = 0.0
+    hm[0, 5, 63, 47] = 1e-30
+    hm[0, 6] = -1.0
+    hm[0, 6, 0, 1] = -0.0
+    hm[0, 7, 10, 4:8] = 2.0
+    ref_c, ref_m = O.argmax_coords(hm)
+    ref_i = O.argmax_index(hm)
+    c, m, i = api.metrics.BasicKeyPointDecoder.heat_map_argmax(hm.to(DEV))
+    assert torch.equal(i.cpu().long(), ref_i)
+    assert np.array_equal(bits(m.cpu().numpy()), bits(ref_m.numpy()))
+    assert torch.equal(c.cpu(), ref_c)
+    c2, m2 = api.metrics.BasicKeyPointDecoder.heat_map_to_axis(hm.to(DEV))
+    assert torch.equal(c2, c) and c2.shape == (1, 8, 2) and m2.shape == (1, 8, 1)
+    # the full decoder must agree with the reference on which joints are refined at all
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hsp, mx, idx = dec.decode_with_index(hm.to(DEV))
+    o_hsp, o_mx = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
+    assert torch.equal(idx.cpu().long(), ref_i)
+    ok = ~torch.isnan(o_hsp)
+    assert torch.equal(torch.isnan(hsp.cpu()), ~ok)
+    assert (hsp.cpu()[ok] - o_hsp[ok]).abs().max().item() <= 1e-4
+
+
+def test_decode_clamp_path_mixed_stencils(api):
+    """Maps whose blurred neighbourhood straddles the 1e-10 clamp take the exact slow path
+    (whole-map blur max); results must still match the reference."""
+    g = torch.Generator().manual_seed(3)
+    hm = 0.02 * torch.randn(4, 17, 64, 48, generator=g)            # noise-dominated: mixed signs after blur
+    yy, xx = torch.meshgrid(torch.arange(64.), torch.arange(48.), indexing="ij")
+    for k in range(17):
+        hm[0, k] = torch.exp(-((xx - 10 - k) ** 2 + (yy - 20 - k) ** 2) / 1.0) - 0.03 * (k + 1) / 17
+    ref_hsp, ref_max = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hsp, mx, idx = dec.decode_with_index(hm.to(DEV))
+    assert torch.equal(idx.cpu().long(), O.argmax_index(hm))
+    assert torch.equal(mx.cpu(), ref_max)
+    # ill-conditioned joints amplify 1-ulp differences: gate on the well
+    # conditioned ones, demand structural agreement (refined or not, finite) on all
+    moved_ref = (ref_hsp != O.argmax_coords(hm)[0]).any(-1)
+    moved = (hsp.cpu() != O.argmax_coords(hm)[0]).any(-1)
+    assert torch.equal(moved, moved_ref)
+    off = (ref_hsp - O.argmax_coords(hm)[0]).abs().max(-1)[0]
+    well = off < 2.0
+    assert well.float().mean() > 0.5
+    assert (hsp.cpu() - ref_hsp)[well].abs().max().item() <= 1e-3
+    assert torch.isfinite(hsp).all()
+
+
+def test_basic_decoder(api, golden):
+    g, d = golden("next_rows"), golden("decode")
+    hm = torch.from_numpy(d["hm_a"]).to(DEV)
+    img, mx = api.metrics.BasicKeyPointDecoder()(hm, torch.from_numpy(d["tinv_a"]).to(DEV))
+    assert np.array_equal(bits(mx.cpu().numpy()), bits(g["basic_max"]))
+    assert np.abs(img.cpu().numpy() - g["basic_img"]).max() <= 1e-3
+    hsp, _ = api.metrics.BasicKeyPointDecoder()(hm, synth.identity_affines(3).to(DEV))
+    assert np.array_equal(hsp.cpu().numpy(), g["basic_hsp"])
+    e, _ = api.metrics.BasicKeyPointDecoder()(torch.from_numpy(d["hm_e"]).to(DEV), synth.identity_affines(1).to(DEV))
+    assert np.array_equal(e.cpu().numpy(), g["basic_edge_hsp"])
+
+
+# ------------------------------------------------------------------------------------ flip test
+def test_flip_decode_golden(api, golden):
+    g = golden("flip")
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hm, hf = torch.from_numpy(g["hm"]).to(DEV), torch.from_numpy(g["hm_flip"]).to(DEV)
+    keep_a, keep_b = hm.clone(), hf.clone()
+    hsp, mx, idx = dec.decode_with_index(hm, None, hf)
+    assert torch.equal(hm, keep_a) and torch.equal(hf, keep_b)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.array_equal(bits(mx.cpu().numpy()), bits(g["max"]))
+    assert np.abs(hsp.cpu().numpy() - g["hsp"]).max() <= 1e-4
+    img, _ = dec.flip_call(hm, hf, torch.from_numpy(g["tinv"]).to(DEV), [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]])
+    assert np.abs(img.cpu().numpy() - g["img"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("b,hw", [(256, (64, 48)), (32, (96, 72)), (4, (20, 22))])
+def test_flip_decode_vs_oracle_and_mirror_identity(api, b, hw):
+    h, w = hw
+    hm, hf = synth.flip_pair(b, height=h, width=w, seed=31)
+    ref_hsp, ref_max = O.flip_decode(hm, hf, None, return_heatmap_space=True)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hsp, mx, idx = dec.decode_with_index(hm.to(DEV), None, hf.to(DEV))
+    assert torch.equal(idx.cpu().long(), O.argmax_index(O.flip_average(hm, hf)))
+    assert torch.equal(mx.cpu(), ref_max)
+    assert (hsp.cpu() - ref_hsp).abs().max().item() <= 1e-4
+    # property: if hm_flip is the exact mirrored/swapped copy of hm, flip decode == plain decode
+    perm = O.swap_permutation(17)
+    mirror = hm.flip(-1)[:, perm].contiguous()
+    a = dec.decode_with_index(hm.to(DEV), None, mirror.to(DEV))
+    p = dec.decode_with_index(hm.to(DEV))
+    assert torch.equal(a[2], p[2]) and torch.equal(a[1], p[1]) and torch.equal(a[0], p[0])
+
+
+# ------------------------------------------------------------------------------------ round trip
+@pytest.mark.parametrize("hw", [(64, 48), (96, 72)])
+def test_encode_decode_round_trip(api, hw):
+    """Size-independent property: decoding an encoded target recovers the centre."""
+    h, w = hw
+    g = torch.Generator().manual_seed(1)
+    mu = torch.rand(512, 17, 2, generator=g)
+    mu[..., 0] = 3 + mu[..., 0] * (w - 7)
+    mu[..., 1] = 3 + mu[..., 1] * (h - 7)
+    joints = torch.cat([mu, torch.ones(512, 17, 1)], -1)
+    t, wt = api.transforms.encode_heat_maps(joints.to(DEV), 2.0, (w, h))
+    assert (wt == 1).all()
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    xy, mx = dec(t, synth.identity_affines(512).to(DEV))
+    err = (xy.cpu() - mu).abs()
+    assert err.max().item() < 0.02, err.max().item()
+    assert (mx > 0.77).all()
+
+
+# ------------------------------------------------------------------------------------ OKS / NMS
+def test_oks_golden(api, golden):
+    g = golden("oks")
+    keep, scores, rank = api.naive.rescore_and_nms(g["kps"], g["box_scores"], g["areas"], g["seg"])
+    assert np.array_equal(keep.cpu().numpy(), g["keep"])
+    assert np.allclose(scores.cpu().numpy(), g["scores"], rtol=1e-15, atol=0)
+    lo, hi = int(g["seg"][0]), int(g["seg"][1])
+    iou = api.naive.oks_iou(g["kps"][lo], g["kps"][lo:hi], g["areas"][lo], g["areas"][lo:hi])
+    assert np.allclose(iou, g["iou0"], rtol=1e-14, atol=1e-300)
+    iou_v = api.naive.oks_iou(g["kps"][lo], g["kps"][lo:hi], g["areas"][lo], g["areas"][lo:hi], in_vis_thresh=0.5)
+    assert np.allclose(iou_v, g["iou0_vis"], rtol=1e-14, atol=1e-300)
+    picks = []
+    for s in range(len(g["seg"]) - 1):
+        lo, hi = int(g["seg"][s]), int(g["seg"][s + 1])
+        got = api.naive.oks_nms(g["kps"][lo:hi], g["scores"][lo:hi], g["areas"][lo:hi], 0.9)
+        picks.extend(i + lo for i in got)
+    assert picks == [int(i) for i in g["picks"]]
+
+
+def test_oks_nms_vs_oracle_large(api):
+    kps, box, area, seg = synth.nms_groups(400, mean_group=20.0, seed=8)
+    keep, scores, rank = api.naive.rescore_and_nms(kps, box, area, seg)
+    o_keep, o_scores, o_picks = O.rescore_and_nms(kps.numpy(), box.numpy(), area.numpy(), seg.numpy())
+    assert np.array_equal(keep.cpu().numpy().astype(bool), o_keep)
+    assert np.allclose(scores.cpu().numpy(), o_scores, rtol=1e-15, atol=0)
+    assert 0.2 < o_keep.mean() < 0.95
+    # pick order per image from (keep, rank)
+    keep_np, rank_np = keep.cpu().numpy().astype(bool), rank.cpu().numpy()
+    for s in range(0, 400, 37):
+        lo, hi = int(seg[s]), int(seg[s + 1])
+        kept = np.nonzero(keep_np[lo:hi])[0]
+        order = [int(i) + lo for i in kept[np.argsort(rank_np[lo:hi][kept])]]
+        assert order == o_picks[s]
+
+
+def test_oks_nms_edge_cases(api):
+    kps, box, area, seg = synth.nms_groups(3, mean_group=5.0, seed=2)
+    # empty segment in the middle, single-person image, and one big image
+    n = kps.shape[0]
+    seg2 = np.array([0, 1, 1, n], dtype=np.int32)
+    keep, rank = api.naive.oks_nms_batched(kps, box, area, seg2, 0.9)
+    assert keep[0].item() == 1
+    o = O.oks_greedy_nms(kps.numpy()[1:], box.numpy()[1:], area.numpy()[1:], 0.9)
+    assert sorted(int(i) + 1 for i in o) == [int(i) for i in np.nonzero(keep.cpu().numpy())[0] if i >= 1]
+    assert api.naive.oks_nms(np.zeros((0, 17, 3)), np.zeros(0), np.zeros(0), 0.9) == []
+    # identical poses: only the best survives
+    same = kps[:1].repeat(6, 1, 1)
+    got = api.naive.oks_nms(same.numpy(), np.array([.1, .5, .3, .9, .2, .4]), np.full(6, 1e4), 0.9)
+    assert got == [3]
+
+
+def test_pack_and_end_to_end_eval_chain(api):
+    """decode -> pack -> rescore -> NMS on the device equals the reference chain."""
+    hm = synth.heatmaps(64, seed=12)
+    tinv, area = synth.inverse_affines(64, seed=12)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    c, m = dec(hm.to(DEV), tinv.to(DEV))
+    kps = api.naive.pack_keypoints(c, m)
+    assert kps.dtype == torch.float64 and kps.shape == (64, 17, 3)
+    assert torch.equal(kps[..., :2].float(), c) and torch.equal(kps[..., 2:].float(), m)
+    seg = np.arange(0, 65, 8, dtype=np.int32)
+    box = torch.rand(64, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    keep, scores, _ = api.naive.rescore_and_nms(kps, box, area, seg)
+    o_keep, o_scores, _ = O.rescore_and_nms(kps.cpu().numpy(), box.numpy(), area.numpy(), seg)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), o_keep)
+    assert np.allclose(scores.cpu().numpy(), o_scores, rtol=1e-15, atol=0)
+
+
+def test_errors_are_loud(api):
+    with pytest.raises(RuntimeError):
+        api.metrics.GaussTaylorKeyPointDecoder()(torch.zeros(1, 17, 64, 48), torch.zeros(1, 2, 3))   # CPU tensors
+    with pytest.raises(ValueError):
+        api.metrics.GaussTaylorKeyPointDecoder()(torch.zeros(1, 17, 64, 48, device=DEV), torch.zeros(2, 2, 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        api.abi.check(-4)
