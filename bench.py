@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""Throughput of the heatmap hot path on N B200s of one node (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                        # the reference's CPU algorithm
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N  # one rank per GPU (N > 1)
+
+A step = one pass of the hot path over PERSONS persons per GPU (K = 17, 64x48 float32 maps):
+encode (joints -> targets, weights), masked-MSE forward+backward (pred, targets, weights ->
+loss, grad) and GaussTaylor decode (pred, trans_inv -> keypoints, scores), issued as BATCH-sized
+launches over distinct buffers (working set >> the 126 MB L2, so every launch streams from HBM).
+With N > 1 every rank does the same amount of work on its own persons (weak scaling) and the
+decoded keypoints are all-gathered over NCCL inside the step.
+
+Prints ONE JSON line (rank 0). `value` = persons/s with inputs resident in HBM; `e2e` = the same
+path fed from pinned host buffers through the public Python API (H2D of joints, predicted
+heatmaps and affines, D2H of loss and keypoints, all inside the timed region); `roofline` = the
+dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the oracle (a CPU
+restatement of the reference's algorithm, pinned bit-exact to it) timed on this box's host.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "persons/sec encode+decode (K=17, 64x48 & 96x72) at 1/2/4/8 B200; % HBM roofline"
+UNIT = "persons/s"
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--persons", type=int, default=8192, help="persons per GPU per step")
+    ap.add_argument("--batch", type=int, default=1024, help="persons per kernel launch")
+    ap.add_argument("--height", type=int, default=64)
+    ap.add_argument("--width", type=int, default=48)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="persons in the cpu_baseline sample")
+    ap.add_argument("--no-ops", action="store_true", help="skip the per-op sweep (64x48 and 96x72)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_reference_rates(persons, height, width, threads, reps=3, encode_workers=1):
+    """persons/s of the reference's CPU algorithm (oracle port) per op on this host.
+
+    encode: the per-person Python/NumPy loop (``encode_workers`` processes, like the reference's
+    DataLoader workers); loss fwd+bwd and decode: ATen on ``threads`` threads."""
+    from oracle import heatmap_oracle as O          # CPU baseline leg: the one product-side use
+    from simple_pose_b200 import synth
+    import numpy as np
+    torch.set_num_threads(max(1, threads))
+    joints = synth.joints(persons, height=height, width=width, seed=0).numpy()
+    tinv = synth.inverse_affines(persons, height=height, width=width, seed=0)[0]
+
+    def best(fn):
+        fn()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            t.append(time.perf_counter() - t0)
+        return min(t)
+
+    if encode_workers > 1:
+        import multiprocessing as mp
+        chunks = [c for c in np.array_split(joints, encode_workers * 4) if len(c)]
+        with mp.get_context("fork").Pool(encode_workers) as pool:
+            t_enc = best(lambda: pool.starmap(O.encode_batch, [(c, 2.0, (width, height)) for c in chunks]))
+    else:
+        t_enc = best(lambda: O.encode_batch(joints, 2.0, (width, height)))
+    tgt_np, wts_np = O.encode_batch(joints, 2.0, (width, height))
+    tgt, wts = torch.from_numpy(tgt_np), torch.from_numpy(wts_np)
+    pred = synth.predictions_like(tgt, seed=1)
+    t_loss = best(lambda: O.masked_mse_loss_and_grad(pred, tgt, wts))
+    t_dec = best(lambda: O.gauss_taylor_decode(pred, tinv))
+    rates = {"encode": persons / t_enc, "loss": persons / t_loss, "decode": persons / t_dec}
+    rates["step"] = persons / (t_enc + t_loss + t_dec)
+    return rates
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = min(cores, 32)
+    sample = args.cpu_sample * 2
+    t0 = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_reference_rates(min(sample, 64), args.height, args.width, cores, reps=1, encode_workers=1)
+    vals = []
+    for _ in range(args.steps):
+        vals.append(cpu_reference_rates(sample, args.height, args.width, cores, reps=1, encode_workers=workers)["step"])
+        if time.perf_counter() - t0 > 240:
+            break
+    value = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "encode + masked-MSE fwd/bwd + GaussTaylor decode, K=17, %dx%d" % (args.height, args.width),
+                   "sample_persons_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d persons per step; encode in %d worker processes (reference: DataLoader "
+                                   "workers), loss/decode on %d ATen threads" % (sample, workers, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def make_inputs(persons, batch, height, width, device, seed):
+    """Per-batch input sets generated on the device: joints, predicted heatmaps, affines."""
+    from simple_pose_b200 import synth
+    sets = []
+    for i in range(persons // batch):
+        s = seed + 1000 * i
+        joints = synth.joints(batch, height=height, width=width, seed=s, device=device)
+        pred = synth.heatmaps(batch, height=height, width=width, seed=s, noise=0.01, device=device)
+        tinv = synth.inverse_affines(batch, height=height, width=width, seed=s, device=device)[0]
+        sets.append((joints, pred, tinv))
+    return sets
+
+
+def time_ops(device, height, width, persons, batch, peak_gbs):
+    """Per-op persons/s and roofline fraction (CUDA events around each launch, distinct buffers)."""
+    from simple_pose_b200.pipeline import HeatmapHotPath, ALGO_BYTES
+    from simple_pose_b200 import synth
+    nb = max(1, persons // batch)
+    sets = make_inputs(nb * batch, batch, height, width, device, seed=50)
+    flips = [synth.heatmaps(batch, height=height, width=width, seed=900 + i, noise=0.01, device=device) for i in range(nb)]
+    paths = [HeatmapHotPath(batch, 17, height, width, device=device) for _ in range(nb)]
+    perm = paths[0].decoder._perm_on(device, 17, None)
+    ops = {
+        "encode": lambda i: paths[i].encode(sets[i][0]),
+        "loss": lambda i: paths[i].loss_fwd_bwd(sets[i][1]),
+        "decode": lambda i: paths[i].decode(sets[i][1], sets[i][2]),
+        "flip_decode": lambda i: paths[i].decode(sets[i][1], sets[i][2], flips[i], perm),
+    }
+    out = {}
+    for name, fn in ops.items():
+        for i in range(nb):
+            fn(i)
+        torch.cuda.synchronize(device)
+        times = []
+        for _ in range(3):
+            evs = []
+            for i in range(nb):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(i)
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize(device)
+            times.extend(a.elapsed_time(b) for a, b in evs)
+        ms = statistics.median(times)
+        bytes_per_launch = ALGO_BYTES[name](17, height, width) * batch
+        gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+        out[name] = {"persons_per_s": batch / (ms * 1e-3), "ms_per_launch": ms, "GBps": gbs, "frac": gbs / peak_gbs}
+    del paths, sets, flips
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from simple_pose_b200 import _abi
+    from simple_pose_b200.pipeline import HeatmapHotPath, ALGO_BYTES
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _abi.lib()
+    peak_gbs, peak_src = hbm_peak()
+    H, W, P, B = args.height, args.width, args.persons, args.batch
+    P = max(B, (P // B) * B)
+    nb = P // B
+
+    sets = make_inputs(P, B, H, W, device, seed=rank * 7919)
+    paths = [HeatmapHotPath(B, 17, H, W, device=device) for _ in range(nb)]      # distinct outputs per batch
+    kp_local = torch.empty((P, 17, 3), dtype=torch.float32, device=device)
+    kp_all = torch.empty((world * P, 17, 3), dtype=torch.float32, device=device) if world > 1 else None
+    op_events = {"encode": [], "loss": [], "decode": []}
+
+    def step(record):
+        for i in range(nb):
+            joints, pred, tinv = sets[i]
+            hp = paths[i]
+            if record:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e[0].record()
+                hp.encode(joints)
+                e[1].record()
+                hp.loss_fwd_bwd(pred)
+                e[2].record()
+                hp.decode(pred, tinv)
+                e[3].record()
+                op_events["encode"].append((e[0], e[1]))
+                op_events["loss"].append((e[1], e[2]))
+                op_events["decode"].append((e[2], e[3]))
+            else:
+                hp.step(joints, pred, tinv)
+            if world > 1:
+                kp_local[i * B:(i + 1) * B, :, :2].copy_(hp.coords)
+                kp_local[i * B:(i + 1) * B, :, 2:].copy_(hp.maxval)
+        if world > 1:
+            dist.all_gather_into_tensor(kp_all, kp_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+    t_end.record()
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * P / (ms_per_step * 1e-3)
+
+    # per-kernel durations measured live inside the timed region
+    op_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in op_events.items()}
+    dominant = max(op_ms, key=op_ms.get)
+    dom_bytes = ALGO_BYTES[dominant](17, H, W) * B
+    achieved = dom_bytes / (op_ms[dominant] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": op_ms[dominant],
+                "share_of_step": op_ms[dominant] / sum(op_ms.values()),
+                "all_kernels": {k: {"ms_per_launch": op_ms[k],
+                                    "GBps": ALGO_BYTES[k](17, H, W) * B / (op_ms[k] * 1e-3) / 1e9,
+                                    "frac": ALGO_BYTES[k](17, H, W) * B / (op_ms[k] * 1e-3) / 1e9 / peak_gbs}
+                                for k in op_ms}}
+
+    # end to end through the public Python API, host buffers in, host results out
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, device, world, rank, P, B, H, W)
+
+    ops = None
+    if rank == 0 and not args.no_ops and world == 1:
+        del paths, sets
+        torch.cuda.empty_cache()
+        ops = {"64x48": time_ops(device, 64, 48, 8192, 1024, peak_gbs),
+               "96x72": time_ops(device, 96, 72, 4096, 512, peak_gbs)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        r = cpu_reference_rates(args.cpu_sample, H, W, cores, reps=3, encode_workers=1)
+        cpu = {"value": r["step"], "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d persons, best of 3: encode %.0f/s (1 core, Python loop), loss fwd+bwd %.0f/s and decode "
+                         "%.0f/s (ATen, %d threads)" % (args.cpu_sample, r["encode"], r["loss"], r["decode"], cores),
+               "per_op": {k: r[k] for k in ("encode", "loss", "decode")}}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2+cfg1 fused step: DarkPose encode + masked-MSE fwd/bwd + GaussTaylor decode "
+                               "(+ NCCL all-gather of keypoints when N>1), K=17, %dx%d" % (H, W),
+                   "persons_per_gpu_per_step": P, "persons_per_launch": B,
+                   "l2": "inputs larger than L2: %d distinct buffer sets, %.0f MB touched per step per GPU" %
+                         (nb, P * (ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)) / 1e6),
+                   "parallelism": "persons sharded, dp%d" % world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
+        "roofline": roofline, "cpu_baseline": cpu, "ops": ops,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, device, world, rank, P, B, H, W):
+    """Same step through the public API with HOST buffers: per batch, H2D of joints, predicted
+    heatmaps and affines from pinned memory on a copy stream (double-buffered against compute),
+    then encode/loss/decode, then D2H of the loss and the keypoints."""
+    import torch.distributed as dist
+    from simple_pose_b200 import synth
+    from simple_pose_b200.commons.transforms import encode_heat_maps
+    from simple_pose_b200.metrics.pose_metrics import GaussTaylorKeyPointDecoder
+    from simple_pose_b200.processors.loss import JointsMSELoss
+
+    nb = P // B
+    # host inputs (pinned). One batch of heatmaps is generated on the device and replicated on
+    # the host side with a cheap perturbation so that host memory holds P distinct persons.
+    h_joints = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    h_pred = torch.empty((P, 17, H, W), dtype=torch.float32).pin_memory()
+    h_tinv = torch.empty((P, 2, 3), dtype=torch.float32).pin_memory()
+    for i in range(nb):
+        s = 31 + 1000 * i + rank
+        h_joints[i * B:(i + 1) * B].copy_(synth.joints(B, height=H, width=W, seed=s, device=device))
+        h_pred[i * B:(i + 1) * B].copy_(synth.heatmaps(B, height=H, width=W, seed=s, device=device))
+        h_tinv[i * B:(i + 1) * B].copy_(synth.inverse_affines(B, height=H, width=W, seed=s, device=device)[0])
+    h_kp = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    h_loss = torch.empty((nb,), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize(device)
+
+    dec = GaussTaylorKeyPointDecoder()
+    crit = JointsMSELoss()
+    copy_stream = torch.cuda.Stream(device)
+    compute = torch.cuda.current_stream(device)
+    slots = [dict(j=torch.empty((B, 17, 3), device=device), p=torch.empty((B, 17, H, W), device=device),
+                  t=torch.empty((B, 2, 3), device=device), ready=torch.cuda.Event(), free=torch.cuda.Event())
+             for _ in range(2)]
+
+    def upload(i):
+        s = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(s["free"])
+            s["j"].copy_(h_joints[i * B:(i + 1) * B], non_blocking=True)
+            s["p"].copy_(h_pred[i * B:(i + 1) * B], non_blocking=True)
+            s["t"].copy_(h_tinv[i * B:(i + 1) * B], non_blocking=True)
+            s["ready"].record(copy_stream)
+
+    def step():
+        upload(0)
+        for i in range(nb):
+            if i + 1 < nb:
+                upload(i + 1)
+            s = slots[i % 2]
+            compute.wait_event(s["ready"])
+            targets, weights = encode_heat_maps(s["j"])
+            pred = s["p"].requires_grad_(True)
+            loss = crit(pred, targets, weights)
+            loss.backward()                                   # grad stays on the device (feeds the backbone)
+            xy, conf = dec(pred.detach(), s["t"])
+            pred.grad = None
+            s["p"].requires_grad_(False)
+            h_kp[i * B:(i + 1) * B, :, :2].copy_(xy, non_blocking=True)
+            h_kp[i * B:(i + 1) * B, :, 2:].copy_(conf, non_blocking=True)
+            h_loss[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            s["free"].record(compute)
+        torch.cuda.synchronize(device)
+        return float(h_loss.sum())
+
+    for s in slots:
+        s["free"].record(compute)
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = P * (17 * 3 * 4 + 17 * H * W * 4 + 24)
+    d2h = P * 17 * 3 * 4 + nb * 4
+    return {"value": world * P * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "note": "public API (encode_heat_maps, JointsMSELoss+backward, GaussTaylorKeyPointDecoder) on pinned host "
+                    "inputs incl. the predicted heatmaps; PCIe-bound"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

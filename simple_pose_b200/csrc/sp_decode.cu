@@ -433,8 +433,8 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
                              const float* trans_inv, const float* blur_w,
                              float* coords, float* maxval, int* argmax,
                              int B, int K, int H, int W, int ksize, int mode, void* stream) {
-    SP_RETURN_IF(!hm || !coords || !maxval, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B > 0 && (!hm || !coords || !maxval), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_BASIC, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(hm_flip && !perm, SP_ERR_BAD_ARGUMENT);
     if (mode == SP_DECODE_GAUSS_TAYLOR) {
@@ -444,8 +444,8 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
         ksize = 0;
     }
     SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
-    SP_RETURN_IF(!sp_aligned16(coords), SP_ERR_BAD_ALIGNMENT);
     if (B == 0) return 0;
+    SP_RETURN_IF(!sp_aligned16(coords), SP_ERR_BAD_ALIGNMENT);
 
     DecodeArgs A;
     A.hm = hm; A.hm_flip = hm_flip; A.perm = perm; A.trans_inv = trans_inv; A.blur_w = blur_w;

@@ -115,8 +115,8 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
 
 extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights,
                              int B, int K, int H, int W, double sigma, void* stream) {
-    SP_RETURN_IF(!joints || !targets || !weights, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B > 0 && (!joints || !targets || !weights), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
     if (B == 0) return 0;
     const int nmaps = B * K;

@@ -1,0 +1,67 @@
+"""The hot path as one object: encode -> masked-MSE fwd/bwd -> decode over a batch of persons.
+
+This is the call a training/eval loop makes per batch once the backbone has produced
+``pred``; it is what ``bench.py`` times and what ``eval_shard.py`` runs per rank. Outputs are
+pre-allocated once (the library itself never allocates device memory).
+"""
+import torch
+
+from . import _abi
+from .metrics.pose_metrics import GaussTaylorKeyPointDecoder
+from .processors.loss import _workspace
+
+ALGO_BYTES = {
+    # algorithmic bytes per person, K joints, H x W float32 maps
+    "encode": lambda k, h, w: k * h * w * 4 + k * 4 + k * 12,
+    "loss": lambda k, h, w: 3 * k * h * w * 4 + k * 4,
+    "decode": lambda k, h, w: k * h * w * 4 + 24 + k * 12,
+    "flip_decode": lambda k, h, w: 2 * k * h * w * 4 + 24 + k * 12,
+}
+
+
+class HeatmapHotPath(object):
+    """Pre-allocated buffers + raw ABI calls for one batch shape on one device."""
+
+    def __init__(self, batch, joints=17, height=64, width=48, sigma=2.0, device=None, kernel_size=11):
+        self.device = torch.device(device) if device is not None else _abi.default_device()
+        self.batch, self.k, self.h, self.w = int(batch), int(joints), int(height), int(width)
+        self.sigma = float(sigma)
+        dev = self.device
+        self.targets = torch.empty((self.batch, self.k, self.h, self.w), dtype=torch.float32, device=dev)
+        self.weights = torch.empty((self.batch, self.k), dtype=torch.float32, device=dev)
+        self.grad = torch.empty_like(self.targets)
+        self.loss = torch.empty((), dtype=torch.float32, device=dev)
+        self.coords = torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=dev)
+        self.maxval = torch.empty((self.batch, self.k, 1), dtype=torch.float32, device=dev)
+        self.decoder = GaussTaylorKeyPointDecoder(kernel_size, joints)
+        self.blur_w = self.decoder._weights_on(dev)
+        self.ksize = int(kernel_size)
+        self._lib = _abi.lib()
+
+    # each method enqueues exactly one kernel on the current stream of self.device
+    def encode(self, joints):
+        _abi.check(self._lib.sp_encode_f32(joints.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
+                                           self.batch, self.k, self.h, self.w, self.sigma,
+                                           _abi.stream_ptr(self.device)))
+
+    def loss_fwd_bwd(self, pred):
+        stream = _abi.stream_ptr(self.device)
+        ws = _workspace(self.device, stream)
+        _abi.check(self._lib.sp_mse_fwd_bwd_f32(pred.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
+                                                self.grad.data_ptr(), self.loss.data_ptr(), ws.data_ptr(),
+                                                ws.numel() * 8, self.batch, self.k, self.h * self.w, 1.0, 0, stream))
+
+    def decode(self, pred, trans_inv, pred_flip=None, perm=None):
+        _abi.check(self._lib.sp_decode_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
+                                           _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
+                                           self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
+                                           self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, _abi.stream_ptr(self.device)))
+
+    def step(self, joints, pred, trans_inv):
+        """encode(joints) -> loss/grad(pred, targets, weights) -> decode(pred). 3 launches."""
+        self.encode(joints)
+        self.loss_fwd_bwd(pred)
+        self.decode(pred, trans_inv)
+        return self.loss, self.coords, self.maxval
+
+    LAUNCHES_PER_STEP = 3

