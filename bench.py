@@ -41,8 +41,8 @@ FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.jso
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--persons", type=int, default=8192, help="persons per GPU per step")
     ap.add_argument("--batch", type=int, default=1024, help="persons per kernel launch")
@@ -224,16 +224,14 @@ def time_ops(device, height, width, persons, batch, peak_gbs):
             fn(i)
         torch.cuda.synchronize(device)
         times = []
-        for _ in range(3):
-            evs = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
             for i in range(nb):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
                 fn(i)
-                b.record()
-                evs.append((a, b))
-            torch.cuda.synchronize(device)
-            times.extend(a.elapsed_time(b) for a, b in evs)
+            b.record()
+            b.synchronize()
+            times.append(a.elapsed_time(b) / nb)
         ms = statistics.median(times)
         bytes_per_launch = ALGO_BYTES[name](17, height, width) * batch
         gbs = bytes_per_launch / (ms * 1e-3) / 1e9
@@ -267,26 +265,11 @@ def run_ours(args):
     paths = [HeatmapHotPath(B, 17, H, W, device=device) for _ in range(nb)]      # distinct outputs per batch
     kp_local = torch.empty((P, 17, 3), dtype=torch.float32, device=device)
     kp_all = torch.empty((world * P, 17, 3), dtype=torch.float32, device=device) if world > 1 else None
-    op_events = {"encode": [], "loss": [], "decode": []}
-
-    def step(record):
+    def step():
         for i in range(nb):
             joints, pred, tinv = sets[i]
             hp = paths[i]
-            if record:
-                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                e[0].record()
-                hp.encode(joints)
-                e[1].record()
-                hp.loss_fwd_bwd(pred)
-                e[2].record()
-                hp.decode(pred, tinv)
-                e[3].record()
-                op_events["encode"].append((e[0], e[1]))
-                op_events["loss"].append((e[1], e[2]))
-                op_events["decode"].append((e[2], e[3]))
-            else:
-                hp.step(joints, pred, tinv)
+            hp.step(joints, pred, tinv)
             if world > 1:
                 kp_local[i * B:(i + 1) * B, :, :2].copy_(hp.coords)
                 kp_local[i * B:(i + 1) * B, :, 2:].copy_(hp.maxval)
@@ -298,8 +281,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def kernel_ms(fn, rounds):
+        """Average launch duration of one kernel: CUDA events around nb back-to-back launches
+        (one per distinct buffer set) on the launching stream, averaged over `rounds`."""
+        tot = 0.0
+        for _ in range(rounds):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(nb):
+                fn(i)
+            b.record()
+            b.synchronize()
+            tot += a.elapsed_time(b) / nb
+        return tot / rounds
+
     for _ in range(max(3, args.warmup)):
-        step(False)
+        step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -308,10 +305,15 @@ def run_ours(args):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):
-        step(True)
+        step()
     t_end.record()
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
+    # per-kernel durations, still under the clock sampler
+    rounds = max(3, min(20, args.steps))
+    op_ms = {"encode": kernel_ms(lambda i: paths[i].encode(sets[i][0]), rounds),
+             "loss": kernel_ms(lambda i: paths[i].loss_fwd_bwd(sets[i][1]), rounds),
+             "decode": kernel_ms(lambda i: paths[i].decode(sets[i][1], sets[i][2]), rounds)}
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -320,8 +322,6 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = world * P / (ms_per_step * 1e-3)
 
-    # per-kernel durations measured live inside the timed region
-    op_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in op_events.items()}
     dominant = max(op_ms, key=op_ms.get)
     dom_bytes = ALGO_BYTES[dominant](17, H, W) * B
     achieved = dom_bytes / (op_ms[dominant] * 1e-3) / 1e9

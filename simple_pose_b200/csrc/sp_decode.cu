@@ -62,6 +62,20 @@ struct Peak {
 };
 
 // ---------------------------------------------------------------------------------------------
+// warp-wide min/max in one instruction (redux.sync.*.f32, sm_100a; SASS CREDUX)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_min_f32(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // argmax of a map that is resident in shared (fast path) or global (generic path) memory
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ Peak warp_best(float v, int i) {
@@ -75,19 +89,6 @@ __device__ __forceinline__ Peak warp_best(float v, int i) {
     p.value = v;
     p.index = i;
     return p;
-}
-
-// exact scalar scan (torch.max semantics incl. NaN); used by the generic path and as the
-// fallback of the vector scan
-template <typename View>
-__device__ __forceinline__ Peak argmax_exact(const View& map, int hw, int lane) {
-    float bv = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < hw; i += 32) {
-        const float v = map.at(i);
-        if (sp::better(v, i, bv, bi)) { bv = v; bi = i; }
-    }
-    return warp_best(bv, bi);
 }
 
 struct DirectView {
@@ -105,6 +106,19 @@ struct FlipAvgView {
         return __fmul_rn(0.5f, __fadd_rn(a[i], b[y * W + (W - 1 - x)]));
     }
 };
+
+// exact scalar scan (torch.max semantics incl. NaN); used by the generic path and as the
+// fallback of the vector scan
+template <typename View>
+__device__ __noinline__ Peak argmax_exact(const View map, int hw, int lane) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < hw; i += 32) {
+        const float v = map.at(i);
+        if (sp::better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    return warp_best(bv, bi);
+}
 
 // Vector scan over a shared-memory map (hw % 4 == 0). If FLIP, first folds the mirrored partner
 // map into `a` in place (W % 4 == 0 so the mirror of an aligned quad is an aligned quad).
@@ -147,27 +161,23 @@ __device__ __forceinline__ Peak argmax_smem(float* a, const float* b, int hw, in
         DirectView view{a};
         return argmax_exact(view, hw, lane);
     }
-    // (value, quad) butterfly: larger value, then smaller quad index
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(SP_FULL, best, o);
-        const int oq = __shfl_xor_sync(SP_FULL, bq, o);
-        if (ov > best || (ov == best && oq < bq)) { best = ov; bq = oq; }
-    }
-    const float4 w = a4[bq];            // broadcast read; first lane of the quad equal to the max
-    const int sub = (w.x == best) ? 0 : (w.y == best) ? 1 : (w.z == best) ? 2 : 3;
+    // all values finite: warp max in one CREDUX, then the smallest quad index that attains it
+    const float gmax = warp_max_f32(best);
+    const unsigned gq = __reduce_min_sync(SP_FULL, (best == gmax) ? (unsigned)bq : 0x7fffffffu);
+    const float4 w = a4[gq];            // broadcast read; first element of the quad equal to the max
+    const int sub = (w.x == gmax) ? 0 : (w.y == gmax) ? 1 : (w.z == gmax) ? 2 : 3;
     Peak p;
     p.value = (sub == 0) ? w.x : (sub == 1) ? w.y : (sub == 2) ? w.z : w.w;   // keeps the sign of a zero
-    p.index = 4 * bq + sub;
+    p.index = 4 * (int)gq + sub;
     return p;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Taylor refinement around an interior peak. All lanes return the same values.
 // ---------------------------------------------------------------------------------------------
+// exact slow path: max over the whole zero-padded blurred map of this joint
 template <typename View>
-__device__ float full_blur_max(const View& map, const float* w, int H, int W, int ks, int lane) {
-    // exact slow path: max over the whole zero-padded blurred map of this joint
+__device__ __noinline__ float full_blur_max(const View map, const float* w, int H, int W, int ks, int lane) {
     const int r = ks >> 1;
     float best = -CUDART_INF_F;
     bool seen_nan = false;
@@ -192,22 +202,53 @@ __device__ float full_blur_max(const View& map, const float* w, int H, int W, in
     return best;
 }
 
+// log of one blurred stencil value on the exact path: log(clamp(blur * ori_max / blur_max, 1e-10))
+__device__ __forceinline__ float exact_log(float blur, float ori_max, float bmax) {
+    const float v = __fdiv_rn(__fmul_rn(blur, ori_max), bmax);
+    return logf((v != v) ? v : fmaxf(v, 1e-10f));            // torch.clamp(min=) keeps NaN
+}
+
+// finite differences + 2x2 solve, same operation order as pose_metrics.py:80-100
+__device__ __forceinline__ bool taylor_step(const float (&L)[kStencil], float& ox, float& oy) {
+    const float dx = __fmul_rn(0.5f, __fsub_rn(L[S_XP1], L[S_XM1]));
+    const float dy = __fmul_rn(0.5f, __fsub_rn(L[S_YP1], L[S_YM1]));
+    const float c2 = __fmul_rn(2.f, L[S_C]);
+    const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_XP2], c2), L[S_XM2]));
+    const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_YP2], c2), L[S_YM2]));
+    const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(L[S_PP], L[S_MP]), L[S_PM]), L[S_MM]));
+    const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
+    if (!(det != 0.f)) return false;                          // det == 0 -> skip; NaN != 0 is true, as in torch
+    const float inv = __fdiv_rn(1.f, det);                    // offset = -H^-1 g, H = [[dxx, dxy], [dxy, dyy]]
+    ox = -__fmul_rn(__fsub_rn(__fmul_rn(dyy, dx), __fmul_rn(dxy, dy)), inv);
+    oy = -__fmul_rn(__fsub_rn(__fmul_rn(dxx, dy), __fmul_rn(dxy, dx)), inv);
+    return true;
+}
+
+// Which of the three cases of the file header applies. Returns 0 = clamp cannot fire (drop the
+// common factor), 1 = exact path with blur_max, 2 = every log equals log(1e-10) -> not refined.
 template <typename View>
-__device__ __forceinline__ void taylor_refine(const View& map, const float* wts, float* patch, int H, int W,
-                                              int ks, int px, int py, float ori_max, int lane, float& ox, float& oy,
-                                              bool& refined) {
+__device__ __forceinline__ int clamp_case(const View& map, const float* wts, int H, int W, int ks, int lane,
+                                          float lo, float hi, bool any_nan, float ori_max, float& bmax) {
+    if (!any_nan && lo >= 2e-10f) return 0;
+    bmax = full_blur_max(map, wts, H, W, ks, lane);
+    if (!any_nan && hi <= 0.f && ori_max > 0.f && bmax > 0.f) return 2;
+    return 1;
+}
+
+// ---- generic kernel size (runtime ks), any memory space -------------------------------------
+template <typename View>
+__device__ __noinline__ bool taylor_refine_generic(const View map, const float* wts, float* patch, int H, int W,
+                                                   int ks, int px, int py, float ori_max, int lane, float& ox, float& oy) {
     const int r = ks >> 1;
     const int P = ks + 4;               // patch side: blur radius + stencil radius 2 on each side
     const int pr = r + 2;
-    // zero-padded patch of the raw map around the peak
     __syncwarp();
-    for (int e = lane; e < P * P; e += 32) {
+    for (int e = lane; e < P * P; e += 32) {   // zero-padded patch of the raw map around the peak
         const int ry = e / P, rx = e - ry * P;
         const int yy = py + ry - pr, xx = px + rx - pr;
         patch[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? map.at(yy * W + xx) : 0.f;
     }
     __syncwarp();
-    // blur at the 13 stencil points: taps are split across lanes, then butterfly sums
     constexpr int kStencilDy[kStencil] = SP_STENCIL_DY;
     constexpr int kStencilDx[kStencil] = SP_STENCIL_DX;
     float acc[kStencil];
@@ -226,69 +267,149 @@ __device__ __forceinline__ void taylor_refine(const View& map, const float* wts,
         for (int s = 0; s < kStencil; ++s) acc[s] += __shfl_xor_sync(SP_FULL, acc[s], o);
     }
     float lo = acc[0], hi = acc[0];
-#pragma unroll
-    for (int s = 1; s < kStencil; ++s) { lo = fminf(lo, acc[s]); hi = fmaxf(hi, acc[s]); }
     bool any_nan = false;
 #pragma unroll
-    for (int s = 0; s < kStencil; ++s) any_nan |= (acc[s] != acc[s]);
-
+    for (int s = 0; s < kStencil; ++s) {
+        lo = fminf(lo, acc[s]);
+        hi = fmaxf(hi, acc[s]);
+        any_nan |= (acc[s] != acc[s]);
+    }
+    float bmax = 1.f;
+    const int which = clamp_case(map, wts, H, W, ks, lane, lo, hi, any_nan, ori_max, bmax);
+    if (which == 2) return false;
     float L[kStencil];
-    if (!any_nan && lo >= 2e-10f) {
-        // clamp cannot fire (scale >= 1 - 1e-5): the common factor cancels in the differences
 #pragma unroll
-        for (int s = 0; s < kStencil; ++s) L[s] = logf(acc[s]);
-    } else if (!any_nan && hi <= 0.f && ori_max > 0.f) {
-        // blur_max > 0 would be needed for a positive scale; with every stencil value <= 0 and a
-        // positive scale all 13 logs equal log(1e-10) -> det == 0 -> not refined. A non-positive
-        // blur_max flips signs, so that sub-case still goes through the exact path below.
-        const float bmax = full_blur_max(map, wts, H, W, ks, lane);
-        if (bmax > 0.f) { refined = false; return; }
+    for (int s = 0; s < kStencil; ++s) L[s] = (which == 0) ? logf(acc[s]) : exact_log(acc[s], ori_max, bmax);
+    return taylor_step(L, ox, oy);
+}
+
+// ---- KS x KS kernel known at compile time, map in shared memory ------------------------------
+// Per-lane share of the KS*KS taps: weights and (row+2, col+2) offsets, set up once per kernel.
+template <int KS>
+struct LaneTaps {
+    static constexpr int N = (KS * KS + 31) / 32;
+    float w[N];
+    int ty2[N], tx2[N];
+    __device__ __forceinline__ void load(const float* wts, int lane) {
 #pragma unroll
-        for (int s = 0; s < kStencil; ++s) L[s] = logf(fmaxf(__fdiv_rn(__fmul_rn(acc[s], ori_max), bmax), 1e-10f));
-    } else {
-        const float bmax = full_blur_max(map, wts, H, W, ks, lane);
-#pragma unroll
-        for (int s = 0; s < kStencil; ++s) {
-            const float v = __fdiv_rn(__fmul_rn(acc[s], ori_max), bmax);
-            // torch.clamp(min=) keeps NaN
-            L[s] = logf((v != v) ? v : fmaxf(v, 1e-10f));
+        for (int j = 0; j < N; ++j) {
+            const int t = lane + 32 * j;
+            const bool real = t < KS * KS;
+            const int tt = real ? t : 0;
+            w[j] = real ? wts[tt] : 0.f;
+            ty2[j] = tt / KS + 2;
+            tx2[j] = tt % KS + 2;
         }
     }
-    // finite differences, same operation order as pose_metrics.py:80-93
-    const float dx = __fmul_rn(0.5f, __fsub_rn(L[S_XP1], L[S_XM1]));
-    const float dy = __fmul_rn(0.5f, __fsub_rn(L[S_YP1], L[S_YM1]));
-    const float c2 = __fmul_rn(2.f, L[S_C]);
-    const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_XP2], c2), L[S_XM2]));
-    const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L[S_YP2], c2), L[S_YM2]));
-    const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(L[S_PP], L[S_MP]), L[S_PM]), L[S_MM]));
-    const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
-    if (!(det != 0.f)) { refined = false; return; }     // det == 0 -> skip; NaN != 0 is true, as in torch
-    // offset = -H^-1 g, H = [[dxx, dxy], [dxy, dyy]]
-    const float inv = __fdiv_rn(1.f, det);
-    ox = -__fmul_rn(__fsub_rn(__fmul_rn(dyy, dx), __fmul_rn(dxy, dy)), inv);
-    oy = -__fmul_rn(__fsub_rn(__fmul_rn(dxx, dy), __fmul_rn(dxy, dx)), inv);
-    refined = true;
+};
+
+// Sum 13 per-lane partials across the warp so that lane 16*b4 + 2*local (+1) ends up holding the
+// total of slot s = 7*b4 + local: recursive halving, 7+4+2+1+1 = 15 shuffles instead of 65.
+__device__ __forceinline__ float reduce_scatter13(float (&v)[kStencil], int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4, up2 = lane & 2;
+    float a[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const float hi = (j + 7 < kStencil) ? v[j + 7] : 0.f;
+        const float send = up16 ? v[j] : hi;
+        const float keep = up16 ? hi : v[j];
+        a[j] = keep + __shfl_xor_sync(SP_FULL, send, 16);
+    }
+    float b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float hi = (j + 4 < 7) ? a[j + 4] : 0.f;
+        const float send = up8 ? a[j] : hi;
+        const float keep = up8 ? hi : a[j];
+        b[j] = keep + __shfl_xor_sync(SP_FULL, send, 8);
+    }
+    float c[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = up4 ? b[j] : b[j + 2];
+        const float keep = up4 ? b[j + 2] : b[j];
+        c[j] = keep + __shfl_xor_sync(SP_FULL, send, 4);
+    }
+    const float send = up2 ? c[0] : c[1];
+    const float keep = up2 ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(SP_FULL, send, 2);
+    d += __shfl_xor_sync(SP_FULL, d, 1);
+    return d;
+}
+__device__ __forceinline__ int slot_of_lane(int lane) { return 7 * (lane >> 4) + ((lane >> 1) & 7); }
+__device__ __forceinline__ bool lane_has_slot(int lane) { return ((lane >> 1) & 7) < ((lane & 16) ? 6 : 7); }
+__device__ __forceinline__ constexpr int lane_of_slot(int s) { return (s >= 7) ? 16 + 2 * (s - 7) : 2 * s; }
+
+template <int KS>
+__device__ __forceinline__ bool taylor_refine_smem(const float* map, const float* wts, float* patch,
+                                                   const LaneTaps<KS>& taps, int H, int W, int px, int py,
+                                                   float ori_max, int lane, float& ox, float& oy) {
+    constexpr int R = KS / 2, P = KS + 4, PR = R + 2;
+    // All 13 windows inside the map (the common case): read the map in place. Otherwise build a
+    // zero-padded P x P patch of the raw map around the peak and read that.
+    const float* org;
+    int stride;
+    if (px >= PR && px + PR < W && py >= PR && py + PR < H) {
+        org = map + (py - PR) * W + (px - PR);
+        stride = W;
+    } else {
+        __syncwarp();
+        for (int e = lane; e < P * P; e += 32) {
+            const int ry = e / P, rx = e - ry * P;
+            const int yy = py + ry - PR, xx = px + rx - PR;
+            patch[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? map[yy * W + xx] : 0.f;
+        }
+        __syncwarp();
+        org = patch;
+        stride = P;
+    }
+    constexpr int kStencilDy[kStencil] = SP_STENCIL_DY;
+    constexpr int kStencilDx[kStencil] = SP_STENCIL_DX;
+    float acc[kStencil];
+#pragma unroll
+    for (int s = 0; s < kStencil; ++s) acc[s] = 0.f;
+#pragma unroll
+    for (int j = 0; j < LaneTaps<KS>::N; ++j) {
+        if (j + 1 < LaneTaps<KS>::N || lane + 32 * j < KS * KS) {      // only the last round is ragged
+            const float* base = org + taps.ty2[j] * stride + taps.tx2[j];
+            const float wv = taps.w[j];
+#pragma unroll
+            for (int s = 0; s < kStencil; ++s) acc[s] = fmaf(wv, base[kStencilDy[s] * stride + kStencilDx[s]], acc[s]);
+        }
+    }
+    const float mine = reduce_scatter13(acc, lane);          // blurred value of this lane's stencil slot
+    const bool own = lane_has_slot(lane);
+    const bool any_nan = __any_sync(SP_FULL, own && (mine != mine));
+    const float lo = warp_min_f32(own ? mine : CUDART_INF_F);
+    const float hi = warp_max_f32(own ? mine : -CUDART_INF_F);
+    float bmax = 1.f;
+    DirectView view{map};
+    const int which = clamp_case(view, wts, H, W, KS, lane, lo, hi, any_nan, ori_max, bmax);
+    if (which == 2) return false;
+    const float mylog = (which == 0) ? logf(mine) : exact_log(mine, ori_max, bmax);   // one log per lane
+    float L[kStencil];
+#pragma unroll
+    for (int s = 0; s < kStencil; ++s) L[s] = __shfl_sync(SP_FULL, mylog, lane_of_slot(s));
+    return taylor_step(L, ox, oy);
 }
 
 // ---------------------------------------------------------------------------------------------
 // everything after the argmax: coordinates, refinement, affine, stores
 // ---------------------------------------------------------------------------------------------
-template <typename View>
-__device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map, const float* wts, float* patch,
-                                           int m, Peak pk, int lane) {
+template <typename View, typename Refine>
+__device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map, int m, Peak pk, int lane,
+                                           Refine&& refine) {
     const int W = A.W, H = A.H;
     const bool positive = pk.value > 0.f;                 // false for NaN, like (max_val > 0.)
-    const int ix = positive ? pk.index % W : 0;
     const int iy = positive ? pk.index / W : 0;
+    const int ix = positive ? pk.index - iy * W : 0;
     float x = (float)ix, y = (float)iy;
 
     if (A.mode == SP_DECODE_GAUSS_TAYLOR) {
         const bool inner = (ix > 1) && (ix < W - 2) && (iy > 1) && (iy < H - 2);
         if (inner) {
             float ox = 0.f, oy = 0.f;
-            bool refined = false;
-            taylor_refine(map, wts, patch, H, W, A.ksize, ix, iy, pk.value, lane, ox, oy, refined);
-            if (refined) {
+            if (refine(ix, iy, pk.value, ox, oy)) {
                 const float nx = __fadd_rn(x, ox), ny = __fadd_rn(y, oy);
                 x = (nx < 0.f) ? 0.f : nx;                // clamp(min=0) that keeps NaN
                 y = (ny < 0.f) ? 0.f : ny;
@@ -330,7 +451,8 @@ constexpr int kBarBytes = 1024;
 constexpr int kWtsBytes = 1024;
 constexpr int kPatchBytes = 1536;
 
-template <bool FLIP>
+// KS = compile-time blur size (11 = the reference's), 0 = runtime A.ksize
+template <bool FLIP, int KS>
 __global__ void __launch_bounds__(512, 1)
 decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -353,6 +475,8 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         sp::mbar_fence_init();
     }
     __syncthreads();
+    LaneTaps<(KS > 0 ? KS : 3)> taps;
+    if (KS > 0 && A.mode == SP_DECODE_GAUSS_TAYLOR) taps.load(wts, lane);
 
     const int gw = blockIdx.x * nwarps + warp;
     const int total = gridDim.x * nwarps;
@@ -374,21 +498,24 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
             if (m < A.nmaps) issue(s, m);
         }
     }
-    int it = 0;
-    for (int m = gw; m < A.nmaps; m += total, ++it) {
-        const int s = it % stages;
-        const uint32_t parity = (uint32_t)(it / stages) & 1u;
+    int s = 0;
+    uint32_t parity = 0;
+    for (int m = gw; m < A.nmaps; m += total) {
         sp::mbar_wait(bars + s, parity);
         float* a = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
         const Peak pk = argmax_smem<FLIP>(a, a + hw, hw, A.W, lane);
         DirectView view{a};
-        finish_map(A, view, wts, patch, m, pk, lane);
+        finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+            if (KS > 0) return taylor_refine_smem<(KS > 0 ? KS : 3)>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
+            return taylor_refine_generic(view, wts, patch, A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
+        });
         __syncwarp();
         const int next = m + stages * total;
         if (lane == 0 && next < A.nmaps) {
             sp::fence_proxy_async_smem();
             issue(s, next);
         }
+        if (++s == stages) { s = 0; parity ^= 1u; }
     }
 }
 
@@ -412,11 +539,15 @@ decode_generic_kernel(const DecodeArgs A) {
             const int b = m / A.K, k = m - b * A.K;
             FlipAvgView view{A.hm + (size_t)m * hw, A.hm_flip + (size_t)(b * A.K + __ldg(A.perm + k)) * hw, A.W};
             const Peak pk = argmax_exact(view, hw, lane);
-            finish_map(A, view, wts, patches[warp], m, pk, lane);
+            finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+                return taylor_refine_generic(view, wts, patches[warp], A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
+            });
         } else {
             DirectView view{A.hm + (size_t)m * hw};
             const Peak pk = argmax_exact(view, hw, lane);
-            finish_map(A, view, wts, patches[warp], m, pk, lane);
+            finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+                return taylor_refine_generic(view, wts, patches[warp], A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
+            });
         }
     }
 }
@@ -477,13 +608,15 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
         int grid = sp_sm_count();
         const int need = (A.nmaps + nwarps - 1) / nwarps;
         if (grid > need) grid = need;
-        if (flip) {
-            SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_tma_kernel<true><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);
-        } else {
-            SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_tma_kernel<false><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);
-        }
+#define SP_LAUNCH_DECODE(F, KS)                                                                                     \
+    do {                                                                                                            \
+        SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<F, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        decode_tma_kernel<F, KS><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);                               \
+    } while (0)
+        const bool ks11 = (ksize == 11) && !env_int("SP_DECODE_RUNTIME_KSIZE", 0);
+        if (flip) { if (ks11) SP_LAUNCH_DECODE(true, 11); else SP_LAUNCH_DECODE(true, 0); }
+        else      { if (ks11) SP_LAUNCH_DECODE(false, 11); else SP_LAUNCH_DECODE(false, 0); }
+#undef SP_LAUNCH_DECODE
         return sp_launch_status();
     }
     int grid = sp_sm_count() * 8;

@@ -127,9 +127,9 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     const size_t smem = (size_t)kWarpsPerCta * (wpad + H) * sizeof(double);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     const bool vec4 = (W % 4 == 0) && sp_aligned16(targets);
-    const int ctas_needed = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int max_ctas = sp_sm_count() * 8;        // 8 resident CTAs of 8 warps per SM
-    const int grid = ctas_needed < max_ctas ? ctas_needed : max_ctas;
+    // one map per warp, no persistence: with ~2 maps per resident warp a grid-stride loop leaves a
+    // ragged second wave; letting the hardware backfill 8-map CTAs balances it
+    const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (vec4) {
         if (smem > 48 * 1024)

@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: host-side logic of the multi-GPU eval path (image-aligned
+sharding, ragged all-gather, global ordering). The kernels themselves are covered by -m gpu."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from simple_pose_b200 import eval_shard, synth
+
+
+def test_shard_images_balanced_and_image_aligned():
+    _, _, _, seg = synth.nms_groups(500, mean_group=20.0, seed=1)
+    seg = seg.numpy()
+    for world in (1, 2, 3, 4, 8):
+        cuts = eval_shard.shard_images(seg, world)
+        assert cuts[0] == 0 and cuts[-1] == 500 and np.all(np.diff(cuts) >= 0)
+        counts = [eval_shard.person_range(seg, cuts, r) for r in range(world)]
+        assert counts[0][0] == 0 and counts[-1][1] == seg[-1]
+        for (a, b), (c, d) in zip(counts[:-1], counts[1:]):
+            assert b == c                                    # contiguous, nothing dropped
+        sizes = np.array([b - a for a, b in counts])
+        assert sizes.max() - sizes.min() <= 2 * np.diff(seg).max()      # balanced to within an image or two
+
+
+def test_shard_images_degenerate():
+    assert list(eval_shard.shard_images([0, 5], 4)) == [0, 0, 0, 0, 1] or list(eval_shard.shard_images([0, 5], 4))[-1] == 1
+    cuts = eval_shard.shard_images([0], 2)
+    assert list(cuts) == [0, 0, 0]
+    cuts = eval_shard.shard_images([0, 0, 0, 7, 7], 2)
+    assert cuts[-1] == 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, seg, table, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cuts = eval_shard.shard_images(seg, world)
+        lo, hi = eval_shard.person_range(seg, cuts, rank)
+        k = 17
+        coords = table[lo:hi, :, :2].contiguous()
+        conf = table[lo:hi, :, 2:].contiguous()
+        keep = (torch.arange(lo, hi) % 3 == 0).to(torch.uint8)
+        scores = torch.arange(lo, hi, dtype=torch.float64) * 0.5
+        rows = eval_shard.pack_results(coords, conf, keep, scores)
+        counts = [eval_shard.person_range(seg, cuts, r) for r in range(world)]
+        full = eval_shard.gather_rows(rows, [b - a for a, b in counts])
+        out[rank] = full.clone()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ragged_all_gather_over_gloo(world):
+    _, _, _, seg = synth.nms_groups(23, mean_group=6.0, seed=4)
+    seg = seg.numpy()
+    n = int(seg[-1])
+    table = torch.randn(n, 17, 3, generator=torch.Generator().manual_seed(0))
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_worker, args=(world, _free_port(), seg, table, out), nprocs=world, join=True)
+    want = torch.cat([table.reshape(n, 51), (torch.arange(n) % 3 == 0).float()[:, None],
+                      (torch.arange(n, dtype=torch.float64) * 0.5).float()[:, None]], dim=1)
+    for r in range(world):
+        assert torch.equal(out[r], want)                     # every rank holds the global table, in order
