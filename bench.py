@@ -64,6 +64,24 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, height, width, batch):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/r*_traffic.json), if one exists for this exact launch shape; else None."""
+    names = {"encode": "encode_refine_kernel<1>", "loss": "mse_fwd_bwd_kernel<1, 1>", "decode": "decode_tma_kernel<0, 11>"}
+    key = "%s @ %dx%d,P=%d" % (names.get(kernel, kernel), height, width, batch)
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json"))
+        for f in reversed(files):
+            with open(os.path.join(pdir, f)) as fh:
+                table = json.load(fh)
+            if key in table:
+                return table[key]["dram_bytes_per_launch"], f
+    except Exception:
+        pass
+    return None, None
+
+
 # ------------------------------------------------------------------------------- clocks sampler
 class ClockSampler(object):
     """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
@@ -120,42 +138,86 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------- reference arm
+def _encode_chunk(args):
+    """Worker body (one DataLoader-worker equivalent): per-person Python/NumPy encode."""
+    from oracle import heatmap_oracle as O
+    joints, width, height = args
+    torch.set_num_threads(1)
+    t, w = O.encode_batch(joints, 2.0, (width, height))
+    return torch.from_numpy(t), torch.from_numpy(w)      # travels back through shared memory
+
+
+class CpuReference(object):
+    """The reference's CPU algorithm for the step (oracle port, pinned bit-exact to the
+    reference): encode = per-person Python/NumPy loop, optionally spread over worker processes
+    the way the reference's DataLoader does (num_workers: 8 in its configs); loss fwd+bwd and
+    decode = ATen on all host threads."""
+
+    def __init__(self, persons, height, width, threads, encode_workers=1):
+        from simple_pose_b200 import synth
+        self.persons, self.h, self.w = persons, height, width
+        torch.set_num_threads(max(1, threads))
+        self.joints = synth.joints(persons, height=height, width=width, seed=0).numpy()
+        self.tinv = synth.inverse_affines(persons, height=height, width=width, seed=0)[0]
+        self.pool = None
+        self.workers = encode_workers
+        if encode_workers > 1:
+            import numpy as np
+            import torch.multiprocessing as mp
+            self.chunks = [(c, width, height) for c in np.array_split(self.joints, encode_workers * 2) if len(c)]
+            self.pool = mp.get_context("fork").Pool(encode_workers)
+        self.targets = self.weights = self.pred = None
+
+    def encode(self):
+        from oracle import heatmap_oracle as O          # CPU baseline leg: the one product-side use
+        if self.pool is not None:
+            parts = self.pool.map(_encode_chunk, self.chunks)
+            self.targets = torch.cat([p[0] for p in parts])
+            self.weights = torch.cat([p[1] for p in parts])
+        else:
+            t, w = O.encode_batch(self.joints, 2.0, (self.w, self.h))
+            self.targets, self.weights = torch.from_numpy(t), torch.from_numpy(w)
+
+    def prepare_pred(self):
+        from simple_pose_b200 import synth
+        if self.targets is None:
+            self.encode()
+        self.pred = synth.predictions_like(self.targets, seed=1)
+
+    def loss(self):
+        from oracle import heatmap_oracle as O
+        return O.masked_mse_loss_and_grad(self.pred, self.targets, self.weights)
+
+    def decode(self):
+        from oracle import heatmap_oracle as O
+        return O.gauss_taylor_decode(self.pred, self.tinv)
+
+    def timed_step(self):
+        t0 = time.perf_counter()
+        self.encode()
+        t1 = time.perf_counter()
+        self.loss()
+        t2 = time.perf_counter()
+        self.decode()
+        t3 = time.perf_counter()
+        return {"encode": t1 - t0, "loss": t2 - t1, "decode": t3 - t2, "step": t3 - t0}
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
 def cpu_reference_rates(persons, height, width, threads, reps=3, encode_workers=1):
-    """persons/s of the reference's CPU algorithm (oracle port) per op on this host.
-
-    encode: the per-person Python/NumPy loop (``encode_workers`` processes, like the reference's
-    DataLoader workers); loss fwd+bwd and decode: ATen on ``threads`` threads."""
-    from oracle import heatmap_oracle as O          # CPU baseline leg: the one product-side use
-    from simple_pose_b200 import synth
-    import numpy as np
-    torch.set_num_threads(max(1, threads))
-    joints = synth.joints(persons, height=height, width=width, seed=0).numpy()
-    tinv = synth.inverse_affines(persons, height=height, width=width, seed=0)[0]
-
-    def best(fn):
-        fn()
-        t = []
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            fn()
-            t.append(time.perf_counter() - t0)
-        return min(t)
-
-    if encode_workers > 1:
-        import multiprocessing as mp
-        chunks = [c for c in np.array_split(joints, encode_workers * 4) if len(c)]
-        with mp.get_context("fork").Pool(encode_workers) as pool:
-            t_enc = best(lambda: pool.starmap(O.encode_batch, [(c, 2.0, (width, height)) for c in chunks]))
-    else:
-        t_enc = best(lambda: O.encode_batch(joints, 2.0, (width, height)))
-    tgt_np, wts_np = O.encode_batch(joints, 2.0, (width, height))
-    tgt, wts = torch.from_numpy(tgt_np), torch.from_numpy(wts_np)
-    pred = synth.predictions_like(tgt, seed=1)
-    t_loss = best(lambda: O.masked_mse_loss_and_grad(pred, tgt, wts))
-    t_dec = best(lambda: O.gauss_taylor_decode(pred, tinv))
-    rates = {"encode": persons / t_enc, "loss": persons / t_loss, "decode": persons / t_dec}
-    rates["step"] = persons / (t_enc + t_loss + t_dec)
-    return rates
+    """persons/s per op and for the whole step (best of `reps` after one warm-up)."""
+    ref = CpuReference(persons, height, width, threads, encode_workers)
+    try:
+        ref.prepare_pred()
+        runs = [ref.timed_step() for _ in range(reps + 1)][1:]
+    finally:
+        ref.close()
+    best = {k: min(r[k] for r in runs) for k in runs[0]}
+    return {k: persons / v for k, v in best.items()}
 
 
 def run_reference(args):
@@ -164,25 +226,37 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     workers = min(cores, 32)
-    sample = args.cpu_sample * 2
-    t0 = time.perf_counter()
-    for _ in range(args.warmup):
-        cpu_reference_rates(min(sample, 64), args.height, args.width, cores, reps=1, encode_workers=1)
-    vals = []
-    for _ in range(args.steps):
-        vals.append(cpu_reference_rates(sample, args.height, args.width, cores, reps=1, encode_workers=workers)["step"])
-        if time.perf_counter() - t0 > 240:
-            break
-    value = statistics.median(vals)
+    sample = args.cpu_sample * 4
+    ref = CpuReference(sample, args.height, args.width, cores, encode_workers=workers)
+    try:
+        ref.prepare_pred()
+        t0 = time.perf_counter()
+        for _ in range(args.warmup):
+            ref.timed_step()
+            if time.perf_counter() - t0 > 60:
+                break
+        times = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            times.append(ref.timed_step())
+            if time.perf_counter() - t0 > 180:
+                break
+    finally:
+        ref.close()
+    total = sum(t["step"] for t in times)
+    value = sample * len(times) / total
+    per_op = {k: sample * len(times) / sum(t[k] for t in times) for k in ("encode", "loss", "decode")}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * sample / value,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "encode + masked-MSE fwd/bwd + GaussTaylor decode, K=17, %dx%d" % (args.height, args.width),
+        "config": {"workload": "cfg2+cfg1 fused step: DarkPose encode + masked-MSE fwd/bwd + GaussTaylor decode, "
+                               "K=17, %dx%d (reference CPU algorithm, bounded sample)" % (args.height, args.width),
                    "sample_persons_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d persons per step; encode in %d worker processes (reference: DataLoader "
-                                   "workers), loss/decode on %d ATen threads" % (sample, workers, cores)},
+                         "sample": "%d persons per step; encode in %d worker processes (the reference's DataLoader "
+                                   "workers), loss fwd+bwd and decode on %d ATen threads; per-op persons/s: encode %.0f, "
+                                   "loss %.0f, decode %.0f" % (sample, workers, cores, per_op["encode"], per_op["loss"], per_op["decode"])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -325,8 +399,9 @@ def run_ours(args):
     dominant = max(op_ms, key=op_ms.get)
     dom_bytes = ALGO_BYTES[dominant](17, H, W) * B
     achieved = dom_bytes / (op_ms[dominant] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dominant, H, W, B)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": op_ms[dominant],
                 "share_of_step": op_ms[dominant] / sum(op_ms.values()),
                 "all_kernels": {k: {"ms_per_launch": op_ms[k],

@@ -64,6 +64,16 @@ int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int sp_encode_f32(const float* joints, float* targets, float* weights,
                   int B, int K, int H, int W, double sigma, void* stream);
 
+/* A1' BasicSimpleTransform.get_heat_map(joints, sigma=2.0, shape=(48, 64), stride=4)
+ *     commons/transforms.py:80-116. joints [B,K,3] f32 in INPUT pixels;
+ *     the centre is quantised to int(x/stride + 0.5) and a side x side window of `table` is pasted
+ *     (clipped to the map). table [side*side] f32 = the reference's float32 Gaussian patch
+ *     exp(-((x-x0)^2+(y-y0)^2)/(2 s^2)), side = len(arange(0, 6s+1)), computed on the host with
+ *     NumPy exactly as the reference does, so pasted values are bit-identical by construction.
+ */
+int sp_encode_basic_f32(const float* joints, const float* table, float* targets, float* weights,
+                        int B, int K, int H, int W, double sigma, int stride, int side, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * A2  0.5 * nn.MSELoss()(pred.mul(mask[..., None, None]), target.mul(mask[..., None, None]))
  *     and its backward; processors/dp_pose_hrnet_solver.py:86,106-107 (same expression in

@@ -1,0 +1,36 @@
+"""Launches every hot-path kernel configuration a few times for ncu (see profiles/README.md).
+
+    ncu --set full --clock-control none --import-source on -k regex:"decode_|encode_|mse_fwd|oks_" \
+        -o gpurun_out/rN_prof python profiles/prof_driver.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from simple_pose_b200 import synth  # noqa: E402
+from simple_pose_b200.pipeline import HeatmapHotPath  # noqa: E402
+from simple_pose_b200.datasets.naive_data import rescore_and_nms  # noqa: E402
+
+dev = torch.device("cuda:0")
+reps = int(os.environ.get("PROF_REPS", "2"))
+for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):
+    hp = HeatmapHotPath(batch, 17, h, w, device=dev)
+    joints = synth.joints(batch, height=h, width=w, seed=1, device=dev)
+    pred = synth.heatmaps(batch, height=h, width=w, seed=1, device=dev)
+    flip = synth.heatmaps(batch, height=h, width=w, seed=2, device=dev)
+    tinv = synth.inverse_affines(batch, height=h, width=w, seed=1, device=dev)[0]
+    perm = hp.decoder._perm_on(dev, 17, None)
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        hp.encode(joints)
+        hp.loss_fwd_bwd(pred)
+        hp.decode(pred, tinv)
+        hp.decode(pred, tinv, flip, perm)
+    torch.cuda.synchronize()
+kps, box, area, seg = synth.nms_groups(512, mean_group=20.0, seed=3)
+for _ in range(reps):
+    rescore_and_nms(kps.to(dev), box.to(dev), area.to(dev), seg)
+torch.cuda.synchronize()
+print("done")

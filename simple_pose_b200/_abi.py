@@ -29,6 +29,7 @@ SIGNATURES = {
     "sp_error_string": (ctypes.c_char_p, [c_int]),
     "sp_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "sp_encode_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_dbl, c_void]),
+    "sp_encode_basic_f32": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int, c_void]),
     "sp_mse_workspace_bytes": (c_size, []),
     "sp_mse_fwd_bwd_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_size,
                                    c_int, c_int, c_int, c_flt, c_int, c_void]),

@@ -63,3 +63,52 @@ class RefineSimpleTransform(object):
             raise ValueError("joints must be [K, 3]")
         targets, weights = encode_heat_maps(arr[None], sigma, shape)
         return targets[0].cpu().numpy(), weights[0].cpu().numpy()
+
+
+def basic_gaussian_table(sigma=2.0):
+    """The fixed patch of ``BasicSimpleTransform.get_heat_map`` (reference :93-99), computed with
+    the same NumPy float32 expressions so that its bits are the reference's."""
+    tmp_size = sigma * 3
+    size = 2 * tmp_size + 1
+    x = np.arange(0, size, 1, np.float32)
+    y = x[:, np.newaxis]
+    x0 = y0 = size // 2
+    return np.ascontiguousarray(np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * (sigma ** 2))), dtype=np.float32)
+
+
+_table_cache = {}
+
+
+def encode_heat_maps_basic(joints, sigma=2.0, shape=(48, 64), stride=4):
+    """Batched ``BasicSimpleTransform.get_heat_map``: joints [B,K,3] in INPUT pixels ->
+    (targets [B,K,H,W] float32, weights [B,K] float32) on the CUDA device."""
+    j = _abi.to_device(joints, torch.float32)
+    if j.dim() != 3 or j.shape[-1] != 3:
+        raise ValueError("joints must be [B, K, 3], got %s" % (tuple(j.shape),))
+    width, height = int(shape[0]), int(shape[1])
+    b, k = int(j.shape[0]), int(j.shape[1])
+    dev = j.device
+    key = (dev, float(sigma))
+    table = _table_cache.get(key)
+    if table is None:
+        table = torch.from_numpy(basic_gaussian_table(sigma)).to(dev)
+        _table_cache[key] = table
+    targets = torch.empty((b, k, height, width), dtype=torch.float32, device=dev)
+    weights = torch.empty((b, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_encode_basic_f32(j.data_ptr(), table.data_ptr(), targets.data_ptr(), weights.data_ptr(),
+                                                  b, k, height, width, float(sigma), int(stride), int(table.shape[0]),
+                                                  _abi.stream_ptr(dev)))
+    return targets, weights
+
+
+class BasicSimpleTransform(object):
+    """Hot-path member of the reference's ``BasicSimpleTransform`` (commons/transforms.py:64-116)."""
+
+    @staticmethod
+    def get_heat_map(joints, sigma=2.0, shape=(48, 64), stride=4):
+        arr = np.ascontiguousarray(np.asarray(joints, dtype=np.float32))
+        if arr.ndim != 2 or arr.shape[1] != 3:
+            raise ValueError("joints must be [K, 3]")
+        targets, weights = encode_heat_maps_basic(arr[None], sigma, shape, stride)
+        return targets[0].cpu().numpy(), weights[0].cpu().numpy()

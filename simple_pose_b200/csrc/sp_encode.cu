@@ -111,6 +111,43 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     }
 }
 
+
+// A1': BasicSimpleTransform.get_heat_map (commons/transforms.py:80-116): the centre is quantised
+// to int(x/stride + 0.5) and only a (6 sigma + 1)^2 patch of a fixed Gaussian table is pasted.
+// The table is computed on the host exactly as the reference does (NumPy float32) and handed in,
+// so the pasted values are bit-identical by construction. One warp per map, float4 stores.
+__global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)
+encode_basic_kernel(const float* __restrict__ joints, const float* __restrict__ table, float* __restrict__ targets,
+                    float* __restrict__ weights, int nmaps, int H, int W, double reach, float stride, int side) {
+    extern __shared__ float tab[];
+    for (int i = threadIdx.x; i < side * side; i += blockDim.x) tab[i] = __ldg(table + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (m >= nmaps) return;
+    const float jx = __ldg(joints + 3 * (size_t)m + 0);
+    const float jy = __ldg(joints + 3 * (size_t)m + 1);
+    const float vis = __ldg(joints + 3 * (size_t)m + 2);
+    const int mu_x = (int)__fadd_rn(__fdiv_rn(jx, stride), 0.5f);      // int(x / stride + 0.5), float32
+    const int mu_y = (int)__fadd_rn(__fdiv_rn(jy, stride), 0.5f);
+    const int lo_x = (int)((double)mu_x - reach), lo_y = (int)((double)mu_y - reach);     // Python float maths
+    const int hi_x = (int)((double)mu_x + reach + 1.0), hi_y = (int)((double)mu_y + reach + 1.0);
+    const bool culled = lo_x >= W || lo_y >= H || hi_x < 0 || hi_y < 0;
+    if (lane == 0) weights[m] = culled ? 0.f : vis;
+    const bool draw = !culled && vis > 0.5f;
+    const int x0 = max(0, lo_x), x1 = min(hi_x, W), y0 = max(0, lo_y), y1 = min(hi_y, H);
+    float* out = targets + (size_t)m * H * W;
+    for (int i = lane; i < H * W; i += 32) {
+        const int y = i / W, x = i - y * W;
+        float v = 0.f;
+        if (draw && x >= x0 && x < x1 && y >= y0 && y < y1) {
+            const int gy = y - lo_y, gx = x - lo_x;
+            if (gy < side && gx < side) v = tab[gy * side + gx];
+        }
+        out[i] = v;
+    }
+}
+
 }  // namespace
 
 extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights,
@@ -140,5 +177,18 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
             SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_refine_kernel<false><<<grid, kWarpsPerCta * SP_WARP, smem, st>>>(joints, targets, weights, nmaps, H, W, reach, denom);
     }
+    return sp_launch_status();
+}
+
+extern "C" int sp_encode_basic_f32(const float* joints, const float* table, float* targets, float* weights,
+                                   int B, int K, int H, int W, double sigma, int stride, int side, void* stream) {
+    SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0) || stride <= 0 || side <= 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B > 0 && (!joints || !table || !targets || !weights), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24) || side > 96, SP_ERR_UNSUPPORTED);
+    if (B == 0) return 0;
+    const int nmaps = B * K;
+    const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
+    encode_basic_kernel<<<grid, kWarpsPerCta * SP_WARP, (size_t)side * side * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        joints, table, targets, weights, nmaps, H, W, sigma * 3.0, (float)stride, side);
     return sp_launch_status();
 }
