@@ -289,6 +289,7 @@ def time_ops(device, height, width, persons, batch, peak_gbs):
     ops = {
         "encode": lambda i: paths[i].encode(sets[i][0]),
         "loss": lambda i: paths[i].loss_fwd_bwd(sets[i][1]),
+        "train_fused": lambda i: paths[i].train_fused(sets[i][0], sets[i][1]),
         "decode": lambda i: paths[i].decode(sets[i][1], sets[i][2]),
         "flip_decode": lambda i: paths[i].decode(sets[i][1], sets[i][2], flips[i], perm),
     }

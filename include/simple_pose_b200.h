@@ -92,6 +92,28 @@ int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const float* mask
                        float* grad, float* loss, void* workspace, size_t workspace_bytes,
                        int B, int K, int HW, float grad_scale, int flags, void* stream);
 
+/* A1+A2(+HeatMapAcc) fused -- SURVEY section 8f ranks 1 and 2: targets are encoded on the fly and never
+ * written (unless `targets` is given), so one pass reads pred and writes grad.
+ *   targets, mask = get_heat_map(joints)                        commons/transforms.py:167-191
+ *   loss = 0.5 * MSELoss(pred*mask, target*mask); backward       processors/dp_pose_hrnet_solver.py:106-107
+ *   HeatMapAcc inputs: argmax of pred*mask and target*mask      metrics/pose_metrics.py:223-224
+ * joints [B,K,3] f32 heatmap px; pred [B,K,H,W] f32; outputs: grad [B,K,H,W] (NULL = forward only),
+ * targets [B,K,H,W] (NULL = do not materialise), weights [B,K] (NULL ok), loss (1 f32),
+ * pred_xy / label_xy [B,K,2] f32 = heat_map_to_axis of the two masked maps (both NULL = skip).
+ * Requires W % 4 == 0 (else SP_ERR_UNSUPPORTED: compose the two separate calls). Workspace as above.
+ */
+int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred, float* grad, float* targets,
+                              float* weights, float* loss, float* pred_xy, float* label_xy,
+                              void* workspace, size_t workspace_bytes,
+                              int B, int K, int H, int W, double sigma, float grad_scale, void* stream);
+
+/* HeatMapAcc.__call__ epilogue, metrics/pose_metrics.py:225-245: per-joint fraction of persons whose
+ * predicted argmax lies within distance_thresh (in units of (W,H)/norm_frac) of the target argmax, over
+ * persons whose target argmax has x > 1 and y > 1, averaged over joints that have any. pred_xy, label_xy
+ * [B,K,2] f32 (heat_map_to_axis outputs); acc: 1 f32 out. */
+int sp_heatmap_acc_f32(const float* pred_xy, const float* label_xy, float* acc,
+                       int B, int K, int H, int W, float distance_thresh, float norm_frac, void* stream);
+
 /* grad[i] *= *scale_dev, skipped entirely (no memory traffic) when *scale_dev == 1.0f.
  * Used by the autograd wrapper when the upstream gradient is not 1 (e.g. GradScaler). */
 int sp_scale_inplace_f32(float* data, long long n, const float* scale_dev, void* stream);

@@ -33,6 +33,8 @@ SIGNATURES = {
     "sp_mse_workspace_bytes": (c_size, []),
     "sp_mse_fwd_bwd_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_size,
                                    c_int, c_int, c_int, c_flt, c_int, c_void]),
+    "sp_encode_mse_fwd_bwd_f32": (c_int, [c_void] * 9 + [c_size, c_int, c_int, c_int, c_int, c_dbl, c_flt, c_void]),
+    "sp_heatmap_acc_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_flt, c_flt, c_void]),
     "sp_scale_inplace_f32": (c_int, [c_void, c_ll, c_void, c_void]),
     "sp_decode_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void]),

@@ -8,38 +8,12 @@
 // stores (32 lanes x float4 = 512 contiguous bytes per instruction). No block-level barrier.
 // Denormal results are kept (no -ftz / fast-math), as in the reference.
 #include "sp_common.cuh"
+#include "sp_gauss.cuh"
 
 namespace {
 
+using namespace sp_gauss;
 constexpr int kWarpsPerCta = 8;
-
-struct JointVerdict {
-    float weight;   // value written to weights[b,k]
-    bool draw;      // whether a Gaussian is rendered (else the map is zero)
-};
-
-// Cull test of transforms.py:180-185. NumPy 2 keeps float32 for float32-scalar (+,-) Python
-// scalar, so the bounds are float32 sums truncated toward zero by int().
-__device__ __forceinline__ JointVerdict judge_joint(float mx, float my, float vis, float reach, int H, int W) {
-    const int lo_x = (int)__fsub_rn(mx, reach);
-    const int lo_y = (int)__fsub_rn(my, reach);
-    const int hi_x = (int)__fadd_rn(__fadd_rn(mx, reach), 1.0f);
-    const int hi_y = (int)__fadd_rn(__fadd_rn(my, reach), 1.0f);
-    JointVerdict v;
-    if (lo_x >= W || lo_y >= H || hi_x < 0 || hi_y < 0) {
-        v.weight = 0.0f;
-        v.draw = false;
-    } else {
-        v.weight = vis;
-        v.draw = vis > 0.5f;
-    }
-    return v;
-}
-
-__device__ __forceinline__ double gauss_factor(int p, float mu, double denom) {
-    const double d = (double)p - (double)mu;
-    return exp(__ddiv_rn(-__dmul_rn(d, d), denom));
-}
 
 template <bool VEC4>
 __global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)

@@ -12,17 +12,12 @@
 // Arithmetic follows ATen so that grad is bit-identical for finite inputs:
 //   d = fl(m*p) - fl(m*t); grad = ((fl(2/N) * d) * 0.5) * m   (mse_loss_backward, then mul backward)
 #include "sp_common.cuh"
+#include "sp_reduce.cuh"
 
 namespace {
 
+using namespace sp_reduce;
 constexpr int kThreads = 256;
-constexpr int kMaxPartials = 4096;
-
-struct MseWorkspace {
-    unsigned int ticket;          // blocks finished so far (returns to 0 at the end of a call)
-    unsigned int pad[3];
-    double partial[kMaxPartials];
-};
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
@@ -44,8 +39,6 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
                    const float* __restrict__ mask, float* __restrict__ grad, float* __restrict__ loss,
                    MseWorkspace* __restrict__ ws, int nmaps, int hw, float norm, float half_scale,
                    double inv_count, int skip_masked) {
-    __shared__ double warp_part[kThreads / 32];
-    __shared__ bool am_last;
     double block_sum = 0.0;
 
     for (int m = blockIdx.x; m < nmaps; m += gridDim.x) {
@@ -91,36 +84,7 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
         block_sum += (double)acc;
     }
 
-    // block reduction (float64), fixed order
-    block_sum = sp::warp_sum(block_sum);
-    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = block_sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) s += warp_part[w];
-        ws->partial[blockIdx.x] = s;
-        __threadfence();
-        const unsigned int t = atomicAdd(&ws->ticket, 1u);
-        am_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!am_last) return;
-
-    // last block: add the partials in index order (thread-strided, then a fixed tree)
-    __threadfence();
-    double s = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) s += __ldcg(&ws->partial[i]);
-    s = sp::warp_sum(s);
-    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) tot += warp_part[w];
-        *loss = (float)(0.5 * tot * inv_count);
-        ws->ticket = 0u;      // restore the zero state for the next call on this stream
-    }
+    finish_loss<kThreads>(block_sum, ws, loss, inv_count);
 }
 
 __global__ void __launch_bounds__(256)

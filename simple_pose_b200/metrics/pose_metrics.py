@@ -124,6 +124,38 @@ class GaussTaylorKeyPointDecoder(BasicKeyPointDecoder):
                        self.kernel_size, _abi.SP_DECODE_GAUSS_TAYLOR, want_index=True)
 
 
+def heatmap_acc_from_axes(pred_xy, label_xy, height, width, distance_thresh=0.5, norm_frac=10.):
+    """HeatMapAcc epilogue on [B,K,2] argmax coordinates -> 0-d float32 tensor (no host sync)."""
+    dev = _abi.require_cuda(pred_xy, label_xy)
+    p = _abi.dense(pred_xy, torch.float32)
+    l = _abi.dense(label_xy, torch.float32)
+    b, k = int(p.shape[0]), int(p.shape[1])
+    acc = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_heatmap_acc_f32(p.data_ptr(), l.data_ptr(), acc.data_ptr(), b, k, int(height),
+                                                 int(width), float(distance_thresh), float(norm_frac),
+                                                 _abi.stream_ptr(dev)))
+    return acc
+
+
+class HeatMapAcc(object):
+    """Drop-in for the reference's ``HeatMapAcc`` (metrics/pose_metrics.py:212-245): two argmax
+    launches + one tiny epilogue, no 17-iteration Python loop and no ``.item()`` syncs. When the
+    loss is computed with ``EncodeJointsMSELoss(with_acc=True)`` even the two argmax passes
+    disappear (they ride along with the loss kernel)."""
+
+    def __init__(self, distance_thresh=0.5, norm_frac=10.):
+        self.distance_thresh = distance_thresh
+        self.norm_frac = norm_frac
+
+    @torch.no_grad()
+    def __call__(self, predicts, targets):
+        preds, _ = BasicKeyPointDecoder.heat_map_to_axis(predicts)
+        labels, _ = BasicKeyPointDecoder.heat_map_to_axis(targets)
+        return heatmap_acc_from_axes(preds, labels, predicts.shape[-2], predicts.shape[-1],
+                                     self.distance_thresh, self.norm_frac)
+
+
 def kps_to_dict_(predicts, scores, img_ids, set_in_list):
     """Reference :172-179 with ONE device->host copy instead of one ``.item()`` + ``.tolist()``
     per person: score = mean + max of the joint peaks, keypoints = [x, y, score] * K."""

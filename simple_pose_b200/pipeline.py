@@ -16,6 +16,8 @@ ALGO_BYTES = {
     "loss": lambda k, h, w: 3 * k * h * w * 4 + k * 4,
     "decode": lambda k, h, w: k * h * w * 4 + 24 + k * 12,
     "flip_decode": lambda k, h, w: 2 * k * h * w * 4 + 24 + k * 12,
+    # fused encode + loss fwd/bwd + HeatMapAcc argmaxes: read pred, write grad (+ joints, weights, axes)
+    "train_fused": lambda k, h, w: 2 * k * h * w * 4 + k * 12 + k * 4 + k * 16,
 }
 
 
@@ -36,6 +38,7 @@ class HeatmapHotPath(object):
         self.decoder = GaussTaylorKeyPointDecoder(kernel_size, joints)
         self.blur_w = self.decoder._weights_on(dev)
         self.ksize = int(kernel_size)
+        self.pred_xy = self.label_xy = None
         self._lib = _abi.lib()
 
     # each method enqueues exactly one kernel on the current stream of self.device
@@ -50,6 +53,19 @@ class HeatmapHotPath(object):
         _abi.check(self._lib.sp_mse_fwd_bwd_f32(pred.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
                                                 self.grad.data_ptr(), self.loss.data_ptr(), ws.data_ptr(),
                                                 ws.numel() * 8, self.batch, self.k, self.h * self.w, 1.0, 0, stream))
+
+    def train_fused(self, joints, pred, with_acc=True):
+        """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) in one launch; targets never materialised."""
+        if with_acc and self.pred_xy is None:
+            self.pred_xy = torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=self.device)
+            self.label_xy = torch.empty_like(self.pred_xy)
+        stream = _abi.stream_ptr(self.device)
+        ws = _workspace(self.device, stream)
+        _abi.check(self._lib.sp_encode_mse_fwd_bwd_f32(
+            joints.data_ptr(), pred.data_ptr(), self.grad.data_ptr(), None, self.weights.data_ptr(),
+            self.loss.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
+            _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
+            self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream))
 
     def decode(self, pred, trans_inv, pred_flip=None, perm=None):
         _abi.check(self._lib.sp_decode_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),

@@ -425,3 +425,97 @@ def test_errors_are_loud(api):
         api.metrics.GaussTaylorKeyPointDecoder()(torch.zeros(1, 17, 64, 48, device=DEV), torch.zeros(2, 2, 3, device=DEV))
     with pytest.raises(RuntimeError):
         api.abi.check(-4)
+
+
+# ------------------------------------------------------------------------------------ section 8f rows
+def test_basic_encoder_golden(api, golden):
+    g = golden("next_rows")
+    t, w = api.transforms.encode_heat_maps_basic(torch.from_numpy(g["joints_q"]).to(DEV), 2.0, (48, 64), 4)
+    assert np.array_equal(bits(t.cpu().numpy()), bits(g["targets_q"]))
+    assert np.array_equal(w.cpu().numpy(), g["weights_q"])
+    t1, w1 = api.transforms.BasicSimpleTransform.get_heat_map(g["joints_q"][0], 2.0, (48, 64), 4)
+    assert np.array_equal(bits(t1), bits(g["targets_q"][0])) and np.array_equal(w1, g["weights_q"][0])
+
+
+@pytest.mark.parametrize("shape,stride,sigma", [((48, 64), 4, 2.0), ((72, 96), 4, 2.0), ((30, 22), 8, 1.5), ((48, 64), 4, 1.0)])
+def test_basic_encoder_vs_oracle(api, shape, stride, sigma):
+    w, h = shape
+    joints = synth.joints(16, height=h * stride, width=w * stride, seed=61)
+    joints[..., :2] += torch.tensor([-20.0, 30.0])           # push some centres off the map
+    t, wt = api.transforms.encode_heat_maps_basic(joints.to(DEV), sigma, shape, stride)
+    ref = [O.encode_person_basic(j, sigma, shape, stride) for j in joints.numpy()]
+    assert np.array_equal(bits(t.cpu().numpy()), bits(np.stack([r[0] for r in ref])))
+    assert np.array_equal(wt.cpu().numpy(), np.stack([r[1] for r in ref]))
+
+
+def test_heat_map_acc_golden_and_oracle(api, golden):
+    g, e = golden("next_rows"), golden("encode")
+    tgt = torch.from_numpy(e["targets_a"])
+    msk = torch.from_numpy(e["weights_a"])[..., None, None]
+    acc = api.metrics.HeatMapAcc()((torch.from_numpy(g["acc_pred"]) * msk).to(DEV), (tgt * msk).to(DEV))
+    assert acc.dim() == 0 and np.float32(acc.item()) == g["acc_value"]
+    for seed, noise in ((1, 0.05), (2, 0.3), (3, 1.0)):
+        j = synth.joints(64, seed=seed)
+        t_np, w_np = O.encode_batch(j.numpy())
+        t, m = torch.from_numpy(t_np), torch.from_numpy(w_np)[..., None, None]
+        p = synth.predictions_like(t, seed=seed + 10, noise=noise)
+        want = O.heat_map_acc(p * m, t * m)
+        got = api.metrics.HeatMapAcc()((p * m).to(DEV), (t * m).to(DEV))
+        assert np.float32(got.item()) == np.float32(float(want)), (seed, got.item(), float(want))
+    # no valid joint at all -> 0
+    z = torch.zeros(2, 17, 64, 48, device=DEV)
+    assert api.metrics.HeatMapAcc()(z, z).item() == 0.0
+
+
+@pytest.mark.parametrize("b,hw,noise", [(128, (64, 48), 0.05), (24, (96, 72), 0.3), (6, (16, 12), 0.5), (5, (10, 6), 0.2)])
+def test_fused_encode_loss_acc(api, b, hw, noise):
+    """EncodeJointsMSELoss(pred, joints) == reference loss/grad on reference-encoded targets, and its
+    accuracy == HeatMapAcc()(pred*mask, target*mask) (solver :106-107,123-124)."""
+    h, w = hw
+    joints = synth.joints(b, height=h, width=w, seed=71)
+    t_np, w_np = O.encode_batch(joints.numpy(), 2.0, (w, h))
+    tgt, msk = torch.from_numpy(t_np), torch.from_numpy(w_np)
+    pred = synth.predictions_like(tgt, seed=72, noise=noise)
+    ref_loss, ref_grad = O.masked_mse_loss_and_grad(pred, tgt, msk)
+    ref_acc = O.heat_map_acc(pred * msk[..., None, None], tgt * msk[..., None, None])
+    crit = api.loss.EncodeJointsMSELoss(sigma=2.0, with_acc=True, keep_targets=True)
+    p = pred.to(DEV).requires_grad_(True)
+    loss, acc = crit(p, joints.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert torch.allclose(p.grad.cpu(), ref_grad, rtol=1e-5, atol=1e-12)
+    assert np.float32(acc.item()) == np.float32(float(ref_acc))
+    assert np.array_equal(crit.weights.cpu().numpy(), w_np)
+    assert_targets_match(crit.targets.cpu().numpy(), t_np)
+    # identical to the two separate kernels
+    t2, w2 = api.transforms.encode_heat_maps(joints.to(DEV), 2.0, (w, h))
+    p2 = pred.to(DEV).requires_grad_(True)
+    l2 = api.loss.JointsMSELoss()(p2, t2, w2)
+    l2.backward()
+    assert torch.equal(p2.grad, p.grad) and torch.equal(t2, crit.targets)
+    assert abs(l2.item() - loss.item()) <= 1e-6 * abs(l2.item())
+    # plain variant (no acc, no targets kept), upstream gradient != 1
+    crit2 = api.loss.EncodeJointsMSELoss()
+    p3 = pred.to(DEV).requires_grad_(True)
+    l3 = crit2(p3, joints.to(DEV))
+    (l3 * 8.0).backward()
+    assert l3.item() == loss.item() and torch.equal(p3.grad, p.grad * 8.0)
+
+
+def test_fused_acc_special_predictions(api):
+    """NaN / Inf / all-negative predicted maps go through the exact argmax fallback."""
+    joints = synth.joints(4, seed=5)
+    joints[..., 2] = 1.0
+    joints[..., 0] = joints[..., 0].clamp(5, 40)
+    joints[..., 1] = joints[..., 1].clamp(5, 55)
+    t_np, w_np = O.encode_batch(joints.numpy())
+    tgt, msk = torch.from_numpy(t_np), torch.from_numpy(w_np)
+    pred = synth.predictions_like(tgt, seed=3, noise=0.1)
+    pred[0, 0, 10, 10] = float("inf")
+    pred[0, 1] = -1.0
+    pred[1, 2, 3, 3] = float("nan")
+    m = msk[..., None, None]
+    want_p, _ = O.argmax_coords(pred * m)
+    want_l, _ = O.argmax_coords(tgt * m)
+    out = api.loss.encode_mse_forward_backward(joints.to(DEV), pred.to(DEV), need_grad=False, want_axes=True)
+    assert torch.equal(out["pred_xy"].cpu(), want_p) and torch.equal(out["label_xy"].cpu(), want_l)
