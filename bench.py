@@ -316,6 +316,53 @@ def time_ops(device, height, width, persons, batch, peak_gbs):
     return out
 
 
+def small_batch_numbers(device, height, width, batch=128, nbatch=64):
+    """The literal cfg-1/cfg-2 shape (batch 128 = 26.7 MB per tensor, launch-latency bound): the step
+    replayed as ONE CUDA graph over `nbatch` distinct buffer sets (working set >> L2), plus the
+    un-graphed latency of a single batch step (3 launches + sync)."""
+    from simple_pose_b200.pipeline import HeatmapHotPath
+    sets = make_inputs(batch * nbatch, batch, height, width, device, seed=4242)
+    paths = [HeatmapHotPath(batch, 17, height, width, device=device) for _ in range(nbatch)]
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            for i in range(nbatch):
+                paths[i].step(*sets[i])
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for i in range(nbatch):
+            paths[i].step(*sets[i])
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    a.record()
+    for _ in range(reps):
+        graph.replay()
+    b.record()
+    b.synchronize()
+    graph_ms = a.elapsed_time(b) / reps
+    lat = []
+    for r in range(30):
+        i = r % nbatch
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        paths[i].step(*sets[i])
+        torch.cuda.synchronize(device)
+        lat.append(time.perf_counter() - t0)
+    out = {"batch": batch, "batches_per_graph": nbatch, "launches_per_graph": nbatch * 3,
+           "graph_persons_per_s": batch * nbatch / (graph_ms * 1e-3), "graph_us_per_batch_step": 1e3 * graph_ms / nbatch,
+           "single_batch_step_latency_us": 1e6 * statistics.median(lat[5:]),
+           "note": "batch-128 steps are launch-latency bound (26.7 MB per tensor = 4 us at the HBM roofline)"}
+    del graph, paths, sets
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from simple_pose_b200 import _abi
@@ -337,17 +384,18 @@ def run_ours(args):
     nb = P // B
 
     sets = make_inputs(P, B, H, W, device, seed=rank * 7919)
-    paths = [HeatmapHotPath(B, 17, H, W, device=device) for _ in range(nb)]      # distinct outputs per batch
-    kp_local = torch.empty((P, 17, 3), dtype=torch.float32, device=device)
-    kp_all = torch.empty((world * P, 17, 3), dtype=torch.float32, device=device) if world > 1 else None
+    # decoded keypoints of all batches land in one flat send buffer: [P*17*2 coords | P*17 scores]
+    kp_local = torch.empty(P * 17 * 3, dtype=torch.float32, device=device)
+    coords_all = kp_local[:P * 17 * 2].view(P, 17, 2)
+    maxval_all = kp_local[P * 17 * 2:].view(P, 17, 1)
+    paths = [HeatmapHotPath(B, 17, H, W, device=device, coords=coords_all[i * B:(i + 1) * B],
+                            maxval=maxval_all[i * B:(i + 1) * B]) for i in range(nb)]    # distinct outputs per batch
+    kp_all = torch.empty(world * P * 17 * 3, dtype=torch.float32, device=device) if world > 1 else None
+
     def step():
         for i in range(nb):
             joints, pred, tinv = sets[i]
-            hp = paths[i]
-            hp.step(joints, pred, tinv)
-            if world > 1:
-                kp_local[i * B:(i + 1) * B, :, :2].copy_(hp.coords)
-                kp_local[i * B:(i + 1) * B, :, 2:].copy_(hp.maxval)
+            paths[i].step(joints, pred, tinv)
         if world > 1:
             dist.all_gather_into_tensor(kp_all, kp_local)
 
@@ -422,6 +470,10 @@ def run_ours(args):
         ops = {"64x48": time_ops(device, 64, 48, 8192, 1024, peak_gbs),
                "96x72": time_ops(device, 96, 72, 4096, 512, peak_gbs)}
 
+    small = None
+    if rank == 0 and world == 1 and not args.no_ops:
+        small = small_batch_numbers(device, H, W)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -447,7 +499,7 @@ def run_ours(args):
                          (nb, P * (ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)) / 1e6),
                    "parallelism": "persons sharded, dp%d" % world},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
-        "roofline": roofline, "cpu_baseline": cpu, "ops": ops,
+        "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small,
     }
     print(json.dumps(line), flush=True)
 

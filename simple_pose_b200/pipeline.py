@@ -24,7 +24,8 @@ ALGO_BYTES = {
 class HeatmapHotPath(object):
     """Pre-allocated buffers + raw ABI calls for one batch shape on one device."""
 
-    def __init__(self, batch, joints=17, height=64, width=48, sigma=2.0, device=None, kernel_size=11):
+    def __init__(self, batch, joints=17, height=64, width=48, sigma=2.0, device=None, kernel_size=11,
+                 coords=None, maxval=None):
         self.device = torch.device(device) if device is not None else _abi.default_device()
         self.batch, self.k, self.h, self.w = int(batch), int(joints), int(height), int(width)
         self.sigma = float(sigma)
@@ -33,8 +34,10 @@ class HeatmapHotPath(object):
         self.weights = torch.empty((self.batch, self.k), dtype=torch.float32, device=dev)
         self.grad = torch.empty_like(self.targets)
         self.loss = torch.empty((), dtype=torch.float32, device=dev)
-        self.coords = torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=dev)
-        self.maxval = torch.empty((self.batch, self.k, 1), dtype=torch.float32, device=dev)
+        # decoder outputs may be views into a larger buffer (e.g. the all-gather send buffer)
+        self.coords = coords if coords is not None else torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=dev)
+        self.maxval = maxval if maxval is not None else torch.empty((self.batch, self.k, 1), dtype=torch.float32, device=dev)
+        assert self.coords.is_contiguous() and self.maxval.is_contiguous()
         self.decoder = GaussTaylorKeyPointDecoder(kernel_size, joints)
         self.blur_w = self.decoder._weights_on(dev)
         self.ksize = int(kernel_size)

@@ -519,3 +519,62 @@ def test_fused_acc_special_predictions(api):
     want_l, _ = O.argmax_coords(tgt * m)
     out = api.loss.encode_mse_forward_backward(joints.to(DEV), pred.to(DEV), need_grad=False, want_axes=True)
     assert torch.equal(out["pred_xy"].cpu(), want_p) and torch.equal(out["label_xy"].cpu(), want_l)
+
+
+# ------------------------------------------------------------------------------------ BASELINE full sizes
+def test_cfg4_full_size_decode_and_nms_vs_oracle(api):
+    """BASELINE config 4: HRNet-W48 384x288 (96x72 maps) decode + OKS-NMS, batch 512 -- the
+    oracle still finishes in about a second at this size, so compare directly."""
+    hm = synth.heatmaps(512, height=96, width=72, seed=404)
+    tinv, area = synth.inverse_affines(512, height=96, width=72, seed=404)
+    ref_hsp, ref_max = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hsp, mx, idx = dec.decode_with_index(hm.to(DEV))
+    assert torch.equal(idx.cpu().long(), O.argmax_index(hm)) and torch.equal(mx.cpu(), ref_max)
+    assert (hsp.cpu() - ref_hsp).abs().max().item() <= 1e-4
+    img, conf = dec(hm.to(DEV), tinv.to(DEV))
+    seg = np.concatenate([[0], np.cumsum(np.random.RandomState(0).randint(1, 40, size=64))])
+    seg = np.unique(np.clip(seg, 0, 512)).astype(np.int32)
+    if seg[-1] != 512:
+        seg = np.append(seg, 512).astype(np.int32)
+    box = torch.rand(512, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    kps = api.naive.pack_keypoints(img, conf)
+    keep, scores, _ = api.naive.rescore_and_nms(kps, box, area, seg)
+    o_keep, o_scores, _ = O.rescore_and_nms(kps.cpu().numpy(), box.numpy(), area.numpy(), seg)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), o_keep)
+    assert np.allclose(scores.cpu().numpy(), o_scores, rtol=1e-15, atol=0)
+
+
+def test_cfg5_coco_val_sized_job_properties(api):
+    """BASELINE config 5: ~104k persons (21.7 GB of 64x48 maps, > 2^31 bytes). Too big for the
+    oracle; checked through size-independent properties: (1) one launch == the same job in 8
+    shards, bit for bit; (2) argmax / max agree with torch.max on the device; (3) a sample of
+    persons agrees with the oracle; (4) encode -> decode round trip at full size."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~50 GB of free device memory")
+    P = 104_000
+    hm = synth.heatmaps(P, seed=505, device=DEV)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    hsp, mx, idx = dec.decode_with_index(hm)
+    cuts = np.linspace(0, P, 9).astype(int)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        h2, m2, i2 = dec.decode_with_index(hm[a:b])
+        assert torch.equal(h2, hsp[a:b]) and torch.equal(m2, mx[a:b]) and torch.equal(i2, idx[a:b])
+    tmax, targ = hm.view(P, 17, -1).max(dim=-1)
+    assert torch.equal(targ.int(), idx) and torch.equal(tmax[..., None], mx)
+    pick = torch.randint(0, P, (96,), generator=torch.Generator().manual_seed(0))
+    pick[0], pick[-1] = 0, P - 1
+    ref_hsp, ref_max = O.gauss_taylor_decode(hm[pick.to(DEV)].cpu(), None, return_heatmap_space=True)
+    assert (hsp[pick.to(DEV)].cpu() - ref_hsp).abs().max().item() <= 1e-4
+    assert torch.isfinite(hsp).all()
+    del hm, tmax, targ
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    mu = torch.rand(P, 17, 2, generator=g, device=DEV)
+    mu[..., 0] = 9 + mu[..., 0] * (48 - 19)
+    mu[..., 1] = 9 + mu[..., 1] * (64 - 19)
+    joints = torch.cat([mu, torch.ones(P, 17, 1, device=DEV)], -1)
+    t, wt = api.transforms.encode_heat_maps(joints)
+    xy, conf = dec(t, synth.identity_affines(P, device=DEV))
+    assert (xy - mu).abs().max().item() < 1e-3 and (wt == 1).all() and (conf > 0.77).all()
