@@ -28,6 +28,7 @@ for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):
         hp.loss_fwd_bwd(pred)
         hp.decode(pred, tinv)
         hp.decode(pred, tinv, flip, perm)
+        hp.train_fused(joints, pred)
     torch.cuda.synchronize()
 kps, box, area, seg = synth.nms_groups(512, mean_group=20.0, seed=3)
 for _ in range(reps):

@@ -336,7 +336,6 @@ __device__ __forceinline__ float reduce_scatter13(float (&v)[kStencil], int lane
     d += __shfl_xor_sync(SP_FULL, d, 1);
     return d;
 }
-__device__ __forceinline__ int slot_of_lane(int lane) { return 7 * (lane >> 4) + ((lane >> 1) & 7); }
 __device__ __forceinline__ bool lane_has_slot(int lane) { return ((lane >> 1) & 7) < ((lane & 16) ? 6 : 7); }
 __device__ __forceinline__ constexpr int lane_of_slot(int s) { return (s >= 7) ? 16 + 2 * (s - 7) : 2 * s; }
 
@@ -396,9 +395,24 @@ __device__ __forceinline__ bool taylor_refine_smem(const float* map, const float
 // ---------------------------------------------------------------------------------------------
 // everything after the argmax: coordinates, refinement, affine, stores
 // ---------------------------------------------------------------------------------------------
+// trans_inv row of the map's person, fetched before the scan so its latency is off the critical path
+struct Affine {
+    float a, b, c, d, e, f;
+};
+__device__ __forceinline__ Affine load_affine(const DecodeArgs& A, int m) {
+    Affine T;
+    T.a = 1.f; T.b = 0.f; T.c = 0.f; T.d = 0.f; T.e = 1.f; T.f = 0.f;
+    if (A.mode != SP_DECODE_ARGMAX && A.trans_inv != nullptr && m < A.nmaps) {
+        const float* p = A.trans_inv + 6 * (size_t)(m / A.K);
+        T.a = __ldg(p + 0); T.b = __ldg(p + 1); T.c = __ldg(p + 2);
+        T.d = __ldg(p + 3); T.e = __ldg(p + 4); T.f = __ldg(p + 5);
+    }
+    return T;
+}
+
 template <typename View, typename Refine>
 __device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map, int m, Peak pk, int lane,
-                                           Refine&& refine) {
+                                           const Affine T, Refine&& refine) {
     const int W = A.W, H = A.H;
     const bool positive = pk.value > 0.f;                 // false for NaN, like (max_val > 0.)
     const int iy = positive ? pk.index / W : 0;
@@ -429,9 +443,8 @@ __device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map,
     if (lane == 0) {
         float outx = x, outy = y;
         if (A.mode != SP_DECODE_ARGMAX && A.trans_inv != nullptr) {
-            const float* T = A.trans_inv + 6 * (size_t)(m / A.K);
-            outx = __fadd_rn(fmaf(y, __ldg(T + 1), __fmul_rn(x, __ldg(T + 0))), __ldg(T + 2));
-            outy = __fadd_rn(fmaf(y, __ldg(T + 4), __fmul_rn(x, __ldg(T + 3))), __ldg(T + 5));
+            outx = __fadd_rn(fmaf(y, T.b, __fmul_rn(x, T.a)), T.c);
+            outy = __fadd_rn(fmaf(y, T.e, __fmul_rn(x, T.d)), T.f);
         }
         reinterpret_cast<float2*>(A.coords)[m] = make_float2(outx, outy);
         A.maxval[m] = pk.value;
@@ -501,11 +514,12 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
     int s = 0;
     uint32_t parity = 0;
     for (int m = gw; m < A.nmaps; m += total) {
+        const Affine T = load_affine(A, m);
         sp::mbar_wait(bars + s, parity);
         float* a = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
         const Peak pk = argmax_smem<FLIP>(a, a + hw, hw, A.W, lane);
         DirectView view{a};
-        finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+        finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
             if (KS > 0) return taylor_refine_smem<(KS > 0 ? KS : 3)>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
             return taylor_refine_generic(view, wts, patch, A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
         });
@@ -535,17 +549,18 @@ decode_generic_kernel(const DecodeArgs A) {
     __syncthreads();
     const int total = gridDim.x * 8;
     for (int m = blockIdx.x * 8 + warp; m < A.nmaps; m += total) {
+        const Affine T = load_affine(A, m);
         if (FLIP) {
             const int b = m / A.K, k = m - b * A.K;
             FlipAvgView view{A.hm + (size_t)m * hw, A.hm_flip + (size_t)(b * A.K + __ldg(A.perm + k)) * hw, A.W};
             const Peak pk = argmax_exact(view, hw, lane);
-            finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+            finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
                 return taylor_refine_generic(view, wts, patches[warp], A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
             });
         } else {
             DirectView view{A.hm + (size_t)m * hw};
             const Peak pk = argmax_exact(view, hw, lane);
-            finish_map(A, view, m, pk, lane, [&](int px, int py, float ori_max, float& ox, float& oy) {
+            finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
                 return taylor_refine_generic(view, wts, patches[warp], A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
             });
         }

@@ -8,6 +8,7 @@ namespace sp_gauss {
 struct JointVerdict {
     float weight;   // value written to weights[b,k]
     bool draw;      // whether a Gaussian is rendered (else the map is zero)
+    float mx, my;   // the centre the verdict was made for
 };
 
 // Cull test of transforms.py:180-185. NumPy 2 keeps float32 for float32-scalar (+,-) Python
@@ -18,6 +19,8 @@ __device__ __forceinline__ JointVerdict judge_joint(float mx, float my, float vi
     const int hi_x = (int)__fadd_rn(__fadd_rn(mx, reach), 1.0f);
     const int hi_y = (int)__fadd_rn(__fadd_rn(my, reach), 1.0f);
     JointVerdict v;
+    v.mx = mx;
+    v.my = my;
     if (lo_x >= W || lo_y >= H || hi_x < 0 || hi_y < 0) {
         v.weight = 0.0f;
         v.draw = false;

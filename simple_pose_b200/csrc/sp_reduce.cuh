@@ -14,7 +14,8 @@ struct MseWorkspace {
     double partial[kMaxPartials];
 };
 
-// Called by ALL threads of every block (gridDim.x <= kMaxPartials). loss = 0.5 * total * inv_count.
+// Called by ALL threads of every block (gridDim.x <= kMaxPartials, blockDim.x <= THREADS, a multiple
+// of 32). loss = 0.5 * total * inv_count.
 template <int THREADS>
 __device__ __forceinline__ void finish_loss(double block_sum, MseWorkspace* __restrict__ ws, float* __restrict__ loss,
                                             double inv_count) {
@@ -25,8 +26,7 @@ __device__ __forceinline__ void finish_loss(double block_sum, MseWorkspace* __re
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) s += warp_part[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += warp_part[w];
         ws->partial[blockIdx.x] = s;
         __threadfence();
         const unsigned int t = atomicAdd(&ws->ticket, 1u);
@@ -37,15 +37,14 @@ __device__ __forceinline__ void finish_loss(double block_sum, MseWorkspace* __re
     // last block: add the partials in index order (thread-strided, then a fixed tree)
     __threadfence();
     double s = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += THREADS) s += __ldcg(&ws->partial[i]);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(&ws->partial[i]);
     s = sp::warp_sum(s);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; ++w) tot += warp_part[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_part[w];
         *loss = (float)(0.5 * tot * inv_count);
         ws->ticket = 0u;      // restore the zero state for the next call on this stream
     }

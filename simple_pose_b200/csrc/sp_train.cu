@@ -16,6 +16,7 @@
 #include "sp_gauss.cuh"
 #include "sp_reduce.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -83,130 +84,300 @@ __device__ __forceinline__ float2 axis_of(float val, int idx, int W) {
     return make_float2((float)(idx - y * W), (float)y);
 }
 
+struct MapIo {                 // per-launch constants of the fused kernel
+    const float* joints;
+    const float* pred;
+    float* grad;
+    float* targets;
+    float* weights;
+    float2* pred_xy;
+    float2* label_xy;
+    int nmaps, H, W;
+    float reach;
+    double denom;
+    float norm, half_scale;
+    int analytic_ok;          // sigma in the range where the target argmax can be found analytically
+};
+
+// One (person, joint) map, one warp. `src` = the predicted map, in shared memory (SMEM_PRED, staged
+// by TMA) or in global memory. Returns this lane's share of sum((m*p - m*t)^2).
+// Per-map running state of one warp while the predicted map streams by (possibly in chunks).
+struct MapState {
+    float acc;                   // this lane's share of sum((m*p - m*t)^2)
+    QuadBest bp, bt;             // running argmax of the masked predicted / target map
+    int y, xq;                   // row and quad-in-row of this lane's next quad
+    bool track, analytic_t, track_t;
+};
+
+__device__ __forceinline__ void begin_map(const MapIo& io, const JointVerdict& jv, MapState& st, int lane, bool acc_on) {
+    const int qpr = io.W >> 2;
+    st.acc = 0.f;
+    st.bp.init();
+    st.bt.init();
+    st.y = lane / qpr;
+    st.xq = lane - st.y * qpr;
+    st.track = acc_on && (jv.weight != 0.f);
+    // The target's argmax is found analytically (3x3 block around the rounded centre) when the
+    // mask and sigma are in the range where float32 rounding cannot create far-away ties.
+    st.analytic_t = st.track && jv.draw && io.analytic_ok && jv.weight >= 0.5f && jv.weight <= 4.f;
+    st.track_t = st.track && jv.draw && !st.analytic_t;
+}
+
+// Quads q = q_begin + lane, +32, ... < q_end of map m; `chunk` points at quad q_begin of the
+// predicted map (shared memory when SMEM_PRED, else global). q_begin is a multiple of 32.
+// UNIT: the mask is exactly 1.0f (the common case), so m*p == p, m*t == t and (...)*m is dropped;
+// the results are bit-identical to the general expressions.
+template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC, bool SMEM_PRED, bool UNIT>
+__device__ __forceinline__ void run_quads_impl(const MapIo& io, int m, const float4* chunk, int q_begin, int q_end,
+                                               const JointVerdict& jv, const double* ex, const double* ey,
+                                               MapState& st, int lane) {
+    const int W = io.W, hw = io.H * io.W, qpr = W >> 2;
+    const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
+    const float mk = jv.weight, norm = io.norm, half_scale = io.half_scale;
+    float4* g4 = reinterpret_cast<float4*>(io.grad + (size_t)m * hw);
+    float4* t4 = reinterpret_cast<float4*>(io.targets + (size_t)m * hw);
+    int y = st.y, xq = st.xq;
+    float acc = st.acc;
+    QuadBest bp = st.bp, bt = st.bt;
+    const bool draw = jv.draw, track = st.track, track_t = st.track_t;
+#pragma unroll 2
+    for (int q = q_begin + lane; q < q_end; q += 32) {
+        const float4 p = SMEM_PRED ? chunk[q - q_begin] : ldg_stream4(chunk + (q - q_begin));
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (draw) {
+            const double2 a = *reinterpret_cast<const double2*>(ex + 4 * xq);
+            const double2 b = *reinterpret_cast<const double2*>(ex + 4 * xq + 2);
+            const double fy = ey[y];
+            t.x = __double2float_rn(__dmul_rn(a.x, fy));
+            t.y = __double2float_rn(__dmul_rn(a.y, fy));
+            t.z = __double2float_rn(__dmul_rn(b.x, fy));
+            t.w = __double2float_rn(__dmul_rn(b.y, fy));
+        }
+        const float px = UNIT ? p.x : __fmul_rn(mk, p.x), py = UNIT ? p.y : __fmul_rn(mk, p.y);
+        const float pz = UNIT ? p.z : __fmul_rn(mk, p.z), pw = UNIT ? p.w : __fmul_rn(mk, p.w);
+        const float tx = UNIT ? t.x : __fmul_rn(mk, t.x), ty = UNIT ? t.y : __fmul_rn(mk, t.y);
+        const float tz = UNIT ? t.z : __fmul_rn(mk, t.z), tw = UNIT ? t.w : __fmul_rn(mk, t.w);
+        const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty), dz = __fsub_rn(pz, tz), dw = __fsub_rn(pw, tw);
+        acc = fmaf(dx, dx, acc);
+        acc = fmaf(dy, dy, acc);
+        acc = fmaf(dz, dz, acc);
+        acc = fmaf(dw, dw, acc);
+        if (WRITE_GRAD) {
+            float4 g;
+            g.x = __fmul_rn(__fmul_rn(norm, dx), half_scale);
+            g.y = __fmul_rn(__fmul_rn(norm, dy), half_scale);
+            g.z = __fmul_rn(__fmul_rn(norm, dz), half_scale);
+            g.w = __fmul_rn(__fmul_rn(norm, dw), half_scale);
+            if (!UNIT) {
+                g.x = __fmul_rn(g.x, mk); g.y = __fmul_rn(g.y, mk); g.z = __fmul_rn(g.z, mk); g.w = __fmul_rn(g.w, mk);
+            }
+            g4[q] = g;
+        }
+        if (WRITE_TARGETS) t4[q] = t;
+        if (ACC && track) bp.push(px, py, pz, pw, q);
+        if (ACC && track_t) bt.push(tx, ty, tz, tw, q);
+        xq += step_x;
+        y += step_y;
+        if (xq >= qpr) { xq -= qpr; ++y; }
+    }
+    st.y = y; st.xq = xq; st.acc = acc; st.bp = bp; st.bt = bt;
+}
+
+template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC, bool SMEM_PRED>
+__device__ __forceinline__ void run_quads(const MapIo& io, int m, const float4* chunk, int q_begin, int q_end,
+                                          const JointVerdict& jv, const double* ex, const double* ey, MapState& st, int lane) {
+    if (jv.weight == 1.0f) run_quads_impl<WRITE_GRAD, WRITE_TARGETS, ACC, SMEM_PRED, true>(io, m, chunk, q_begin, q_end, jv, ex, ey, st, lane);
+    else                   run_quads_impl<WRITE_GRAD, WRITE_TARGETS, ACC, SMEM_PRED, false>(io, m, chunk, q_begin, q_end, jv, ex, ey, st, lane);
+}
+
+// HeatMapAcc coordinates of both masked maps (heat_map_to_axis). The winning quad of the predicted
+// map is re-read from global memory (L2-resident: it has just streamed through), so the staged
+// copy may already have been recycled.
+__device__ __forceinline__ void end_map_acc(const MapIo& io, int m, const JointVerdict& jv, const double* ex,
+                                            const double* ey, const MapState& st, int lane) {
+    const int W = io.W, hw = io.H * io.W, qpr = W >> 2;
+    const float mk = jv.weight;
+    float2 pxy = make_float2(0.f, 0.f), lxy = make_float2(0.f, 0.f);
+    if (st.track) {
+        const float* src = io.pred + (size_t)m * hw;
+        float pv;
+        int pi;
+        if (__any_sync(SP_FULL, st.bp.poison != st.bp.poison)) {
+            MaskedPredView view{src, mk};
+            argmax_exact_scan(view, hw, lane, pv, pi);
+        } else {
+            const float gmax = warp_max_f32(st.bp.best);
+            const unsigned gq = __reduce_min_sync(SP_FULL, (st.bp.best == gmax) ? (unsigned)st.bp.bq : 0x7fffffffu);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(src) + gq);
+            const float a = __fmul_rn(mk, w.x), b = __fmul_rn(mk, w.y), c = __fmul_rn(mk, w.z);
+            const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
+            pv = gmax;
+            pi = 4 * (int)gq + sub;
+        }
+        pxy = axis_of(pv, pi, W);
+        // target map: fl(m * t); always finite
+        if (st.analytic_t) {
+            // factors decrease monotonically away from the centre, so every maximiser of the
+            // rounded products lies in the 3x3 block around the nearest in-map pixel
+            const int xn = min(max(__float2int_rn(jv.mx), 0), W - 1), yn = min(max(__float2int_rn(jv.my), 0), io.H - 1);
+            const int yy = yn - 1 + lane / 3, xx = xn - 1 + lane % 3;
+            const bool in = lane < 9 && yy >= 0 && yy < io.H && xx >= 0 && xx < W;
+            float v = -CUDART_INF_F;
+            if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[xx], ey[yy])));
+            const float gmax = warp_max_f32(v);
+            const unsigned gi = __reduce_min_sync(SP_FULL, (in && v == gmax) ? (unsigned)(yy * W + xx) : 0x7fffffffu);
+            lxy = axis_of(gmax, (int)gi, W);
+        } else if (jv.draw) {
+            const float gmax = warp_max_f32(st.bt.best);
+            const unsigned gq = __reduce_min_sync(SP_FULL, (st.bt.best == gmax) ? (unsigned)st.bt.bq : 0x7fffffffu);
+            const int gy = (int)gq / qpr, gx = 4 * ((int)gq - gy * qpr);
+            const double fy = ey[gy];
+            const float a = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 0], fy)));
+            const float b = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 1], fy)));
+            const float c = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 2], fy)));
+            const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
+            lxy = axis_of(gmax, 4 * (int)gq + sub, W);
+        }
+    }
+    if (lane == 0) {
+        io.pred_xy[m] = pxy;
+        io.label_xy[m] = lxy;
+    }
+}
+
+struct Joint3 {
+    float x, y, v;
+};
+__device__ __forceinline__ Joint3 load_joint(const MapIo& io, int m) {
+    Joint3 j;
+    j.x = j.y = j.v = 0.f;
+    if (m < io.nmaps) {
+        j.x = __ldg(io.joints + 3 * (size_t)m + 0);
+        j.y = __ldg(io.joints + 3 * (size_t)m + 1);
+        j.v = __ldg(io.joints + 3 * (size_t)m + 2);
+    }
+    return j;
+}
+
+// joint -> verdict, weight store, float64 factors into this warp's shared-memory slice
+__device__ __forceinline__ JointVerdict prepare_map(const MapIo& io, int m, const Joint3 j, double* ex, double* ey, int lane) {
+    const float mx = j.x, my = j.y, vis = j.v;
+    const JointVerdict jv = judge_joint(mx, my, vis, io.reach, io.H, io.W);
+    if (lane == 0 && io.weights) io.weights[m] = jv.weight;
+    __syncwarp();
+    if (jv.draw) {
+        for (int i = lane; i < io.W + io.H; i += 32) {
+            if (i < io.W) ex[i] = gauss_factor(i, mx, io.denom);
+            else          ey[i - io.W] = gauss_factor(i - io.W, my, io.denom);
+        }
+    }
+    __syncwarp();
+    return jv;
+}
+
+// Variant A: predicted maps read straight from global memory (any map size).
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
 __global__ void __launch_bounds__(kThreads)
-encode_mse_kernel(const float* __restrict__ joints, const float* __restrict__ pred, float* __restrict__ grad,
-                  float* __restrict__ targets, float* __restrict__ weights, float* __restrict__ loss,
-                  MseWorkspace* __restrict__ ws, float2* __restrict__ pred_xy, float2* __restrict__ label_xy,
-                  int nmaps, int H, int W, float reach, double denom, float norm, float half_scale, double inv_count) {
+encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count) {
     extern __shared__ __align__(16) double factors[];   // per warp: ex[Wpad] then ey[H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int wpad = (W + 1) & ~1;
-    double* ex = factors + (size_t)warp * (wpad + H);
+    const int wpad = (io.W + 1) & ~1;
+    double* ex = factors + (size_t)warp * (wpad + io.H);
     double* ey = ex + wpad;
-    const int hw = H * W;
-    const int nq = hw >> 2;
-    const int qpr = W >> 2;
-    const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
+    const int hw = io.H * io.W;
     const int total_warps = gridDim.x * kWarps;
-    double warp_sum_sq = 0.0;
-
-    for (int m = blockIdx.x * kWarps + warp; m < nmaps; m += total_warps) {
-        const float mx = __ldg(joints + 3 * (size_t)m + 0);
-        const float my = __ldg(joints + 3 * (size_t)m + 1);
-        const float vis = __ldg(joints + 3 * (size_t)m + 2);
-        const JointVerdict jv = judge_joint(mx, my, vis, reach, H, W);
-        const float mk = jv.weight;
-        if (lane == 0 && weights) weights[m] = mk;
-        __syncwarp();
-        if (jv.draw) {
-            for (int i = lane; i < W + H; i += 32) {
-                if (i < W) ex[i] = gauss_factor(i, mx, denom);
-                else       ey[i - W] = gauss_factor(i - W, my, denom);
-            }
-        }
-        __syncwarp();
-
-        const float4* p4 = reinterpret_cast<const float4*>(pred + (size_t)m * hw);
-        float4* g4 = reinterpret_cast<float4*>(grad + (size_t)m * hw);
-        float4* t4 = reinterpret_cast<float4*>(targets + (size_t)m * hw);
-        int y = lane / qpr;
-        int xq = lane - y * qpr;
-        float acc = 0.f;
-        QuadBest bp, bt;
-        bp.init();
-        bt.init();
-        const bool track = ACC && (mk != 0.f);
-#pragma unroll 4
-        for (int q = lane; q < nq; q += 32) {
-            const float4 p = ldg_stream4(p4 + q);
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jv.draw) {
-                const double2 a = *reinterpret_cast<const double2*>(ex + 4 * xq);
-                const double2 b = *reinterpret_cast<const double2*>(ex + 4 * xq + 2);
-                const double fy = ey[y];
-                t.x = __double2float_rn(__dmul_rn(a.x, fy));
-                t.y = __double2float_rn(__dmul_rn(a.y, fy));
-                t.z = __double2float_rn(__dmul_rn(b.x, fy));
-                t.w = __double2float_rn(__dmul_rn(b.y, fy));
-            }
-            const float px = __fmul_rn(mk, p.x), py = __fmul_rn(mk, p.y), pz = __fmul_rn(mk, p.z), pw = __fmul_rn(mk, p.w);
-            const float tx = __fmul_rn(mk, t.x), ty = __fmul_rn(mk, t.y), tz = __fmul_rn(mk, t.z), tw = __fmul_rn(mk, t.w);
-            const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty), dz = __fsub_rn(pz, tz), dw = __fsub_rn(pw, tw);
-            acc = fmaf(dx, dx, acc);
-            acc = fmaf(dy, dy, acc);
-            acc = fmaf(dz, dz, acc);
-            acc = fmaf(dw, dw, acc);
-            if (WRITE_GRAD) {
-                float4 g;
-                g.x = __fmul_rn(__fmul_rn(__fmul_rn(norm, dx), half_scale), mk);
-                g.y = __fmul_rn(__fmul_rn(__fmul_rn(norm, dy), half_scale), mk);
-                g.z = __fmul_rn(__fmul_rn(__fmul_rn(norm, dz), half_scale), mk);
-                g.w = __fmul_rn(__fmul_rn(__fmul_rn(norm, dw), half_scale), mk);
-                g4[q] = g;
-            }
-            if (WRITE_TARGETS) t4[q] = t;
-            if (track) {
-                bp.push(px, py, pz, pw, q);
-                bt.push(tx, ty, tz, tw, q);
-            }
-            xq += step_x;
-            y += step_y;
-            if (xq >= qpr) { xq -= qpr; ++y; }
-        }
-        warp_sum_sq += (double)acc;
-
-        if (ACC) {
-            float2 pxy = make_float2(0.f, 0.f), lxy = make_float2(0.f, 0.f);
-            if (track) {
-                // predicted map: fl(m * p)
-                float pv;
-                int pi;
-                if (__any_sync(SP_FULL, bp.poison != bp.poison)) {
-                    MaskedPredView view{pred + (size_t)m * hw, mk};
-                    argmax_exact_scan(view, hw, lane, pv, pi);
-                } else {
-                    const float gmax = warp_max_f32(bp.best);
-                    const unsigned gq = __reduce_min_sync(SP_FULL, (bp.best == gmax) ? (unsigned)bp.bq : 0x7fffffffu);
-                    const float4 w = __ldg(p4 + gq);
-                    const float a = __fmul_rn(mk, w.x), b = __fmul_rn(mk, w.y), c = __fmul_rn(mk, w.z);
-                    const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
-                    pv = gmax;
-                    pi = 4 * (int)gq + sub;
-                }
-                pxy = axis_of(pv, pi, W);
-                // target map: fl(m * t); always finite
-                if (jv.draw) {
-                    const float gmax = warp_max_f32(bt.best);
-                    const unsigned gq = __reduce_min_sync(SP_FULL, (bt.best == gmax) ? (unsigned)bt.bq : 0x7fffffffu);
-                    const int gy = (int)gq / qpr, gx = 4 * ((int)gq - gy * qpr);
-                    const double fy = ey[gy];
-                    const float a = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 0], fy)));
-                    const float b = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 1], fy)));
-                    const float c = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 2], fy)));
-                    const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
-                    lxy = axis_of(gmax, 4 * (int)gq + sub, W);
-                }
-            }
-            if (lane == 0) {
-                pred_xy[m] = pxy;
-                label_xy[m] = lxy;
-            }
-        }
+    double sum_sq = 0.0;
+    Joint3 jn = load_joint(io, blockIdx.x * kWarps + warp);
+    for (int m = blockIdx.x * kWarps + warp; m < io.nmaps; m += total_warps) {
+        const Joint3 jc = jn;
+        jn = load_joint(io, m + total_warps);               // next map's joint: latency hidden behind this map
+        const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);
+        MapState st;
+        begin_map(io, jv, st, lane, ACC);
+        run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, false>(io, m, reinterpret_cast<const float4*>(io.pred + (size_t)m * hw),
+                                                         0, hw >> 2, jv, ex, ey, st, lane);
+        if (ACC) end_map_acc(io, m, jv, ex, ey, st, lane);
+        sum_sq += (double)st.acc;
     }
-    // every lane carries the squared error of the quads it visited
-    finish_loss<kThreads>(warp_sum_sq, ws, loss, inv_count);
+    finish_loss<512>(sum_sq, ws, loss, inv_count);     // every lane carries the quads it visited
+}
+
+// Variant B (default): persistent, one CTA per SM, up to 32 warps. Every warp streams its predicted
+// maps through a private ring of small shared-memory slots (1-D TMA bulk copies of `chunk_quads`
+// quads each, mbarrier complete_tx). The map is consumed strictly in order, so a slot is re-armed
+// with the chunk `ring` positions ahead -- possibly of the warp's NEXT map -- the moment it has been
+// read: the copy engine runs a full ring ahead of the arithmetic, nothing stalls on individual
+// global loads, and a 6 KB ring per warp leaves room for 32 resident warps to hide the float64
+// and shared-memory latencies.
+// dynamic smem: [mbarriers 1024 B][factors per warp][ring slots per warp]
+template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
+__global__ void __launch_bounds__(1024, 1)
+encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count,
+                       int nwarps, int ring, int chunk_quads) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = io.H * io.W;
+    const int nq = hw >> 2;
+    const int chunks_per_map = nq / chunk_quads;                 // host guarantees divisibility
+    const uint32_t chunk_bytes = (uint32_t)chunk_quads * 16u;
+    const int wpad = (io.W + 1) & ~1;
+    const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * ring;
+    double* ex = reinterpret_cast<double*>(smem_raw + 1024 + warp * fac_bytes);
+    double* ey = ex + wpad;
+    unsigned char* slots = smem_raw + 1024 + (size_t)nwarps * fac_bytes + (size_t)warp * ring * chunk_bytes;
+    if (lane == 0) {
+        for (int r = 0; r < ring; ++r) sp::mbar_init(bars + r, 1);
+        sp::mbar_fence_init();
+    }
+    __syncthreads();
+    const int gw = blockIdx.x * nwarps + warp;
+    const int total = gridDim.x * nwarps;
+    const int my_maps = (gw < io.nmaps) ? (io.nmaps - gw + total - 1) / total : 0;
+    const long long my_chunks = (long long)my_maps * chunks_per_map;
+
+    // producer cursor (lane 0 only): next chunk to request = (map pm, chunk pc), into slot ps
+    int pm = gw, pc = 0, ps = 0;
+    long long issued = 0;
+    auto issue_next = [&]() {
+        sp::mbar_expect_tx(bars + ps, chunk_bytes);
+        sp::bulk_g2s(slots + (size_t)ps * chunk_bytes, io.pred + (size_t)pm * hw + (size_t)pc * chunk_quads * 4,
+                     chunk_bytes, bars + ps);
+        ++issued;
+        if (++pc == chunks_per_map) { pc = 0; pm += total; }
+        if (++ps == ring) ps = 0;
+    };
+    if (lane == 0)
+        for (int r = 0; r < ring && issued < my_chunks; ++r) issue_next();
+
+    double sum_sq = 0.0;
+    int cs = 0;                 // consumer slot
+    uint32_t parity = 0;
+    Joint3 jn = load_joint(io, gw);
+    for (int m = gw; m < io.nmaps; m += total) {
+        const Joint3 jc = jn;
+        jn = load_joint(io, m + total);                                 // next map's joint, a whole map ahead
+        const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);   // overlaps the copies in flight
+        MapState st;
+        begin_map(io, jv, st, lane, ACC);
+        for (int c = 0; c < chunks_per_map; ++c) {
+            sp::mbar_wait(bars + cs, parity);
+            const float4* chunk = reinterpret_cast<const float4*>(slots + (size_t)cs * chunk_bytes);
+            run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, chunk, c * chunk_quads, (c + 1) * chunk_quads,
+                                                            jv, ex, ey, st, lane);
+            __syncwarp();
+            if (lane == 0 && issued < my_chunks) {
+                sp::fence_proxy_async_smem();
+                issue_next();                                           // refills the slot just drained
+            }
+            if (++cs == ring) { cs = 0; parity ^= 1u; }
+        }
+        if (ACC) end_map_acc(io, m, jv, ex, ey, st, lane);
+        sum_sq += (double)st.acc;
+    }
+    finish_loss<1024>(sum_sq, ws, loss, inv_count);
 }
 
 // HeatMapAcc epilogue (metrics/pose_metrics.py:227-245) on the [B,K] argmax coordinates.
@@ -268,21 +439,75 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     const float norm = (float)(2.0 / count);
     const float half_scale = 0.5f * grad_scale;
     const int wpad = (W + 1) & ~1;
-    const size_t smem = (size_t)kWarps * (wpad + H) * sizeof(double);
+    const size_t fac_bytes = (size_t)(wpad + H) * sizeof(double);
+    MapIo io;
+    io.joints = joints; io.pred = pred; io.grad = grad; io.targets = targets; io.weights = weights;
+    io.pred_xy = reinterpret_cast<float2*>(pred_xy); io.label_xy = reinterpret_cast<float2*>(label_xy);
+    io.nmaps = nmaps; io.H = H; io.W = W; io.reach = reach; io.denom = denom; io.norm = norm; io.half_scale = half_scale;
+    io.analytic_ok = (sigma >= 0.25 && sigma <= 64.0) ? 1 : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
+    const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
+
+    // Ring variant: needs the map to split into equal chunks of a multiple of 32 quads (<= 4 KB)
+    const int nq = (H * W) >> 2;
+    const char* force = getenv("SP_TRAIN_FORCE_LDG");
+    int chunk_quads = 0;
+    if ((H * W) % 4 == 0 && nq % 32 == 0) {
+        int want = 192;                                   // 3 KB
+        const char* ec = getenv("SP_TRAIN_CHUNK_QUADS");
+        if (ec && *ec) want = atoi(ec);
+        if (want < 32) want = 32;
+        for (int d = want - want % 32; d >= 32; d -= 32)
+            if (nq % d == 0) { chunk_quads = d; break; }
+    }
+    if (chunk_quads > 0 && !(force && force[0] == '1')) {
+        const size_t chunk_bytes = (size_t)chunk_quads * 16;
+        const size_t budget = 227 * 1024 - 1024;
+        int ring = 2;
+        const char* er = getenv("SP_TRAIN_RING");
+        if (er && *er) ring = atoi(er);
+        if (ring < 1) ring = 1;
+        if (ring > 8) ring = 8;
+        int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
+        if (nwarps > 32) nwarps = 32;
+        const char* ew = getenv("SP_TRAIN_WARPS");
+        if (ew && *ew) nwarps = atoi(ew) < nwarps ? atoi(ew) : nwarps;
+        if (nwarps < 1) nwarps = 1;
+        SP_RETURN_IF((size_t)nwarps * ring * 8 > 1024, SP_ERR_UNSUPPORTED);
+        const size_t smem = 1024 + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
+        int grid = sp_sm_count();
+        const int need = (nmaps + nwarps - 1) / nwarps;
+        if (grid > need) grid = need;
+#define SP_LAUNCH_RING(G, T, A)                                                                                              \
+    do {                                                                                                                     \
+        SP_CUDA(cudaFuncSetAttribute(encode_mse_ring_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        encode_mse_ring_kernel<G, T, A><<<grid, nwarps * 32, smem, st>>>(io, loss, ws, 1.0 / count, nwarps, ring, chunk_quads); \
+    } while (0)
+        switch (sel) {
+            case 0: SP_LAUNCH_RING(false, false, false); break;
+            case 1: SP_LAUNCH_RING(false, false, true); break;
+            case 2: SP_LAUNCH_RING(false, true, false); break;
+            case 3: SP_LAUNCH_RING(false, true, true); break;
+            case 4: SP_LAUNCH_RING(true, false, false); break;
+            case 5: SP_LAUNCH_RING(true, false, true); break;
+            case 6: SP_LAUNCH_RING(true, true, false); break;
+            default: SP_LAUNCH_RING(true, true, true); break;
+        }
+#undef SP_LAUNCH_RING
+        return sp_launch_status();
+    }
+
+    const size_t smem = (size_t)kWarps * fac_bytes;
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     int grid = (nmaps + kWarps - 1) / kWarps;
     if (grid > kMaxPartials) grid = kMaxPartials;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
 #define SP_LAUNCH_TRAIN(G, T, A)                                                                                         \
     do {                                                                                                                 \
         if (smem > 48 * 1024)                                                                                            \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        encode_mse_kernel<G, T, A><<<grid, kThreads, smem, st>>>(joints, pred, grad, targets, weights, loss, ws,         \
-            reinterpret_cast<float2*>(pred_xy), reinterpret_cast<float2*>(label_xy), nmaps, H, W, reach, denom, norm,    \
-            half_scale, 1.0 / count);                                                                                    \
+        encode_mse_kernel<G, T, A><<<grid, kThreads, smem, st>>>(io, loss, ws, 1.0 / count);                             \
     } while (0)
-    const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
     switch (sel) {
         case 0: SP_LAUNCH_TRAIN(false, false, false); break;
         case 1: SP_LAUNCH_TRAIN(false, false, true); break;

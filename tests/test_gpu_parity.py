@@ -578,3 +578,53 @@ def test_cfg5_coco_val_sized_job_properties(api):
     t, wt = api.transforms.encode_heat_maps(joints)
     xy, conf = dec(t, synth.identity_affines(P, device=DEV))
     assert (xy - mu).abs().max().item() < 1e-3 and (wt == 1).all() and (conf > 0.77).all()
+
+
+@pytest.mark.parametrize("env", [{"SP_TRAIN_FORCE_LDG": "1"}, {"SP_TRAIN_WARPS": "3", "SP_TRAIN_RING": "2"},
+                                 {"SP_TRAIN_RING": "1"}, {"SP_TRAIN_RING": "4", "SP_TRAIN_CHUNK_QUADS": "64"},
+                                 {"SP_TRAIN_CHUNK_QUADS": "768", "SP_TRAIN_RING": "1"}, {"SP_TRAIN_WARPS": "1", "SP_TRAIN_RING": "8"}])
+def test_fused_kernel_variants_agree(api, env):
+    """Every chunk/ring/warp layout of the TMA ring and the plain-load variant give identical outputs."""
+    joints = synth.joints(40, seed=81).to(DEV)
+    pred = synth.heatmaps(40, seed=82).to(DEV)
+    base = api.loss.encode_mse_forward_backward(joints, pred, want_targets=True, want_axes=True)
+    os.environ.update(env)
+    try:
+        other = api.loss.encode_mse_forward_backward(joints, pred, want_targets=True, want_axes=True)
+    finally:
+        for k in env:
+            del os.environ[k]
+    for key in ("grad", "targets", "weights", "pred_xy", "label_xy"):
+        assert torch.equal(base[key], other[key]), key
+    assert abs(base["loss"].item() - other["loss"].item()) <= 1e-6 * abs(base["loss"].item())
+
+
+def test_fused_label_argmax_ties_and_outside_centres(api):
+    """The analytic target argmax (3x3 block around the rounded centre) must reproduce torch.max's
+    first-index rule on exact ties (half-integer centres), near ties, centres outside the map and
+    non-unit weights."""
+    g = torch.Generator().manual_seed(17)
+    j = synth.joints(256, seed=91)
+    j[:64, :, 0] = torch.randint(-7, 54, (64, 17), generator=g).float() + 0.5          # exact x ties
+    j[32:96, :, 1] = torch.randint(-7, 70, (64, 17), generator=g).float() + 0.5        # exact y ties
+    j[96:128, :, 0] = torch.randint(0, 47, (32, 17), generator=g).float() + 0.5 + 1e-6 * torch.randn(32, 17, generator=g)
+    j[128:160, :, 2] = 2.0                                                               # weight 2 (COCO "visible")
+    j[160:176, :, 2] = 0.75                                                              # odd weight
+    t_np, w_np = O.encode_batch(j.numpy())
+    m = torch.from_numpy(w_np)[..., None, None]
+    want, _ = O.argmax_coords(torch.from_numpy(t_np) * m)
+    pred = torch.zeros(256, 17, 64, 48, device=DEV)
+    out = api.loss.encode_mse_forward_backward(j.to(DEV), pred, need_grad=False, want_axes=True)
+    assert torch.equal(out["label_xy"].cpu(), want)
+    os.environ["SP_TRAIN_FORCE_LDG"] = "1"
+    try:
+        out2 = api.loss.encode_mse_forward_backward(j.to(DEV), pred, need_grad=False, want_axes=True)
+    finally:
+        del os.environ["SP_TRAIN_FORCE_LDG"]
+    assert torch.equal(out2["label_xy"].cpu(), want)
+    # sigma outside the analytic range falls back to the tracked argmax
+    t3 = np.stack([O.encode_person(x, 0.2, (48, 64))[0] for x in j.numpy()[:8]])
+    w3 = np.stack([O.encode_person(x, 0.2, (48, 64))[1] for x in j.numpy()[:8]])
+    want3, _ = O.argmax_coords(torch.from_numpy(t3) * torch.from_numpy(w3)[..., None, None])
+    out3 = api.loss.encode_mse_forward_backward(j[:8].to(DEV), pred[:8], sigma=0.2, need_grad=False, want_axes=True)
+    assert torch.equal(out3["label_xy"].cpu(), want3)
