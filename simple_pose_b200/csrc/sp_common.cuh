@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/simple_pose_b200.h"
 
 #define SP_WARP 32
@@ -27,11 +28,43 @@ static inline int sp_sm_count() {
 
 static inline int sp_launch_status() { return (int)cudaGetLastError(); }
 
+// Every kernel of the library is launched with programmatic dependent launch (PDL) allowed: its
+// CTAs may be scheduled while the previous kernel on the stream is still draining, which hides the
+// launch latency and the prologue (mbarrier init, index setup) behind the predecessor's tail. The
+// contract inside the kernels: sp::grid_dep_wait() before the first global-memory access (it returns
+// once the predecessor has completed and its writes are visible), sp::grid_dep_launch() right
+// after it so that the successor can be scheduled as soon as SM resources free up.
+// SP_NO_PDL=1 in the environment restores plain stream-ordered launches.
+static inline bool sp_pdl_enabled() {
+    const char* v = getenv("SP_NO_PDL");
+    return !(v && v[0] == '1');
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sp_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 namespace sp {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// ---- programmatic dependent launch ----------------------------------------------------------
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier (shared::cta) ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

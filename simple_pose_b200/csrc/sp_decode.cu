@@ -456,7 +456,8 @@ __device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map,
 // fast path: persistent CTAs, per-warp TMA rings
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory layout:
-//   [0, 1024)                      mbarriers (nwarps * stages * 8 B)
+//   [0, 512)                       mbarriers (nwarps * stages * 8 B)
+//   [512, 1016)                    map index held by each (warp, stage); [1016] CTA work counter
 //   [1024, 1024 + 1024)            blur weights (<= 225 floats)
 //   then per warp                  patch (kPatchFloats floats, padded to 1536 B)
 //   then per warp, per stage       map a (hw floats) [+ map b if FLIP]
@@ -465,6 +466,10 @@ constexpr int kWtsBytes = 1024;
 constexpr int kPatchBytes = 1536;
 
 // KS = compile-time blur size (11 = the reference's), 0 = runtime A.ksize
+//
+// Work distribution: CTA c owns the contiguous map range [c*nmaps/grid, (c+1)*nmaps/grid) (sizes
+// differ by at most one map across SMs) and its warps pull maps from a shared-memory counter, so
+// the tail of a launch is one map per warp instead of a whole stride of the grid.
 template <bool FLIP, int KS>
 __global__ void __launch_bounds__(512, 1)
 decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
@@ -476,25 +481,36 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
     const uint32_t stage_bytes = FLIP ? 2u * map_bytes : map_bytes;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * stages;
+    int* claimed = reinterpret_cast<int*>(smem + kBarBytes / 2) + warp * stages;    // map held by each stage
+    int& next_map = *reinterpret_cast<int*>(smem + kBarBytes - 8);                  // CTA work counter
     float* wts = reinterpret_cast<float*>(smem + kBarBytes);
     float* patch = reinterpret_cast<float*>(smem + kBarBytes + kWtsBytes + (size_t)warp * kPatchBytes);
     unsigned char* ring = smem + kBarBytes + kWtsBytes + (size_t)nwarps * kPatchBytes +
                           (size_t)warp * stages * stage_bytes;
 
-    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
-        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
+    const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
+    if (threadIdx.x == 0) next_map = range_lo;
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) sp::mbar_init(bars + s, 1);
         sp::mbar_fence_init();
     }
+    sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
+    sp::grid_dep_launch();
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
     LaneTaps<(KS > 0 ? KS : 3)> taps;
     if (KS > 0 && A.mode == SP_DECODE_GAUSS_TAYLOR) taps.load(wts, lane);
 
-    const int gw = blockIdx.x * nwarps + warp;
-    const int total = gridDim.x * nwarps;
-
-    auto issue = [&](int s, int m) {
+    // lane 0: claim the next map of this CTA and start its copy into stage s (or park -1)
+    auto claim_and_issue = [&](int s) {
+        const int m = atomicAdd(&next_map, 1);
+        if (m >= range_hi) {
+            claimed[s] = -1;
+            return;
+        }
+        claimed[s] = m;
         float* dst = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
         sp::mbar_expect_tx(bars + s, stage_bytes);
         sp::bulk_g2s(dst, A.hm + (size_t)m * hw, map_bytes, bars + s);
@@ -505,15 +521,14 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         }
     };
 
-    if (lane == 0) {
-        for (int s = 0; s < stages; ++s) {
-            const int m = gw + s * total;
-            if (m < A.nmaps) issue(s, m);
-        }
-    }
+    if (lane == 0)
+        for (int s = 0; s < stages; ++s) claim_and_issue(s);
     int s = 0;
     uint32_t parity = 0;
-    for (int m = gw; m < A.nmaps; m += total) {
+    for (;;) {
+        __syncwarp();
+        const int m = *reinterpret_cast<volatile int*>(claimed + s);
+        if (m < 0) break;                                  // claims are handed out in order: nothing follows
         const Affine T = load_affine(A, m);
         sp::mbar_wait(bars + s, parity);
         float* a = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
@@ -524,10 +539,9 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
             return taylor_refine_generic(view, wts, patch, A.H, A.W, A.ksize, px, py, ori_max, lane, ox, oy);
         });
         __syncwarp();
-        const int next = m + stages * total;
-        if (lane == 0 && next < A.nmaps) {
+        if (lane == 0) {
             sp::fence_proxy_async_smem();
-            issue(s, next);
+            claim_and_issue(s);
         }
         if (++s == stages) { s = 0; parity ^= 1u; }
     }
@@ -544,6 +558,8 @@ decode_generic_kernel(const DecodeArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int hw = A.H * A.W;
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
     if (A.mode == SP_DECODE_GAUSS_TAYLOR)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
@@ -617,6 +633,7 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
         if (stages > 4) stages = 4;
         stages = env_int("SP_DECODE_STAGES", stages);
         if (stages < 1) stages = 1;
+        while (nwarps * stages > 64 && stages > 1) --stages;       // mbarrier / claim tables hold 64 entries
         while ((size_t)nwarps * (stages * stage_bytes + kPatchBytes) > budget && stages > 1) --stages;
         while ((size_t)nwarps * (stages * stage_bytes + kPatchBytes) > budget && nwarps > 1) --nwarps;
         const size_t smem = kBarBytes + kWtsBytes + (size_t)nwarps * (kPatchBytes + stages * stage_bytes);
@@ -626,7 +643,7 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
 #define SP_LAUNCH_DECODE(F, KS)                                                                                     \
     do {                                                                                                            \
         SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<F, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        decode_tma_kernel<F, KS><<<grid, nwarps * 32, smem, st>>>(A, nwarps, stages);                               \
+        SP_CUDA(sp_launch(decode_tma_kernel<F, KS>, dim3(grid), dim3(nwarps * 32), smem, st, A, nwarps, stages));        \
     } while (0)
         const bool ks11 = (ksize == 11) && !env_int("SP_DECODE_RUNTIME_KSIZE", 0);
         if (flip) { if (ks11) SP_LAUNCH_DECODE(true, 11); else SP_LAUNCH_DECODE(true, 0); }
@@ -637,7 +654,7 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
     int grid = sp_sm_count() * 8;
     const int need = (A.nmaps + 7) / 8;
     if (grid > need) grid = need;
-    if (flip) decode_generic_kernel<true><<<grid, 256, 0, st>>>(A);
-    else      decode_generic_kernel<false><<<grid, 256, 0, st>>>(A);
+    if (flip) SP_CUDA(sp_launch(decode_generic_kernel<true>, dim3(grid), dim3(256), 0, st, A));
+    else      SP_CUDA(sp_launch(decode_generic_kernel<false>, dim3(grid), dim3(256), 0, st, A));
     return sp_launch_status();
 }

@@ -27,6 +27,8 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     double* ey = ex + wpad;
     const int hw = H * W;
     const int total_warps = gridDim.x * kWarpsPerCta;
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
 
     for (int m = blockIdx.x * kWarpsPerCta + warp; m < nmaps; m += total_warps) {
         const float mx = __ldg(joints + 3 * (size_t)m + 0);
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)
 encode_basic_kernel(const float* __restrict__ joints, const float* __restrict__ table, float* __restrict__ targets,
                     float* __restrict__ weights, int nmaps, int H, int W, double reach, float stride, int side) {
     extern __shared__ float tab[];
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
     for (int i = threadIdx.x; i < side * side; i += blockDim.x) tab[i] = __ldg(table + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -145,11 +149,11 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     if (vec4) {
         if (smem > 48 * 1024)
             SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encode_refine_kernel<true><<<grid, kWarpsPerCta * SP_WARP, smem, st>>>(joints, targets, weights, nmaps, H, W, reach, denom);
+        SP_CUDA(sp_launch(encode_refine_kernel<true>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom));
     } else {
         if (smem > 48 * 1024)
             SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        encode_refine_kernel<false><<<grid, kWarpsPerCta * SP_WARP, smem, st>>>(joints, targets, weights, nmaps, H, W, reach, denom);
+        SP_CUDA(sp_launch(encode_refine_kernel<false>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom));
     }
     return sp_launch_status();
 }
@@ -162,7 +166,7 @@ extern "C" int sp_encode_basic_f32(const float* joints, const float* table, floa
     if (B == 0) return 0;
     const int nmaps = B * K;
     const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
-    encode_basic_kernel<<<grid, kWarpsPerCta * SP_WARP, (size_t)side * side * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        joints, table, targets, weights, nmaps, H, W, sigma * 3.0, (float)stride, side);
+    SP_CUDA(sp_launch(encode_basic_kernel, dim3(grid), dim3(kWarpsPerCta * SP_WARP), (size_t)side * side * sizeof(float),
+                      static_cast<cudaStream_t>(stream), joints, table, targets, weights, nmaps, H, W, sigma * 3.0, (float)stride, side));
     return sp_launch_status();
 }

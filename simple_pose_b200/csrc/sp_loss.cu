@@ -40,6 +40,8 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
                    MseWorkspace* __restrict__ ws, int nmaps, int hw, float norm, float half_scale,
                    double inv_count, int skip_masked) {
     double block_sum = 0.0;
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
 
     for (int m = blockIdx.x; m < nmaps; m += gridDim.x) {
         const float mk = __ldg(mask + m);
@@ -89,6 +91,8 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
 
 __global__ void __launch_bounds__(256)
 scale_inplace_kernel(float* __restrict__ data, long long n, const float* __restrict__ scale_dev) {
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
     const float s = __ldg(scale_dev);
     if (s == 1.0f) return;
     const long long n4 = n >> 2;
@@ -126,7 +130,7 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
     const int skip = (flags & SP_MSE_SKIP_MASKED) ? 1 : 0;
 #define SP_LAUNCH_MSE(V, G) \
-    mse_fwd_bwd_kernel<V, G><<<grid, kThreads, 0, st>>>(pred, target, mask, grad, loss, ws, nmaps, HW, norm, half_scale, 1.0 / count, skip)
+    SP_CUDA(sp_launch(mse_fwd_bwd_kernel<V, G>, dim3(grid), dim3(kThreads), 0, st, pred, target, mask, grad, loss, ws, nmaps, HW, norm, half_scale, 1.0 / count, skip))
     if (vec4) { if (grad) SP_LAUNCH_MSE(true, true); else SP_LAUNCH_MSE(true, false); }
     else      { if (grad) SP_LAUNCH_MSE(false, true); else SP_LAUNCH_MSE(false, false); }
 #undef SP_LAUNCH_MSE
@@ -141,6 +145,6 @@ extern "C" int sp_scale_inplace_f32(float* data, long long n, const float* scale
     const long long cap = (long long)sp_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    scale_inplace_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n, scale_dev);
+    SP_CUDA(sp_launch(scale_inplace_kernel, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), data, n, scale_dev));
     return sp_launch_status();
 }

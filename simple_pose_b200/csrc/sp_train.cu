@@ -288,6 +288,8 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
     const int hw = io.H * io.W;
     const int total_warps = gridDim.x * kWarps;
     double sum_sq = 0.0;
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
     Joint3 jn = load_joint(io, blockIdx.x * kWarps + warp);
     for (int m = blockIdx.x * kWarps + warp; m < io.nmaps; m += total_warps) {
         const Joint3 jc = jn;
@@ -310,7 +312,13 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
 // read: the copy engine runs a full ring ahead of the arithmetic, nothing stalls on individual
 // global loads, and a 6 KB ring per warp leaves room for 32 resident warps to hide the float64
 // and shared-memory latencies.
-// dynamic smem: [mbarriers 1024 B][factors per warp][ring slots per warp]
+// Work distribution: CTA c owns the contiguous map range [c*nmaps/grid, (c+1)*nmaps/grid); its warps
+// claim maps from a shared-memory counter (lane 0, one map ahead of the copies it is issuing) and
+// pass the claimed indices to the consuming lanes through a small per-warp FIFO.
+// dynamic smem: [mbarriers 1024 B][claim FIFOs + work counter 2048 B][factors per warp][ring slots per warp]
+constexpr int kFifo = 16;          // entries per warp; the producer is never more than ring+2 <= 10 maps ahead
+constexpr int kRingHeader = 1024 + 2048 + 64;
+
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
 __global__ void __launch_bounds__(1024, 1)
 encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count,
@@ -325,40 +333,61 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     const int wpad = (io.W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * ring;
-    double* ex = reinterpret_cast<double*>(smem_raw + 1024 + warp * fac_bytes);
+    volatile int* fifo = reinterpret_cast<int*>(smem_raw + 1024) + warp * kFifo;
+    int& next_map = *reinterpret_cast<int*>(smem_raw + 1024 + 2048);
+    double* ex = reinterpret_cast<double*>(smem_raw + kRingHeader + warp * fac_bytes);
     double* ey = ex + wpad;
-    unsigned char* slots = smem_raw + 1024 + (size_t)nwarps * fac_bytes + (size_t)warp * ring * chunk_bytes;
+    unsigned char* slots = smem_raw + kRingHeader + (size_t)nwarps * fac_bytes + (size_t)warp * ring * chunk_bytes;
+    const int range_lo = (int)((long long)blockIdx.x * io.nmaps / gridDim.x);
+    const int range_hi = (int)((long long)(blockIdx.x + 1) * io.nmaps / gridDim.x);
+    if (threadIdx.x == 0) next_map = range_lo;
     if (lane == 0) {
         for (int r = 0; r < ring; ++r) sp::mbar_init(bars + r, 1);
         sp::mbar_fence_init();
     }
     __syncthreads();
-    const int gw = blockIdx.x * nwarps + warp;
-    const int total = gridDim.x * nwarps;
-    const int my_maps = (gw < io.nmaps) ? (io.nmaps - gw + total - 1) / total : 0;
-    const long long my_chunks = (long long)my_maps * chunks_per_map;
+    sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
+    sp::grid_dep_launch();
 
-    // producer cursor (lane 0 only): next chunk to request = (map pm, chunk pc), into slot ps
-    int pm = gw, pc = 0, ps = 0;
-    long long issued = 0;
+    // producer (lane 0 only): copies chunk pc of map pm into slot ps; pnext = the map claimed after pm
+    int pm = -1, pnext = -1, pc = 0, ps = 0, tail = 0;
+    auto claim = [&]() {
+        const int m = atomicAdd(&next_map, 1);
+        const int got = (m < range_hi) ? m : -1;
+        fifo[tail & (kFifo - 1)] = got;
+        ++tail;
+        return got;
+    };
     auto issue_next = [&]() {
+        if (pm < 0) return;
         sp::mbar_expect_tx(bars + ps, chunk_bytes);
         sp::bulk_g2s(slots + (size_t)ps * chunk_bytes, io.pred + (size_t)pm * hw + (size_t)pc * chunk_quads * 4,
                      chunk_bytes, bars + ps);
-        ++issued;
-        if (++pc == chunks_per_map) { pc = 0; pm += total; }
+        if (++pc == chunks_per_map) {
+            pc = 0;
+            pm = pnext;
+            pnext = (pm >= 0) ? claim() : -1;
+        }
         if (++ps == ring) ps = 0;
     };
-    if (lane == 0)
-        for (int r = 0; r < ring && issued < my_chunks; ++r) issue_next();
+    if (lane == 0) {
+        pm = claim();
+        pnext = (pm >= 0) ? claim() : -1;
+        for (int r = 0; r < ring; ++r) issue_next();
+    }
+    __syncwarp();
 
     double sum_sq = 0.0;
     int cs = 0;                 // consumer slot
     uint32_t parity = 0;
-    Joint3 jn = load_joint(io, gw);
-    for (int m = gw; m < io.nmaps; m += total) {
+    int head = 0;
+    int m = fifo[0];
+    Joint3 jn = load_joint(io, m >= 0 ? m : io.nmaps);
+    while (m >= 0) {
         const Joint3 jc = jn;
-        jn = load_joint(io, m + total);                                 // next map's joint, a whole map ahead
+        // the producer claimed this map's successor before it issued this map's first chunk
+        const int m_next = fifo[(head + 1) & (kFifo - 1)];
+        jn = load_joint(io, m_next >= 0 ? m_next : io.nmaps);           // next map's joint, a whole map ahead
         const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);   // overlaps the copies in flight
         MapState st;
         begin_map(io, jv, st, lane, ACC);
@@ -368,7 +397,7 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
             run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, chunk, c * chunk_quads, (c + 1) * chunk_quads,
                                                             jv, ex, ey, st, lane);
             __syncwarp();
-            if (lane == 0 && issued < my_chunks) {
+            if (lane == 0) {
                 sp::fence_proxy_async_smem();
                 issue_next();                                           // refills the slot just drained
             }
@@ -376,6 +405,9 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         }
         if (ACC) end_map_acc(io, m, jv, ex, ey, st, lane);
         sum_sq += (double)st.acc;
+        __syncwarp();
+        ++head;
+        m = m_next;
     }
     finish_loss<1024>(sum_sq, ws, loss, inv_count);
 }
@@ -385,6 +417,8 @@ __global__ void __launch_bounds__(256)
 heatmap_acc_kernel(const float2* __restrict__ pred_xy, const float2* __restrict__ label_xy, float* __restrict__ acc,
                    int B, int K, float norm_x, float norm_y, float thresh) {
     extern __shared__ int counters[];        // hit[K], valid[K]
+    sp::grid_dep_wait();
+    sp::grid_dep_launch();
     int* hit = counters;
     int* valid = counters + K;
     for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) counters[k] = 0;
@@ -463,7 +497,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     }
     if (chunk_quads > 0 && !(force && force[0] == '1')) {
         const size_t chunk_bytes = (size_t)chunk_quads * 16;
-        const size_t budget = 227 * 1024 - 1024;
+        const size_t budget = 227 * 1024 - kRingHeader;
         int ring = 2;
         const char* er = getenv("SP_TRAIN_RING");
         if (er && *er) ring = atoi(er);
@@ -475,14 +509,14 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         if (ew && *ew) nwarps = atoi(ew) < nwarps ? atoi(ew) : nwarps;
         if (nwarps < 1) nwarps = 1;
         SP_RETURN_IF((size_t)nwarps * ring * 8 > 1024, SP_ERR_UNSUPPORTED);
-        const size_t smem = 1024 + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
+        const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
         int grid = sp_sm_count();
         const int need = (nmaps + nwarps - 1) / nwarps;
         if (grid > need) grid = need;
 #define SP_LAUNCH_RING(G, T, A)                                                                                              \
     do {                                                                                                                     \
         SP_CUDA(cudaFuncSetAttribute(encode_mse_ring_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        encode_mse_ring_kernel<G, T, A><<<grid, nwarps * 32, smem, st>>>(io, loss, ws, 1.0 / count, nwarps, ring, chunk_quads); \
+        SP_CUDA(sp_launch(encode_mse_ring_kernel<G, T, A>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, ring, chunk_quads)); \
     } while (0)
         switch (sel) {
             case 0: SP_LAUNCH_RING(false, false, false); break;
@@ -506,7 +540,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     do {                                                                                                                 \
         if (smem > 48 * 1024)                                                                                            \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        encode_mse_kernel<G, T, A><<<grid, kThreads, smem, st>>>(io, loss, ws, 1.0 / count);                             \
+        SP_CUDA(sp_launch(encode_mse_kernel<G, T, A>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count));       \
     } while (0)
     switch (sel) {
         case 0: SP_LAUNCH_TRAIN(false, false, false); break;
@@ -530,8 +564,8 @@ extern "C" int sp_heatmap_acc_f32(const float* pred_xy, const float* label_xy, f
     SP_RETURN_IF(!sp_aligned16(pred_xy) || !sp_aligned16(label_xy), SP_ERR_BAD_ALIGNMENT);
     // norm = tensor([W, H], float32) / norm_frac
     const float nx = (float)W / norm_frac, ny = (float)H / norm_frac;
-    heatmap_acc_kernel<<<1, 256, (size_t)2 * K * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float2*>(pred_xy), reinterpret_cast<const float2*>(label_xy), acc, B, K, nx, ny,
-        distance_thresh);
+    SP_CUDA(sp_launch(heatmap_acc_kernel, dim3(1), dim3(256), (size_t)2 * K * sizeof(int), static_cast<cudaStream_t>(stream),
+                      reinterpret_cast<const float2*>(pred_xy), reinterpret_cast<const float2*>(label_xy), acc, B, K, nx, ny,
+                      distance_thresh));
     return sp_launch_status();
 }
