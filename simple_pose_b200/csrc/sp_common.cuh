@@ -26,6 +26,12 @@ static inline int sp_sm_count() {
     return cached[dev];
 }
 
+static inline int sp_env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    if (!v || !*v) return fallback;
+    return atoi(v);
+}
+
 static inline int sp_launch_status() { return (int)cudaGetLastError(); }
 
 // Every kernel of the library is launched with programmatic dependent launch (PDL) allowed: its

@@ -3,11 +3,22 @@
 //  loss = 0.5 * MSELoss(pred * mask[..., None, None], target * mask[..., None, None]); loss.backward()).
 //
 // HBM-bound: reads pred and target once, writes grad once (3 streams; the ATen sequence makes
-// ~6 passes and two temporaries). Each CTA walks whole (person, joint) maps so the mask is a
-// per-map scalar; 16-byte loads, several in flight per thread. The sum of squares is
-// accumulated per thread in float32 over a few elements, then in float64 across the block;
-// block partials go to the caller's workspace and the last block to finish adds them in a
-// fixed order (deterministic, no floating-point atomics) and writes the scalar loss.
+// ~6 passes and two temporaries).
+//
+// Main kernel (mse_ring_kernel): persistent, one CTA per SM. A CTA owns a contiguous range of
+// fixed-size chunks (a chunk never straddles a map, so the mask is one scalar per chunk) and deals
+// them round-robin to its warps, so at any moment the SM reads and writes ONE contiguous window of
+// a few tens of KB -- HBM row-buffer friendly -- instead of one stream per warp. Every warp owns a
+// small ring of shared-memory slots filled by 1-D TMA bulk copies (pred chunk + target chunk on one
+// mbarrier); it consumes a slot with 16-byte shared loads, stores the gradient with coalesced
+// 16-byte global stores and re-arms the slot at once. Measured on B200 (scratch/stream_bench.cu):
+// for a 2-reads-1-write stream ~50-100 KB in flight per SM in few, large requests beats both the
+// classic "many threads, one float4 each" loop (-8 %) and deeper rings (HBM read/write turnarounds).
+// Fallback (mse_fwd_bwd_kernel): any shape / alignment, and the SKIP_MASKED variant.
+//
+// The sum of squares is accumulated per thread in float32 over a few elements, then in float64;
+// block partials go to the caller's workspace and the last block to finish adds them in a fixed
+// order (deterministic, no floating-point atomics) and writes the scalar loss.
 //
 // Arithmetic follows ATen so that grad is bit-identical for finite inputs:
 //   d = fl(m*p) - fl(m*t); grad = ((fl(2/N) * d) * 0.5) * m   (mse_loss_backward, then mul backward)
@@ -89,6 +100,79 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
     finish_loss<kThreads>(block_sum, ws, loss, inv_count);
 }
 
+// dynamic smem: [mbarriers 1024 B][per warp: ring x (pred chunk | target chunk)]
+constexpr int kRingBarBytes = 1024;
+
+template <bool WRITE_GRAD>
+__global__ void __launch_bounds__(1024, 1)
+mse_ring_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ mask,
+                float* __restrict__ grad, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
+                long long nchunks, int chunk_quads, int chunks_per_map, int nwarps, int ring,
+                float norm, float half_scale, double inv_count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t chunk_bytes = (uint32_t)chunk_quads * 16u;
+    const size_t chunk_floats = (size_t)chunk_quads * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * ring;
+    unsigned char* slots = smem_raw + kRingBarBytes + (size_t)warp * ring * 2 * chunk_bytes;
+    if (lane == 0) {
+        for (int r = 0; r < ring; ++r) sp::mbar_init(bars + r, 1);
+        sp::mbar_fence_init();
+    }
+    __syncwarp();
+    const long long lo = (long long)blockIdx.x * nchunks / gridDim.x;
+    const long long hi = (long long)(blockIdx.x + 1) * nchunks / gridDim.x;
+    sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
+    sp::grid_dep_launch();
+
+    long long pi = lo + warp;       // producer cursor (lane 0): next chunk to request, into slot ps
+    int ps = 0;
+    auto issue_next = [&]() {
+        if (pi >= hi) return;
+        unsigned char* dst = slots + (size_t)ps * 2 * chunk_bytes;
+        sp::mbar_expect_tx(bars + ps, 2 * chunk_bytes);
+        sp::bulk_g2s(dst, pred + pi * chunk_floats, chunk_bytes, bars + ps);
+        sp::bulk_g2s(dst + chunk_bytes, target + pi * chunk_floats, chunk_bytes, bars + ps);
+        pi += nwarps;
+        if (++ps == ring) ps = 0;
+    };
+    if (lane == 0)
+        for (int r = 0; r < ring; ++r) issue_next();
+
+    double sum_sq = 0.0;
+    int cs = 0;
+    uint32_t parity = 0;
+    for (long long i = lo + warp; i < hi; i += nwarps) {
+        const float mk = __ldg(mask + i / chunks_per_map);          // latency hidden behind the wait below
+        sp::mbar_wait(bars + cs, parity);
+        const float4* p4 = reinterpret_cast<const float4*>(slots + (size_t)cs * 2 * chunk_bytes);
+        const float4* t4 = reinterpret_cast<const float4*>(slots + (size_t)cs * 2 * chunk_bytes + chunk_bytes);
+        float4* g4 = reinterpret_cast<float4*>(grad + i * chunk_floats);
+        float acc = 0.f;
+#pragma unroll 3
+        for (int q = lane; q < chunk_quads; q += 32) {
+            const float4 p = p4[q];
+            const float4 t = t4[q];
+            float4 g;
+            float d;
+            d = sq_err_and_grad(p.x, t.x, mk, norm, half_scale, g.x); acc = fmaf(d, d, acc);
+            d = sq_err_and_grad(p.y, t.y, mk, norm, half_scale, g.y); acc = fmaf(d, d, acc);
+            d = sq_err_and_grad(p.z, t.z, mk, norm, half_scale, g.z); acc = fmaf(d, d, acc);
+            d = sq_err_and_grad(p.w, t.w, mk, norm, half_scale, g.w); acc = fmaf(d, d, acc);
+            if (WRITE_GRAD) g4[q] = g;
+        }
+        sum_sq += (double)acc;
+        __syncwarp();
+        if (lane == 0) {
+            sp::fence_proxy_async_smem();
+            issue_next();                                           // refills the slot just drained
+        }
+        if (++cs == ring) { cs = 0; parity ^= 1u; }
+    }
+    finish_loss<1024>(sum_sq, ws, loss, inv_count);
+}
+
 __global__ void __launch_bounds__(256)
 scale_inplace_kernel(float* __restrict__ data, long long n, const float* __restrict__ scale_dev) {
     sp::grid_dep_wait();
@@ -123,12 +207,50 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
     const float norm = (float)(2.0 / count);       // ATen: norm = 2 / numel, applied in float32
     const float half_scale = 0.5f * grad_scale;    // the 0.5 of the loss expression times upstream grad
     const bool vec4 = (HW % 4 == 0) && sp_aligned16(pred) && sp_aligned16(target) && (!grad || sp_aligned16(grad));
-    int grid = sp_sm_count() * 8;
-    if (grid > nmaps) grid = nmaps;
-    if (grid > kMaxPartials) grid = kMaxPartials;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
     const int skip = (flags & SP_MSE_SKIP_MASKED) ? 1 : 0;
+
+    // ring kernel: needs 16-byte rows and a chunk size (in quads) that divides the map
+    if (vec4 && !skip && !sp_env_int("SP_LOSS_FORCE_LDG", 0)) {
+        const int nq = HW >> 2;
+        int want = sp_env_int("SP_LOSS_CHUNK_QUADS", 192);           // 3 KB per stream
+        if (want < 8) want = 8;
+        if (want > 2048) want = 2048;
+        int chunk_quads = 0;
+        for (int d = want < nq ? want : nq; d >= 8; --d)
+            if (nq % d == 0) { chunk_quads = d; break; }
+        if (chunk_quads * 2 >= (want < nq ? want : nq)) {            // else: awkward map size, use the fallback
+            int ring = sp_env_int("SP_LOSS_RING", 3);
+            if (ring < 1) ring = 1;
+            if (ring > 8) ring = 8;
+            int nwarps = sp_env_int("SP_LOSS_WARPS", 4);   // 4 warps x 3 slots x 6 KB = 72 KB in flight per SM (sweep: profiles/)
+            if (nwarps < 1) nwarps = 1;
+            if (nwarps > 32) nwarps = 32;
+            const size_t slot_bytes = (size_t)chunk_quads * 32;      // pred chunk + target chunk
+            while (nwarps > 1 && (kRingBarBytes + (size_t)nwarps * ring * slot_bytes > 227 * 1024 || nwarps * ring * 8 > kRingBarBytes)) --nwarps;
+            const size_t smem = kRingBarBytes + (size_t)nwarps * ring * slot_bytes;
+            if (smem <= 227 * 1024 && nwarps * ring * 8 <= kRingBarBytes) {
+                const long long nchunks = (long long)nmaps * (nq / chunk_quads);
+                int grid = sp_sm_count();
+                if ((long long)grid * nwarps > nchunks) grid = (int)((nchunks + nwarps - 1) / nwarps);
+                if (grad) {
+                    SP_CUDA(cudaFuncSetAttribute(mse_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    SP_CUDA(sp_launch(mse_ring_kernel<true>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
+                                      nchunks, chunk_quads, nq / chunk_quads, nwarps, ring, norm, half_scale, 1.0 / count));
+                } else {
+                    SP_CUDA(cudaFuncSetAttribute(mse_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    SP_CUDA(sp_launch(mse_ring_kernel<false>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
+                                      nchunks, chunk_quads, nq / chunk_quads, nwarps, ring, norm, half_scale, 1.0 / count));
+                }
+                return sp_launch_status();
+            }
+        }
+    }
+
+    int grid = sp_sm_count() * 8;
+    if (grid > nmaps) grid = nmaps;
+    if (grid > kMaxPartials) grid = kMaxPartials;
 #define SP_LAUNCH_MSE(V, G) \
     SP_CUDA(sp_launch(mse_fwd_bwd_kernel<V, G>, dim3(grid), dim3(kThreads), 0, st, pred, target, mask, grad, loss, ws, nmaps, HW, norm, half_scale, 1.0 / count, skip))
     if (vec4) { if (grad) SP_LAUNCH_MSE(true, true); else SP_LAUNCH_MSE(true, false); }

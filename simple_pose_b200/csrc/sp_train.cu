@@ -504,7 +504,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         if (ring < 1) ring = 1;
         if (ring > 8) ring = 8;
         int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
-        if (nwarps > 32) nwarps = 32;
+        if (nwarps > 16) nwarps = 16;                     // 16 x 2 x 3 KB = 96 KB in flight per SM: more is slower (sweep: profiles/)
         const char* ew = getenv("SP_TRAIN_WARPS");
         if (ew && *ew) nwarps = atoi(ew) < nwarps ? atoi(ew) : nwarps;
         if (nwarps < 1) nwarps = 1;
