@@ -228,9 +228,9 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
             if (nwarps < 1) nwarps = 1;
             if (nwarps > 32) nwarps = 32;
             const size_t slot_bytes = (size_t)chunk_quads * 32;      // pred chunk + target chunk
-            while (nwarps > 1 && (kRingBarBytes + (size_t)nwarps * ring * slot_bytes > 227 * 1024 || nwarps * ring * 8 > kRingBarBytes)) --nwarps;
+            while (nwarps > 1 && (kRingBarBytes + (size_t)nwarps * ring * slot_bytes > 226 * 1024 || nwarps * ring * 8 > kRingBarBytes)) --nwarps;
             const size_t smem = kRingBarBytes + (size_t)nwarps * ring * slot_bytes;
-            if (smem <= 227 * 1024 && nwarps * ring * 8 <= kRingBarBytes) {
+            if (smem <= 226 * 1024 && nwarps * ring * 8 <= kRingBarBytes) {    // 1 KB spare for static shared memory
                 const long long nchunks = (long long)nmaps * (nq / chunk_quads);
                 int grid = sp_sm_count();
                 if ((long long)grid * nwarps > nchunks) grid = (int)((nchunks + nwarps - 1) / nwarps);

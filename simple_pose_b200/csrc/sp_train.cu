@@ -44,12 +44,17 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 struct QuadBest {
     float best;
     int bq;
+    int bsub;          // first element of quad bq that equals best
     float poison;
-    __device__ __forceinline__ void init() { best = -CUDART_INF_F; bq = 0x3fffffff; poison = 0.f; }
+    __device__ __forceinline__ void init() { best = -CUDART_INF_F; bq = 0x0fffffff; bsub = 0; poison = 0.f; }
     __device__ __forceinline__ void push(float a, float b, float c, float d, int q) {
         const float m4 = sp::fmax_nan(sp::fmax_nan(a, b), sp::fmax_nan(c, d));
         poison = fmaf(m4, 0.f, poison);
-        if (m4 > best) { best = m4; bq = q; }
+        if (m4 > best) {
+            best = m4;
+            bq = q;
+            bsub = (a == m4) ? 0 : (b == m4) ? 1 : (c == m4) ? 2 : 3;
+        }
     }
 };
 
@@ -140,7 +145,7 @@ __device__ __forceinline__ void run_quads_impl(const MapIo& io, int m, const flo
     float acc = st.acc;
     QuadBest bp = st.bp, bt = st.bt;
     const bool draw = jv.draw, track = st.track, track_t = st.track_t;
-#pragma unroll 2
+#pragma unroll 3
     for (int q = q_begin + lane; q < q_end; q += 32) {
         const float4 p = SMEM_PRED ? chunk[q - q_begin] : ldg_stream4(chunk + (q - q_begin));
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,7 +200,7 @@ __device__ __forceinline__ void run_quads(const MapIo& io, int m, const float4* 
 // copy may already have been recycled.
 __device__ __forceinline__ void end_map_acc(const MapIo& io, int m, const JointVerdict& jv, const double* ex,
                                             const double* ey, const MapState& st, int lane) {
-    const int W = io.W, hw = io.H * io.W, qpr = W >> 2;
+    const int W = io.W, hw = io.H * io.W;
     const float mk = jv.weight;
     float2 pxy = make_float2(0.f, 0.f), lxy = make_float2(0.f, 0.f);
     if (st.track) {
@@ -206,13 +211,10 @@ __device__ __forceinline__ void end_map_acc(const MapIo& io, int m, const JointV
             MaskedPredView view{src, mk};
             argmax_exact_scan(view, hw, lane, pv, pi);
         } else {
-            const float gmax = warp_max_f32(st.bp.best);
-            const unsigned gq = __reduce_min_sync(SP_FULL, (st.bp.best == gmax) ? (unsigned)st.bp.bq : 0x7fffffffu);
-            const float4 w = __ldg(reinterpret_cast<const float4*>(src) + gq);
-            const float a = __fmul_rn(mk, w.x), b = __fmul_rn(mk, w.y), c = __fmul_rn(mk, w.z);
-            const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
-            pv = gmax;
-            pi = 4 * (int)gq + sub;
+            // every lane tracked the first maximal element of its own quads: the smallest flat index
+            // among the lanes that hold the warp-wide maximum is torch.max's answer
+            pv = warp_max_f32(st.bp.best);
+            pi = (int)__reduce_min_sync(SP_FULL, (st.bp.best == pv) ? (unsigned)(4 * st.bp.bq + st.bp.bsub) : 0x7fffffffu);
         }
         pxy = axis_of(pv, pi, W);
         // target map: fl(m * t); always finite
@@ -229,14 +231,8 @@ __device__ __forceinline__ void end_map_acc(const MapIo& io, int m, const JointV
             lxy = axis_of(gmax, (int)gi, W);
         } else if (jv.draw) {
             const float gmax = warp_max_f32(st.bt.best);
-            const unsigned gq = __reduce_min_sync(SP_FULL, (st.bt.best == gmax) ? (unsigned)st.bt.bq : 0x7fffffffu);
-            const int gy = (int)gq / qpr, gx = 4 * ((int)gq - gy * qpr);
-            const double fy = ey[gy];
-            const float a = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 0], fy)));
-            const float b = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 1], fy)));
-            const float c = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[gx + 2], fy)));
-            const int sub = (a == gmax) ? 0 : (b == gmax) ? 1 : (c == gmax) ? 2 : 3;
-            lxy = axis_of(gmax, 4 * (int)gq + sub, W);
+            const unsigned gi = __reduce_min_sync(SP_FULL, (st.bt.best == gmax) ? (unsigned)(4 * st.bt.bq + st.bt.bsub) : 0x7fffffffu);
+            lxy = axis_of(gmax, (int)gi, W);
         }
     }
     if (lane == 0) {
@@ -320,7 +316,7 @@ constexpr int kFifo = 16;          // entries per warp; the producer is never mo
 constexpr int kRingHeader = 1024 + 2048 + 64;
 
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count,
                        int nwarps, int ring, int chunk_quads) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -409,7 +405,7 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         ++head;
         m = m_next;
     }
-    finish_loss<1024>(sum_sq, ws, loss, inv_count);
+    finish_loss<512>(sum_sq, ws, loss, inv_count);
 }
 
 // HeatMapAcc epilogue (metrics/pose_metrics.py:227-245) on the [B,K] argmax coordinates.
@@ -497,16 +493,15 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     }
     if (chunk_quads > 0 && !(force && force[0] == '1')) {
         const size_t chunk_bytes = (size_t)chunk_quads * 16;
-        const size_t budget = 227 * 1024 - kRingHeader;
+        const size_t budget = 226 * 1024 - kRingHeader;        // 1 KB spare for static shared memory
         int ring = 2;
         const char* er = getenv("SP_TRAIN_RING");
         if (er && *er) ring = atoi(er);
         if (ring < 1) ring = 1;
         if (ring > 8) ring = 8;
         int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
-        if (nwarps > 16) nwarps = 16;                     // 16 x 2 x 3 KB = 96 KB in flight per SM: more is slower (sweep: profiles/)
-        const char* ew = getenv("SP_TRAIN_WARPS");
-        if (ew && *ew) nwarps = atoi(ew) < nwarps ? atoi(ew) : nwarps;
+        if (nwarps > 16) nwarps = 16;      // 16 x 2 x 3 KB = 96 KB in flight per SM; more warps = more HBM streams = slower
+        { const int w = sp_env_int("SP_TRAIN_WARPS", 16); if (w < nwarps) nwarps = w; }
         if (nwarps < 1) nwarps = 1;
         SP_RETURN_IF((size_t)nwarps * ring * 8 > 1024, SP_ERR_UNSUPPORTED);
         const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
