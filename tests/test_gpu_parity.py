@@ -628,3 +628,93 @@ def test_fused_label_argmax_ties_and_outside_centres(api):
     want3, _ = O.argmax_coords(torch.from_numpy(t3) * torch.from_numpy(w3)[..., None, None])
     out3 = api.loss.encode_mse_forward_backward(j[:8].to(DEV), pred[:8], sigma=0.2, need_grad=False, want_axes=True)
     assert torch.equal(out3["label_xy"].cpu(), want3)
+
+
+# --------------------------------------------------------------- kernel layouts and launch ordering
+@pytest.mark.parametrize("env", [{"SP_LOSS_FORCE_LDG": "1"}, {"SP_LOSS_WARPS": "1", "SP_LOSS_RING": "1"},
+                                 {"SP_LOSS_WARPS": "7", "SP_LOSS_RING": "4", "SP_LOSS_CHUNK_QUADS": "64"},
+                                 {"SP_LOSS_WARPS": "32", "SP_LOSS_RING": "2", "SP_LOSS_CHUNK_QUADS": "96"},
+                                 {"SP_LOSS_CHUNK_QUADS": "768", "SP_LOSS_RING": "8"},
+                                 {"SP_LOSS_CHUNK_QUADS": "100"}, {"SP_NO_PDL": "1"}])
+@pytest.mark.parametrize("b,hw", [(40, (64, 48)), (3, (96, 72)), (9, (20, 12))])
+def test_loss_kernel_variants_agree(api, env, b, hw):
+    """Every chunk/ring/warp layout of the TMA-ring loss kernel, the plain-load fallback and the
+    non-PDL launch give bit-identical gradients and the same loss (float64 partial order aside)."""
+    h, w = hw
+    tgt = synth.heatmaps(b, height=h, width=w, seed=11).to(DEV)
+    msk = (torch.rand(b, 17, generator=torch.Generator().manual_seed(12)) > 0.25).float().to(DEV)
+    msk[0, 0] = 2.0                                                # non-unit weight
+    pred = synth.predictions_like(tgt.cpu(), seed=13).to(DEV)
+    base_loss, base_grad = api.loss.mse_forward_backward(pred, tgt, msk)
+    fwd_only, none = api.loss.mse_forward_backward(pred, tgt, msk, need_grad=False)
+    assert none is None and fwd_only.item() == base_loss.item()
+    os.environ.update(env)
+    try:
+        loss, grad = api.loss.mse_forward_backward(pred, tgt, msk)
+        loss_f, _ = api.loss.mse_forward_backward(pred, tgt, msk, need_grad=False)
+    finally:
+        for k in env:
+            del os.environ[k]
+    assert torch.equal(grad, base_grad)
+    assert abs(loss.item() - base_loss.item()) <= 1e-6 * abs(base_loss.item())
+    assert loss_f.item() == loss.item()
+    ref_loss, ref_grad = O.masked_mse_loss_and_grad(pred.cpu(), tgt.cpu(), msk.cpu())
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert torch.allclose(grad.cpu(), ref_grad, rtol=1e-5, atol=1e-12)
+
+
+def test_back_to_back_dependent_launches(api):
+    """Programmatic dependent launch: every kernel may be scheduled while its predecessor drains, so
+    the chain encode -> loss (reads the targets just written, RAW) -> decode (reads the gradient
+    just written) -> encode (overwrites the targets the loss was reading, WAR), issued 40 times
+    without any host synchronisation, must give exactly what the stream-ordered launches give."""
+    from simple_pose_b200.pipeline import HeatmapHotPath
+    n, rounds = 96, 40
+    hp = HeatmapHotPath(n, 17, 64, 48, device=torch.device(DEV))
+    joints = [synth.joints(n, seed=200 + i).to(DEV) for i in range(4)]
+    pred = [synth.heatmaps(n, seed=300 + i).to(DEV) for i in range(4)]
+    ident = synth.identity_affines(n, device=DEV)
+    losses = torch.zeros(rounds, device=DEV)
+    coords = torch.zeros(rounds, n, 17, 2, device=DEV)
+
+    def chain(sync):
+        losses.zero_()
+        coords.zero_()
+        for r in range(rounds):
+            hp.encode(joints[r % 4])
+            hp.loss_fwd_bwd(pred[r % 4])
+            hp.decode(hp.targets, ident)             # decodes what the encoder of this round wrote
+            losses[r].copy_(hp.loss)
+            coords[r].copy_(hp.coords)
+            hp.train_fused(joints[(r + 1) % 4], pred[r % 4])    # same loss buffer, different value
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return losses.clone(), coords.clone()
+
+    os.environ["SP_NO_PDL"] = "1"
+    try:
+        want_l, want_c = chain(sync=True)
+    finally:
+        del os.environ["SP_NO_PDL"]
+    for _ in range(3):
+        got_l, got_c = chain(sync=False)
+        assert torch.equal(got_l, want_l) and torch.equal(got_c, want_c)
+    assert len(set(want_l.tolist())) >= 4            # the four input sets really differ
+
+
+@pytest.mark.parametrize("b,k", [(1, 1), (1, 17), (3, 17), (9, 16), (149, 1), (31, 5)])
+def test_decode_work_distribution_covers_every_map(api, b, k):
+    """CTAs own contiguous map ranges and their warps claim maps dynamically: every output slot is
+    written exactly once for map counts below, at and above the CTA / warp counts."""
+    hm = synth.heatmaps(b, joints=k, seed=21).to(DEV)
+    dec = api.metrics.GaussTaylorKeyPointDecoder(num_joints=k)
+    got = dec.decode_with_index(hm)
+    os.environ["SP_DECODE_FORCE_GENERIC"] = "1"
+    try:
+        want = dec.decode_with_index(hm)
+    finally:
+        del os.environ["SP_DECODE_FORCE_GENERIC"]
+    assert torch.equal(got[2], want[2]) and torch.equal(got[1], want[1])
+    assert (got[0] - want[0]).abs().max().item() <= 1e-5
+    assert torch.equal(got[2].long().cpu(), O.argmax_index(hm.cpu()))
