@@ -30,6 +30,9 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-6,
               "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
 
 
+OURS = re.compile(r"(encode_|mse_|decode_|oks_|rescore_|pack_|heatmap_acc|scale_inplace)\w*kernel")
+
+
 def short(name):
     m = re.search(r"(\w+_kernel)(<[^>]*>)?", name)
     return (m.group(1) + (m.group(2) or "")) if m else name[:60]
@@ -69,14 +72,19 @@ def main():
         lines = [ln for ln in fh if ln.startswith('"')]
     with open(os.path.join(HERE, tag + "_launches.csv"), "w") as fh:
         fh.writelines(lines)
+    skipped = 0
     for r in csv.reader(lines):
         if not r or not r[0].isdigit():
+            continue
+        if not OURS.search(r[4]):
+            skipped += 1            # torch kernels that build the synthetic inputs before the timed steps
             continue
         agg.setdefault(short(r[4]), []).append(float(r[-1]))
     total = sum(sum(v) for v in agg.values())
     md = ["# ncu summary %s" % tag, "",
           "Launch list (`%s_launches.csv`, `ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache and"
-          " serialised: compare shares, not absolutes):" % tag, "",
+          " serialised: compare shares, not absolutes; %d launches of torch/NCCL setup kernels that generate the synthetic"
+          " inputs before the steps are left out of the shares):" % (tag, skipped), "",
           "| kernel | launches | avg us | share of step |", "|---|---|---|---|"]
     for k, v in agg.items():
         md.append("| `%s` | %d | %.1f | %.3f |" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / total))
