@@ -408,6 +408,359 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     finish_loss<512>(sum_sq, ws, loss, inv_count);
 }
 
+// Variant C (default for W = 48 and W = 72 when grad is wanted and targets are not): the ring of
+// variant B with the per-quad and per-chunk bookkeeping compiled away. With QPR quads per row, the
+// (row, quad-in-row) pattern a lane sees repeats every PERIOD = QPR / gcd(32, QPR) warp steps and
+// advances by ROWS = 32 / gcd(32, QPR) rows, so the chunk body is fully unrolled over PPC periods
+// with per-lane constants: no index arithmetic, for PERIOD <= 3 the lane's x factors live in
+// registers (one shared-memory load per quad left: the row factor), ring depth and chunk size are
+// template parameters, shared memory is addressed with 32-bit offsets, the draw / unit-mask /
+// tracking decisions are made once per map (three specialisations of the map body), and the running
+// argmax keeps only (value, quad) -- the position inside the winning quad is recovered at the end
+// of the NEXT map from a 16-byte re-read that has had a whole map to complete.
+// Why it matters: with 16 warps per SM each warp issues about one instruction every 8 cycles, so
+// the kernel's time is (instructions per quad) x latency until the copy engine becomes the limit.
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+
+template <int QPR>
+struct Tile {
+    static constexpr int G = cgcd(32, QPR);
+    static constexpr int PERIOD = QPR / G;
+    static constexpr int ROWS = 32 / G;
+    static constexpr bool EX_IN_REGS = PERIOD <= 3;
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ double lds64f(uint32_t addr) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ double2 lds128d(uint32_t addr) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Per-warp ring of RING slots of CHUNK_BYTES, all shared-memory addresses 32-bit.
+template <int RING, int CHUNK_BYTES>
+struct TileRing {
+    uint32_t bar0, slot0;        // shared addresses of this warp's first barrier / slot
+    uint32_t cs, parity;         // consumer slot and phase
+    // producer side (lane 0): next chunk to request
+    const char* src;             // global address of the next chunk
+    int left;                    // chunks of the current map still to request (0: no map)
+    int pnext;                   // map claimed after the current one (-1: none)
+    uint32_t ps;
+    int tail, range_hi;
+    volatile int* fifo;
+    int* next_map;
+    const char* pred;
+    size_t map_bytes;
+    int chunks_per_map;
+
+    __device__ __forceinline__ int claim() {
+        const int m = atomicAdd(next_map, 1);
+        const int got = (m < range_hi) ? m : -1;
+        fifo[tail & (kFifo - 1)] = got;
+        ++tail;
+        return got;
+    }
+    __device__ __forceinline__ void start(int m) {           // lane 0
+        left = 0;
+        pnext = -1;
+        if (m >= 0) {
+            src = pred + (size_t)m * map_bytes;
+            left = chunks_per_map;
+            pnext = claim();
+        }
+    }
+    __device__ __forceinline__ void issue_next() {           // lane 0
+        if (left == 0) return;
+        const uint32_t bar = bar0 + ps * 8u, dst = slot0 + ps * (uint32_t)CHUNK_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(CHUNK_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "n"(CHUNK_BYTES), "r"(bar) : "memory");
+        src += CHUNK_BYTES;
+        if (--left == 0 && pnext >= 0) {
+            src = pred + (size_t)pnext * map_bytes;
+            left = chunks_per_map;
+            pnext = claim();
+        }
+        if (RING > 1) ps = (ps + 1 == RING) ? 0u : ps + 1;
+    }
+    __device__ __forceinline__ uint32_t wait() {             // returns the shared address of the chunk
+        const uint32_t bar = bar0 + cs * 8u;
+        while (!mbar_try_wait_a(bar, parity)) {
+        }
+        return slot0 + cs * (uint32_t)CHUNK_BYTES;
+    }
+    __device__ __forceinline__ void release(int lane) {
+        __syncwarp();
+        if (lane == 0) {
+            sp::fence_proxy_async_smem();
+            issue_next();                                    // refills the slot just drained
+        }
+        if (RING > 1) {
+            if (++cs == RING) { cs = 0; parity ^= 1u; }
+        } else {
+            parity ^= 1u;
+        }
+    }
+};
+
+// The predicted-map argmax of one map whose winning quad is still on its way back from L2.
+struct PendingAxis {
+    int m;              // < 0: nothing pending
+    int quad;
+    float gmax, mk;
+    float4 v;
+};
+
+__device__ __forceinline__ void flush_pending(const MapIo& io, PendingAxis& pd, int lane) {
+    if (pd.m < 0) return;
+    const float a = __fmul_rn(pd.mk, pd.v.x), b = __fmul_rn(pd.mk, pd.v.y), c = __fmul_rn(pd.mk, pd.v.z);
+    const int sub = (a == pd.gmax) ? 0 : (b == pd.gmax) ? 1 : (c == pd.gmax) ? 2 : 3;
+    if (lane == 0) io.pred_xy[pd.m] = axis_of(pd.gmax, 4 * pd.quad + sub, io.W);
+    pd.m = -1;
+}
+
+// MODE 0: Gaussian drawn, mask == 1, argmax tracked iff ACC (the common case);
+// MODE 1: nothing drawn and mask == 0 (invisible / culled joint): target 0, no tracking;
+// MODE 2: anything else (odd mask values, sigma outside the analytic range): run-time flags.
+template <int QPR, int PPC, int RING, bool ACC, int MODE>
+__device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVerdict& jv, const double* ex, const double* ey,
+                                          TileRing<RING, PPC * 32 * Tile<QPR>::PERIOD * 16>& rg, PendingAxis& pd, int lane) {
+    using T = Tile<QPR>;
+    constexpr int PERIOD = T::PERIOD, ROWS = T::ROWS;
+    constexpr int CHUNK_QUADS = PPC * 32 * PERIOD;
+    const int hw = io.H * io.W;
+    const bool draw = (MODE == 0) ? true : (MODE == 1) ? false : jv.draw;
+    const bool unit = (MODE == 0);
+    const bool track = ACC && ((MODE == 0) ? true : (MODE == 1) ? false : (jv.weight != 0.f));
+    const bool analytic_t = track && draw && io.analytic_ok && jv.weight >= 0.5f && jv.weight <= 4.f;
+    const bool track_t = (MODE == 2) && track && draw && !analytic_t;
+    const float mk = unit ? 1.0f : jv.weight, norm = io.norm, half_scale = io.half_scale;
+
+    // per-lane constants of one period: shared addresses of the row factor and of the x factors
+    const uint32_t ex_a = sp::smem_u32(ex), ey_a = sp::smem_u32(ey);
+    uint32_t eya[PERIOD], exa[PERIOD];
+#pragma unroll
+    for (int j = 0; j < PERIOD; ++j) {
+        const int q = lane + 32 * j;
+        const int y = q / QPR;
+        eya[j] = ey_a + 8u * (uint32_t)y;
+        exa[j] = ex_a + 32u * (uint32_t)(q - y * QPR);
+    }
+    double exr[T::EX_IN_REGS ? PERIOD : 1][4];
+    if (T::EX_IN_REGS && draw) {
+#pragma unroll
+        for (int j = 0; j < PERIOD; ++j) {
+            const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u);
+            exr[j][0] = a.x; exr[j][1] = a.y; exr[j][2] = b.x; exr[j][3] = b.y;
+        }
+    }
+
+    float acc = 0.f;
+    float best = -CUDART_INF_F, tbest = -CUDART_INF_F;
+    int bq = lane, tbq = lane;
+    int qlane = lane;                                   // this lane's quad at step 0 of the current chunk
+    float4* g4 = reinterpret_cast<float4*>(io.grad + (size_t)m * hw) + lane;
+    const int chunks = (hw >> 2) / CHUNK_QUADS;
+
+#pragma unroll 1
+    for (int c = 0; c < chunks; ++c) {
+        const uint32_t chunk = rg.wait() + 16u * (uint32_t)lane;
+#pragma unroll
+        for (int it = 0; it < PPC; ++it) {
+#pragma unroll
+            for (int j = 0; j < PERIOD; ++j) {
+                constexpr int kDummy = 0;
+                (void)kDummy;
+                const int step = it * PERIOD + j;
+                const float4 p = lds128(chunk + 512u * step);
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (draw) {
+                    const double fy = lds64f(eya[j] + 8u * (uint32_t)(it * ROWS));
+                    double e0, e1, e2, e3;
+                    if (T::EX_IN_REGS) {
+                        e0 = exr[j][0]; e1 = exr[j][1]; e2 = exr[j][2]; e3 = exr[j][3];
+                    } else {
+                        const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u);
+                        e0 = a.x; e1 = a.y; e2 = b.x; e3 = b.y;
+                    }
+                    t.x = __double2float_rn(__dmul_rn(e0, fy));
+                    t.y = __double2float_rn(__dmul_rn(e1, fy));
+                    t.z = __double2float_rn(__dmul_rn(e2, fy));
+                    t.w = __double2float_rn(__dmul_rn(e3, fy));
+                }
+                const float px = unit ? p.x : __fmul_rn(mk, p.x), py = unit ? p.y : __fmul_rn(mk, p.y);
+                const float pz = unit ? p.z : __fmul_rn(mk, p.z), pw = unit ? p.w : __fmul_rn(mk, p.w);
+                const float tx = unit ? t.x : __fmul_rn(mk, t.x), ty = unit ? t.y : __fmul_rn(mk, t.y);
+                const float tz = unit ? t.z : __fmul_rn(mk, t.z), tw = unit ? t.w : __fmul_rn(mk, t.w);
+                const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty), dz = __fsub_rn(pz, tz), dw = __fsub_rn(pw, tw);
+                acc = fmaf(dx, dx, acc);
+                acc = fmaf(dy, dy, acc);
+                acc = fmaf(dz, dz, acc);
+                acc = fmaf(dw, dw, acc);
+                float4 g;
+                g.x = __fmul_rn(__fmul_rn(norm, dx), half_scale);
+                g.y = __fmul_rn(__fmul_rn(norm, dy), half_scale);
+                g.z = __fmul_rn(__fmul_rn(norm, dz), half_scale);
+                g.w = __fmul_rn(__fmul_rn(norm, dw), half_scale);
+                if (!unit) {
+                    g.x = __fmul_rn(g.x, mk); g.y = __fmul_rn(g.y, mk); g.z = __fmul_rn(g.z, mk); g.w = __fmul_rn(g.w, mk);
+                }
+                g4[32 * step] = g;
+                if (track) {
+                    const float m4 = sp::fmax_nan(sp::fmax_nan(px, py), sp::fmax_nan(pz, pw));
+                    if (m4 > best) bq = qlane + 32 * step;
+                    best = sp::fmax_nan(best, m4);          // NaN sticks: resolved by the exact scan below
+                }
+                if (track_t) {
+                    const float m4 = fmaxf(fmaxf(tx, ty), fmaxf(tz, tw));
+                    if (m4 > tbest) { tbest = m4; tbq = qlane + 32 * step; }
+                }
+            }
+        }
+        g4 += CHUNK_QUADS;
+        qlane += CHUNK_QUADS;
+#pragma unroll
+        for (int j = 0; j < PERIOD; ++j) eya[j] += 8u * (uint32_t)(PPC * ROWS);
+        rg.release(lane);
+    }
+
+    if (ACC) {
+        flush_pending(io, pd, lane);                 // the previous map's quad arrived long ago
+        float2 lxy = make_float2(0.f, 0.f);
+        if (track) {
+            const float* src = io.pred + (size_t)m * hw;
+            if (__any_sync(SP_FULL, best != best)) {
+                float pv;
+                int pi;
+                MaskedPredView view{src, mk};
+                argmax_exact_scan(view, hw, lane, pv, pi);
+                if (lane == 0) io.pred_xy[m] = axis_of(pv, pi, io.W);
+            } else {
+                // every lane kept the first quad holding its own maximum: the smallest quad among
+                // the lanes that hold the warp-wide maximum contains torch.max's answer
+                const float gmax = warp_max_f32(best);
+                const int gq = (int)__reduce_min_sync(SP_FULL, (best == gmax) ? (unsigned)bq : 0x7fffffffu);
+                pd.m = m;
+                pd.quad = gq;
+                pd.gmax = gmax;
+                pd.mk = mk;
+                pd.v = __ldg(reinterpret_cast<const float4*>(src) + gq);
+            }
+            if (analytic_t) {
+                const int W = io.W;
+                const int xn = min(max(__float2int_rn(jv.mx), 0), W - 1), yn = min(max(__float2int_rn(jv.my), 0), io.H - 1);
+                const int yy = yn - 1 + lane / 3, xx = xn - 1 + lane % 3;
+                const bool in = lane < 9 && yy >= 0 && yy < io.H && xx >= 0 && xx < W;
+                float v = -CUDART_INF_F;
+                if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[xx], ey[yy])));
+                const float gmax = warp_max_f32(v);
+                const unsigned gi = __reduce_min_sync(SP_FULL, (in && v == gmax) ? (unsigned)(yy * W + xx) : 0x7fffffffu);
+                lxy = axis_of(gmax, (int)gi, W);
+            } else if (track_t) {
+                const float gmax = warp_max_f32(tbest);
+                const int gq = (int)__reduce_min_sync(SP_FULL, (tbest == gmax) ? (unsigned)tbq : 0x7fffffffu);
+                const int y = gq / QPR, x4 = 4 * (gq - y * QPR);
+                int sub = 3;
+#pragma unroll
+                for (int e = 2; e >= 0; --e)
+                    if (__fmul_rn(mk, __double2float_rn(__dmul_rn(ex[x4 + e], ey[y]))) == gmax) sub = e;
+                lxy = axis_of(gmax, 4 * gq + sub, io.W);
+            }
+        } else if (lane == 0) {
+            io.pred_xy[m] = make_float2(0.f, 0.f);
+        }
+        if (lane == 0) io.label_xy[m] = lxy;
+    }
+    return acc;
+}
+
+// dynamic smem: same layout as variant B
+template <int QPR, int PPC, int RING, bool ACC>
+__global__ void __launch_bounds__(512, 1)
+encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count, int nwarps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int CHUNK_BYTES = PPC * 32 * Tile<QPR>::PERIOD * 16;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = io.H * io.W;
+    const int wpad = (io.W + 1) & ~1;
+    const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
+    volatile int* fifo = reinterpret_cast<int*>(smem_raw + 1024) + warp * kFifo;
+    int* next_map = reinterpret_cast<int*>(smem_raw + 1024 + 2048);
+    double* ex = reinterpret_cast<double*>(smem_raw + kRingHeader + warp * fac_bytes);
+    double* ey = ex + wpad;
+    TileRing<RING, CHUNK_BYTES> rg;
+    const uint32_t base = sp::smem_u32(smem_raw);
+    rg.bar0 = base + (uint32_t)(warp * RING * 8);
+    rg.slot0 = base + (uint32_t)(kRingHeader + (size_t)nwarps * fac_bytes + (size_t)warp * RING * CHUNK_BYTES);
+    rg.cs = 0; rg.parity = 0; rg.ps = 0; rg.tail = 0; rg.left = 0; rg.pnext = -1; rg.src = nullptr;
+    rg.fifo = fifo; rg.next_map = next_map;
+    rg.pred = reinterpret_cast<const char*>(io.pred);
+    rg.map_bytes = (size_t)hw * 4;
+    rg.chunks_per_map = hw * 4 / CHUNK_BYTES;
+    const int range_lo = (int)((long long)blockIdx.x * io.nmaps / gridDim.x);
+    rg.range_hi = (int)((long long)(blockIdx.x + 1) * io.nmaps / gridDim.x);
+    if (threadIdx.x == 0) *next_map = range_lo;
+    if (lane == 0) {
+        for (int r = 0; r < RING; ++r) sp::mbar_init(reinterpret_cast<uint64_t*>(smem_raw) + warp * RING + r, 1);
+        sp::mbar_fence_init();
+    }
+    __syncthreads();
+    sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
+    sp::grid_dep_launch();
+
+    if (lane == 0) {
+        rg.start(rg.claim());
+        for (int r = 0; r < RING; ++r) rg.issue_next();
+    }
+    __syncwarp();
+
+    double sum_sq = 0.0;
+    PendingAxis pd;
+    pd.m = -1; pd.quad = 0; pd.gmax = 0.f; pd.mk = 0.f; pd.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int head = 0;
+    int m = fifo[0];
+    Joint3 jn = load_joint(io, m >= 0 ? m : io.nmaps);
+    while (m >= 0) {
+        const Joint3 jc = jn;
+        const int m_next = fifo[(head + 1) & (kFifo - 1)];   // claimed before this map's first chunk was issued
+        jn = load_joint(io, m_next >= 0 ? m_next : io.nmaps);
+        const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);
+        float acc;
+        if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
+            acc = tile_map<QPR, PPC, RING, ACC, 0>(io, m, jv, ex, ey, rg, pd, lane);
+        else if (!jv.draw && jv.weight == 0.0f)
+            acc = tile_map<QPR, PPC, RING, ACC, 1>(io, m, jv, ex, ey, rg, pd, lane);
+        else
+            acc = tile_map<QPR, PPC, RING, ACC, 2>(io, m, jv, ex, ey, rg, pd, lane);
+        sum_sq += (double)acc;
+        __syncwarp();
+        ++head;
+        m = m_next;
+    }
+    if (ACC) flush_pending(io, pd, lane);
+    finish_loss<512>(sum_sq, ws, loss, inv_count);
+}
+
 // HeatMapAcc epilogue (metrics/pose_metrics.py:227-245) on the [B,K] argmax coordinates.
 __global__ void __launch_bounds__(256)
 heatmap_acc_kernel(const float2* __restrict__ pred_xy, const float2* __restrict__ label_xy, float* __restrict__ acc,
@@ -490,6 +843,52 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         if (want < 32) want = 32;
         for (int d = want - want % 32; d >= 32; d -= 32)
             if (nq % d == 0) { chunk_quads = d; break; }
+    }
+    // Variant C: W = 48 / 72 (12 / 18 quads per row), whole periods per map, grad wanted, targets not
+    const int qpr = W >> 2;
+    if ((qpr == 12 || qpr == 18) && grad && !targets && !(force && force[0] == '1') && !sp_env_int("SP_TRAIN_NO_TILE", 0)) {
+        const int period = (qpr == 12) ? Tile<12>::PERIOD : Tile<18>::PERIOD;
+        const int rows = (qpr == 12) ? Tile<12>::ROWS : Tile<18>::ROWS;
+        // tuned layouts (PPC periods per chunk, ring depth); SP_TRAIN_TILE_CFG picks another compiled one
+        const int cfg = sp_env_int("SP_TRAIN_TILE_CFG", 0);
+        int ppc = 1, ring = 2;
+        if (qpr == 12) {
+            if (cfg == 1) { ppc = 1; ring = 2; } else if (cfg == 2) { ppc = 2; ring = 2; } else if (cfg == 3) { ppc = 4; ring = 1; } else { ppc = 2; ring = 1; }
+        } else {
+            if (cfg == 1) { ppc = 1; ring = 1; } else { ppc = 1; ring = 2; }
+        }
+        const int periods = nq / (32 * period);
+        if (H % rows == 0 && periods % ppc == 0) {
+            const size_t chunk_bytes = (size_t)ppc * 32 * period * 16;
+            const size_t budget = 226 * 1024 - kRingHeader;
+            int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
+            if (nwarps > 16) nwarps = 16;
+            { const int w = sp_env_int("SP_TRAIN_WARPS", 16); if (w < nwarps) nwarps = w; }
+            if (nwarps >= 1) {
+                const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
+                int grid = sp_sm_count();
+                const int need = (nmaps + nwarps - 1) / nwarps;
+                if (grid > need) grid = need;
+#define SP_LAUNCH_TILE(Q, P, R)                                                                                              \
+    do {                                                                                                                     \
+        if (pred_xy) {                                                                                                       \
+            SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps)); \
+        } else {                                                                                                             \
+            SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps)); \
+        }                                                                                                                    \
+    } while (0)
+                if (qpr == 12) {
+                    if (ppc == 1) SP_LAUNCH_TILE(12, 1, 2); else if (ppc == 2 && ring == 2) SP_LAUNCH_TILE(12, 2, 2);
+                    else if (ppc == 4) SP_LAUNCH_TILE(12, 4, 1); else SP_LAUNCH_TILE(12, 2, 1);
+                } else {
+                    if (ring == 1) SP_LAUNCH_TILE(18, 1, 1); else SP_LAUNCH_TILE(18, 1, 2);
+                }
+#undef SP_LAUNCH_TILE
+                return sp_launch_status();
+            }
+        }
     }
     if (chunk_quads > 0 && !(force && force[0] == '1')) {
         const size_t chunk_bytes = (size_t)chunk_quads * 16;

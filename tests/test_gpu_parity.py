@@ -582,21 +582,52 @@ def test_cfg5_coco_val_sized_job_properties(api):
 
 @pytest.mark.parametrize("env", [{"SP_TRAIN_FORCE_LDG": "1"}, {"SP_TRAIN_WARPS": "3", "SP_TRAIN_RING": "2"},
                                  {"SP_TRAIN_RING": "1"}, {"SP_TRAIN_RING": "4", "SP_TRAIN_CHUNK_QUADS": "64"},
-                                 {"SP_TRAIN_CHUNK_QUADS": "768", "SP_TRAIN_RING": "1"}, {"SP_TRAIN_WARPS": "1", "SP_TRAIN_RING": "8"}])
-def test_fused_kernel_variants_agree(api, env):
-    """Every chunk/ring/warp layout of the TMA ring and the plain-load variant give identical outputs."""
-    joints = synth.joints(40, seed=81).to(DEV)
-    pred = synth.heatmaps(40, seed=82).to(DEV)
+                                 {"SP_TRAIN_CHUNK_QUADS": "768", "SP_TRAIN_RING": "1"}, {"SP_TRAIN_WARPS": "1", "SP_TRAIN_RING": "8"},
+                                 {"SP_TRAIN_NO_TILE": "1"}, {"SP_TRAIN_NO_TILE": "1", "SP_TRAIN_RING": "3", "SP_TRAIN_WARPS": "5"},
+                                 {"SP_TRAIN_TILE_CFG": "1"}, {"SP_TRAIN_TILE_CFG": "2", "SP_TRAIN_WARPS": "3"},
+                                 {"SP_TRAIN_TILE_CFG": "3", "SP_TRAIN_WARPS": "7"}, {"SP_TRAIN_WARPS": "1"}, {"SP_NO_PDL": "1"}])
+@pytest.mark.parametrize("hw", [(64, 48), (96, 72)])
+def test_fused_kernel_variants_agree(api, env, hw):
+    """Every chunk/ring/warp layout of the period-tiled kernel, the generic TMA ring and the
+    plain-load variant give identical outputs (weights 0, 1 and odd values all present)."""
+    h, w = hw
+    joints = synth.joints(40, height=h, width=w, seed=81)
+    joints[3, :, 2] = 2.0
+    joints[5, :, 2] = 0.75
+    joints[7, :, 2] = 0.25
+    joints = joints.to(DEV)
+    pred = synth.heatmaps(40, height=h, width=w, seed=82).to(DEV)
+    pred[1, 2, 5, 7] = float("nan")
+    pred[2, 3] = -1.0
+    pred[2, 4] = float("-inf")
+    pred[4, 0, h - 1, w - 1] = float("inf")
     base = api.loss.encode_mse_forward_backward(joints, pred, want_targets=True, want_axes=True)
+    slim = api.loss.encode_mse_forward_backward(joints, pred, want_axes=True)
+    bare = api.loss.encode_mse_forward_backward(joints, pred)
     os.environ.update(env)
     try:
         other = api.loss.encode_mse_forward_backward(joints, pred, want_targets=True, want_axes=True)
+        other_slim = api.loss.encode_mse_forward_backward(joints, pred, want_axes=True)
+        other_bare = api.loss.encode_mse_forward_backward(joints, pred)
     finally:
         for k in env:
             del os.environ[k]
     for key in ("grad", "targets", "weights", "pred_xy", "label_xy"):
-        assert torch.equal(base[key], other[key]), key
-    assert abs(base["loss"].item() - other["loss"].item()) <= 1e-6 * abs(base["loss"].item())
+        assert torch.equal(base[key].nan_to_num(nan=7.0), other[key].nan_to_num(nan=7.0)), key
+        for alt in (slim, other_slim):      # period-tiled kernel (no targets requested)
+            if alt[key] is not None:
+                assert torch.equal(base[key].nan_to_num(nan=7.0), alt[key].nan_to_num(nan=7.0)), key
+    for alt in (bare, other_bare):
+        assert torch.equal(base["grad"].nan_to_num(nan=7.0), alt["grad"].nan_to_num(nan=7.0))
+        assert torch.equal(base["weights"], alt["weights"])
+    # the odd-weight / special-value maps against torch on the device
+    m = base["weights"][..., None, None]
+    tv, ti = (pred * m).flatten(2).max(dim=-1)
+    want_xy = torch.stack([(ti % w).float(), (ti // w).float()], -1) * (tv > 0)[..., None]
+    assert torch.equal(base["pred_xy"], want_xy)
+    lv, li = (base["targets"] * m).flatten(2).max(dim=-1)
+    want_l = torch.stack([(li % w).float(), (li // w).float()], -1) * (lv > 0)[..., None]
+    assert torch.equal(base["label_xy"], want_l)
 
 
 def test_fused_label_argmax_ties_and_outside_centres(api):
