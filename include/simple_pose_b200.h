@@ -174,6 +174,23 @@ int sp_rescore_f64(const double* kps, const double* box_scores, double* scores,
 int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps,
                     int N, int K, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Eval-side caller of the decoder ("next": the data either side of the path):
+ * BasicTransform.__call__ without the image warp, datasets/naive_data.py:44-56 =
+ * box_to_center_scale (commons/joint_utils.py:39-56) + get_affine_transform(center, scale, 0,
+ * output_shape) (commons/joint_utils.py:115-152, cv.getAffineTransform = 6x6 LU in float64).
+ *
+ * boxes_xyxy    [P,4] f64  detection boxes (x1, y1, x2, y2), the JSON floats of :84-95
+ * center, scale [P,2] f32 out (nullable); area [P] f32 out = scale_w * scale_h (nullable)
+ * trans_inv     [P,2,3] f32 out = what collate_fn ships (.float(), :114-116) (nullable)
+ * trans_inv_f64 [P,2,3] f64 out = the unrounded cv result (nullable; at least one of the two)
+ * w_h_ratio = input_w / input_h; (out_w, out_h) = heatmap size; scale_mult = 1.25.
+ * Bit-identical to the reference (same roundings, same LU pivoting and operation order).
+ */
+int sp_box_affine_f64(const double* boxes_xyxy, float* center, float* scale, float* area,
+                      float* trans_inv, double* trans_inv_f64, int P, double w_h_ratio,
+                      int out_w, int out_h, float scale_mult, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

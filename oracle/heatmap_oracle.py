@@ -361,3 +361,112 @@ def kps_score(max_val):
     """Person score of ``kps_to_dict_`` (metrics/pose_metrics.py:176): mean + max of the
     joint peak values. max_val [B,K,1] -> [B]."""
     return max_val.mean(dim=(1, 2)) + max_val.amax(dim=(1, 2))
+
+
+# --------------------------------------------------------------------------- box -> affine (eval-side caller)
+def box_center_scale(x, y, w, h, aspect_ratio=1.0, scale_mult=1.25):
+    """``box_to_center_scale`` (commons/joint_utils.py:39-56). x, y, w, h are Python floats
+    (float64 arithmetic); centre and scale are float32 arrays; ``scale * scale_mult`` is a
+    float32 multiplication (NumPy 2 keeps float32 for array * Python scalar)."""
+    center = np.zeros(2, dtype=np.float32)
+    center[0] = x + w * 0.5
+    center[1] = y + h * 0.5
+    if w > aspect_ratio * h:
+        h = w / aspect_ratio
+    elif w < aspect_ratio * h:
+        w = h * aspect_ratio
+    scale = np.array([w, h], dtype=np.float32)
+    if center[0] != -1:
+        scale = scale * np.float32(scale_mult)
+    return center, scale
+
+
+def affine_triangles(center, scale, output_size):
+    """The two point triples of ``get_affine_transform(center, scale, 0, output_size)``
+    (commons/joint_utils.py:115-150) for rot = 0, shift = 0, as float32 [3,2] arrays. The second
+    points are float64 sums rounded to float32 (float32 array + Python list), the third points
+    float32 arithmetic (``get_3rd_point`` :72-75)."""
+    center = np.asarray(center, dtype=np.float32)
+    src_w = np.float32(scale[0])
+    dst_w, dst_h = output_size[0], output_size[1]
+    half = np.float64(src_w * np.float32(-0.5))                  # get_dir([0, src_w*-0.5], 0)[1]: float32 -> float64
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0] = center
+    src[1, 0] = np.float64(center[0]) + 0.0
+    src[1, 1] = np.float64(center[1]) + half
+    dst[0] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, 0] = dst_w * 0.5 + 0.0
+    dst[1, 1] = dst_h * 0.5 + np.float64(np.float32(dst_w * -0.5))
+    for tri in (src, dst):
+        direct = tri[0] - tri[1]
+        tri[2] = tri[1] + np.array([-direct[1], direct[0]], dtype=np.float32)
+    return src, dst
+
+
+def solve_affine_lu(p_from, p_to):
+    """``cv.getAffineTransform(p_from, p_to)`` restated: OpenCV (pinned by the reference only as
+    ``opencv-python``, README.md:12; 4.13.0 here) fills the 6x6 system
+    [x y 1 0 0 0; 0 0 0 x y 1] m = (x', y') per point in float64 and solves it with its in-place
+    partial-pivot LU (first row of maximal |pivot|, ``d = -1/pivot``, ``row_j += (a_ji * d) * row_i``,
+    back substitution ``(b_i - sum a_ik x_k) / a_ii``), no fused multiply-add. Bit-identical to
+    cv2 on every probe (tests/test_oracle_vs_reference.py). Returns float64 [2,3]."""
+    a = np.zeros((6, 6), dtype=np.float64)
+    b = np.zeros(6, dtype=np.float64)
+    for i in range(3):
+        px, py = float(p_from[i][0]), float(p_from[i][1])
+        a[2 * i, 0:3] = (px, py, 1.0)
+        a[2 * i + 1, 3:6] = (px, py, 1.0)
+        b[2 * i] = float(p_to[i][0])
+        b[2 * i + 1] = float(p_to[i][1])
+    n = 6
+    for i in range(n):
+        k = i
+        for j in range(i + 1, n):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if abs(a[k, i]) < np.finfo(np.float64).eps * 100:
+            return np.zeros((2, 3), dtype=np.float64)            # singular: OpenCV leaves the result zero
+        if k != i:
+            a[[i, k]] = a[[k, i]]
+            b[[i, k]] = b[[k, i]]
+        d = -1.0 / a[i, i]
+        for j in range(i + 1, n):
+            alpha = a[j, i] * d
+            for c in range(i + 1, n):
+                a[j, c] = a[j, c] + alpha * a[i, c]
+            b[j] = b[j] + alpha * b[i]
+    x = np.zeros(n, dtype=np.float64)
+    for i in range(n - 1, -1, -1):
+        s = b[i]
+        for k in range(i + 1, n):
+            s = s - a[i, k] * x[k]
+        x[i] = s / a[i, i]
+    return x.reshape(2, 3)
+
+
+def affine_pair(center, scale, output_size):
+    """(trans, trans_inv) of ``get_affine_transform(center, scale, 0, output_size)``, float64 [2,3]."""
+    src, dst = affine_triangles(center, scale, output_size)
+    return solve_affine_lu(src, dst), solve_affine_lu(dst, src)
+
+
+def box_affines(boxes_xyxy, input_shape=(192, 256), output_shape=(48, 64), scale_mult=1.25):
+    """``BasicTransform.__call__`` without the image warp (datasets/naive_data.py:44-56) for a list
+    of detection boxes [x1, y1, x2, y2] (Python floats): centre, scale, area = scale_w * scale_h
+    (float32 product) and the heatmap -> image affine ``trans_inv`` as the collate function ships
+    it (``.float()``, :114-116). Returns float32 arrays center [P,2], scale [P,2], area [P],
+    trans_inv [P,2,3]."""
+    ratio = input_shape[0] / input_shape[1]
+    n = len(boxes_xyxy)
+    center = np.zeros((n, 2), np.float32)
+    scale = np.zeros((n, 2), np.float32)
+    area = np.zeros(n, np.float32)
+    tinv = np.zeros((n, 2, 3), np.float32)
+    for i, (x1, y1, x2, y2) in enumerate(boxes_xyxy):
+        x1, y1, x2, y2 = float(x1), float(y1), float(x2), float(y2)
+        c, s = box_center_scale(x1, y1, x2 - x1, y2 - y1, ratio, scale_mult)
+        _, ti = affine_pair(c, s, output_shape)
+        center[i], scale[i], area[i] = c, s, s[0] * s[1]
+        tinv[i] = ti.astype(np.float32)
+    return center, scale, area, tinv

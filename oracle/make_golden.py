@@ -88,11 +88,35 @@ def edge_maps(h=64, w=48):
     return hm
 
 
+def affine_fixtures(ref):
+    """Box -> (centre, scale, area, trans_inv) from the reference's own box_to_center_scale +
+    get_affine_transform (the body of BasicTransform.__call__, datasets/naive_data.py:44-56)."""
+    out = {}
+    for tag, inp, outp in (("a", (192, 256), (48, 64)), ("b", (288, 384), (72, 96))):
+        boxes = synth.detection_boxes(96, seed=61, ratio_exact_every=8, ratio=inp[0] / inp[1]).numpy()
+        boxes[1] = [10.0, 20.0, 10.0 + 1e-3, 20.0 + 2e-3]           # tiny box
+        boxes[2] = [-1.5, 7.0, -0.5, 9.0]                           # centre x == -1: scale_mult skipped
+        boxes[3] = [100.0, 50.0, 100.0, 50.0]                       # degenerate: singular system
+        c, s, a, t64 = [], [], [], []
+        for x1, y1, x2, y2 in boxes.tolist():
+            ci, si = ref.box_to_center_scale(x1, y1, x2 - x1, y2 - y1, inp[0] / inp[1])
+            _, ti = ref.get_affine_transform(ci, si, 0, outp)
+            c.append(ci); s.append(si); a.append(si[0] * si[1]); t64.append(ti)
+        out.update({"boxes_" + tag: boxes, "center_" + tag: np.stack(c), "scale_" + tag: np.stack(s),
+                    "area_" + tag: np.array(a, dtype=np.float32), "tinv64_" + tag: np.stack(t64),
+                    "tinv_" + tag: torch.from_numpy(np.stack(t64)).float().numpy(),
+                    "shapes_" + tag: np.array([inp, outp], dtype=np.int32)})
+    np.savez_compressed(os.path.join(GOLDEN, "affine.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_loader.load()
     torch.manual_seed(0)
+    affine_fixtures(ref)
+    if "--only-affine" in sys.argv:
+        return
 
     # ---------------------------------------------------------------- encode
     ja = synth.joints(3, height=64, width=48, seed=3).numpy()

@@ -43,6 +43,7 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_void]),
     "sp_rescore_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_dbl, c_void]),
     "sp_pack_kps_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void]),
+    "sp_box_affine_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_dbl, c_int, c_int, c_flt, c_void]),
 }
 
 _lock = threading.Lock()

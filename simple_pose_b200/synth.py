@@ -173,3 +173,20 @@ def nms_groups(images, mean_group=20.0, seed=0, num_joints=17, dup_frac=0.5, jit
     perm = torch.randperm(n, generator=g).double()
     box_scores = (perm + 0.5) / n
     return kps, box_scores, areas, seg.to(torch.int32)
+
+
+def detection_boxes(persons, seed=0, ratio_exact_every=0, ratio=0.75):
+    """COCO-like detection boxes [P,4] float64 (x1, y1, x2, y2): w ~ U(8,400), h ~ U(8,560), top-left
+    corner in [-40,640) x [-40,480) (detectors do emit slightly negative corners). With
+    ``ratio_exact_every`` > 0 every n-th box has w == ratio * h exactly (neither branch of the
+    aspect fix of ``box_to_center_scale``)."""
+    g = _gen(seed + 982451653, "cpu")
+    u = torch.rand(persons, 4, generator=g, dtype=torch.float64)
+    w = 8.0 + 392.0 * u[:, 0]
+    h = 8.0 + 552.0 * u[:, 1]
+    x = -40.0 + 680.0 * u[:, 2]
+    y = -40.0 + 520.0 * u[:, 3]
+    if ratio_exact_every:
+        h[::ratio_exact_every] = torch.floor(h[::ratio_exact_every] / 4.0) * 4.0
+        w[::ratio_exact_every] = h[::ratio_exact_every] * ratio
+    return torch.stack([x, y, x + w, y + h], dim=1)

@@ -521,6 +521,49 @@ def test_fused_acc_special_predictions(api):
     assert torch.equal(out["pred_xy"].cpu(), want_p) and torch.equal(out["label_xy"].cpu(), want_l)
 
 
+# ------------------------------------------------------------------------------------ box -> affine (eval-side caller)
+def test_box_affines_golden_and_oracle(api, golden):
+    """sp_box_affine_f64 == the reference's box_to_center_scale + get_affine_transform, bit for bit
+    (float64 matrix included), on the frozen fixtures and on seeded boxes against the oracle."""
+    g = golden("affine")
+    for tag in ("a", "b"):
+        inp, outp = [tuple(int(v) for v in r) for r in g["shapes_" + tag]]
+        out = api.naive.box_affines(g["boxes_" + tag], inp, outp, want_f64=True)
+        for key, name in (("center", "center_"), ("scale", "scale_"), ("area", "area_"), ("trans_inv", "tinv_"),
+                          ("trans_inv_f64", "tinv64_")):
+            assert np.array_equal(bits(out[key].cpu().numpy()), bits(g[name + tag])), (tag, key)
+    for inp, outp in (((192, 256), (48, 64)), ((288, 384), (72, 96)), ((256, 256), (64, 64))):
+        boxes = synth.detection_boxes(3000, seed=88, ratio_exact_every=32, ratio=inp[0] / inp[1])
+        c, s, a, tinv = O.box_affines(boxes.tolist(), inp, outp)
+        out = api.naive.box_affines(boxes.to(DEV), inp, outp)
+        assert np.array_equal(bits(out["center"].cpu().numpy()), bits(c))
+        assert np.array_equal(bits(out["scale"].cpu().numpy()), bits(s))
+        assert np.array_equal(bits(out["area"].cpu().numpy()), bits(a))
+        assert np.array_equal(bits(out["trans_inv"].cpu().numpy()), bits(tinv))
+    assert api.naive.box_affines(np.zeros((0, 4)))["trans_inv"].shape == (0, 2, 3)
+
+
+def test_boxes_to_keypoints_device_resident(api):
+    """Eval chain without host round trips: boxes -> trans_inv/area (device) -> decode -> pack ->
+    rescore + NMS, against the oracle fed with the reference-style per-box transforms."""
+    n = 200
+    boxes = synth.detection_boxes(n, seed=99)
+    hm = synth.heatmaps(n, seed=99)
+    c, s, a, tinv = O.box_affines(boxes.tolist())
+    want_xy, want_conf = O.gauss_taylor_decode(hm, torch.from_numpy(tinv))
+    aff = api.naive.box_affines(boxes.to(DEV))
+    xy, conf = api.metrics.GaussTaylorKeyPointDecoder()(hm.to(DEV), aff["trans_inv"])
+    mag = float(np.abs(tinv[:, 0, 0]).max())
+    assert (xy.cpu() - want_xy).abs().max().item() <= 1e-4 * mag + 1e-3 and torch.equal(conf.cpu(), want_conf)
+    seg = np.arange(0, n + 1, 10, dtype=np.int32)
+    box_scores = torch.linspace(0.95, 0.05, n, dtype=torch.float64)
+    kps = api.naive.pack_keypoints(xy, conf)
+    keep, scores, _ = api.naive.rescore_and_nms(kps, box_scores, aff["area"].double(), seg)
+    o_keep, o_scores, _ = O.rescore_and_nms(kps.cpu().numpy(), box_scores.numpy(), a.astype(np.float64), seg)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), o_keep)
+    assert np.allclose(scores.cpu().numpy(), o_scores, rtol=1e-15, atol=0)
+
+
 # ------------------------------------------------------------------------------------ BASELINE full sizes
 def test_cfg4_full_size_decode_and_nms_vs_oracle(api):
     """BASELINE config 4: HRNet-W48 384x288 (96x72 maps) decode + OKS-NMS, batch 512 -- the

@@ -75,3 +75,23 @@ def test_heat_map_acc(ref):
     tgt = torch.from_numpy(O.encode_batch(synth.joints(8, seed=17).numpy())[0])
     pred = synth.predictions_like(tgt, seed=18, noise=0.3)
     assert float(ref.HeatMapAcc()(pred, tgt)) == float(O.heat_map_acc(pred, tgt))
+
+
+@pytest.mark.parametrize("inp,outp", [((192, 256), (48, 64)), ((288, 384), (72, 96)), ((256, 256), (64, 64))])
+def test_box_affines(ref, inp, outp):
+    """box_to_center_scale + get_affine_transform(rot=0) (the body of BasicTransform.__call__): the
+    oracle's restatement of OpenCV's 6x6 LU is bit-identical to cv2, both directions."""
+    boxes = synth.detection_boxes(400, seed=77, ratio_exact_every=16, ratio=inp[0] / inp[1]).tolist()
+    boxes += [[10.0, 20.0, 10.001, 20.002], [-1.5, 7.0, -0.5, 9.0], [100.0, 50.0, 100.0, 50.0], [0.0, 0.0, 1e6, 3.0]]
+    c, s, a, tinv = O.box_affines(boxes, inp, outp)
+    for i, (x1, y1, x2, y2) in enumerate(boxes):
+        rc, rs = ref.box_to_center_scale(x1, y1, x2 - x1, y2 - y1, inp[0] / inp[1])
+        rt, rti = ref.get_affine_transform(rc, rs, 0, outp)
+        oc, os_ = O.box_center_scale(x1, y1, x2 - x1, y2 - y1, inp[0] / inp[1])
+        ot, oti = O.affine_pair(oc, os_, outp)
+        assert oc.dtype == rc.dtype and os_.dtype == rs.dtype
+        assert np.array_equal(bits(rc), bits(oc)) and np.array_equal(bits(rs), bits(os_)), i
+        assert np.array_equal(bits(rt), bits(ot)) and np.array_equal(bits(rti), bits(oti)), i
+        assert np.array_equal(bits(c[i]), bits(rc)) and np.array_equal(bits(s[i]), bits(rs))
+        assert np.float32(rs[0] * rs[1]) == a[i]
+        assert np.array_equal(bits(tinv[i]), bits(torch.from_numpy(rti).float().numpy()))
