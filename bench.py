@@ -68,7 +68,7 @@ def ncu_traffic(kernel, height, width, batch):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
     (profiles/r*_traffic.json), if one exists for this exact launch shape; else None."""
     names = {"encode": "encode_refine_kernel<1>", "loss": "mse_ring_kernel<1>", "decode": "decode_tma_kernel<0, 11>",
-             "train_fused": "encode_mse_ring_kernel<1, 0, 1>", "flip_decode": "decode_tma_kernel<1, 11>"}
+             "train_fused": "encode_mse_tile_kernel<12, 2, 1, 1>", "flip_decode": "decode_tma_kernel<1, 11>"}
     key = "%s @ %dx%d,P=%d" % (names.get(kernel, kernel), height, width, batch)
     pdir = os.path.join(ROOT, "profiles")
     try:

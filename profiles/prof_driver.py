@@ -15,7 +15,7 @@ from simple_pose_b200.datasets.naive_data import rescore_and_nms  # noqa: E402
 
 dev = torch.device("cuda:0")
 reps = int(os.environ.get("PROF_REPS", "2"))
-for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):
+for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):  # summarize.py labels launches by this order
     hp = HeatmapHotPath(batch, 17, h, w, device=dev)
     joints = synth.joints(batch, height=h, width=w, seed=1, device=dev)
     pred = synth.heatmaps(batch, height=h, width=w, seed=1, device=dev)

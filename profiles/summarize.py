@@ -102,6 +102,8 @@ def main():
         i = order[k["kernel"]]
         order[k["kernel"]] += 1
         shape = "64x48,P=1024" if i < reps else "96x72,P=512"
+        if k["kernel"].startswith("encode_mse_tile_kernel<"):       # the template argument names the map width
+            shape = "64x48,P=1024" if k["kernel"].startswith("encode_mse_tile_kernel<12") else "96x72,P=512"
         if k["kernel"].split("<")[0] in ("rescore_kernel", "oks_nms_kernel"):
             shape = "512 images, ~10.7k persons"
         k["config"] = shape

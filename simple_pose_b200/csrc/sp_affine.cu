@@ -70,7 +70,6 @@ box_affine_kernel(const double* __restrict__ boxes, float* __restrict__ center, 
                   float* __restrict__ area, float* __restrict__ trans_inv, double* __restrict__ trans_inv_f64,
                   int P, double ratio, double dst_w, double dst_h, float scale_mult) {
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const double x1 = boxes[4 * (size_t)i + 0], y1 = boxes[4 * (size_t)i + 1];

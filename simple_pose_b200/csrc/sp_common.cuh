@@ -35,11 +35,14 @@ static inline int sp_env_int(const char* name, int fallback) {
 static inline int sp_launch_status() { return (int)cudaGetLastError(); }
 
 // Every kernel of the library is launched with programmatic dependent launch (PDL) allowed: its
-// CTAs may be scheduled while the previous kernel on the stream is still draining, which hides the
+// CTAs may be scheduled as soon as CTAs of the previous kernel on the stream exit, which hides the
 // launch latency and the prologue (mbarrier init, index setup) behind the predecessor's tail. The
 // contract inside the kernels: sp::grid_dep_wait() before the first global-memory access (it returns
-// once the predecessor has completed and its writes are visible), sp::grid_dep_launch() right
-// after it so that the successor can be scheduled as soon as SM resources free up.
+// once the predecessor has completed and its writes are visible). No kernel triggers its
+// dependents early (griddepcontrol.launch_dependents): the implicit trigger at CTA exit is what
+// is wanted here. An early trigger was measured to cost 6-17 us per transition whenever two
+// DIFFERENT kernels alternate on a stream (encode+loss+decode step: 1535 us with it, 1455 us
+// without; scratch/seq_step.py), and to gain < 1 % for back-to-back launches of one kernel.
 // SP_NO_PDL=1 in the environment restores plain stream-ordered launches.
 static inline bool sp_pdl_enabled() {
     const char* v = getenv("SP_NO_PDL");
@@ -70,7 +73,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 // ---- programmatic dependent launch ----------------------------------------------------------
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier (shared::cta) ---------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

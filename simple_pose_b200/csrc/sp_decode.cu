@@ -496,7 +496,6 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         sp::mbar_fence_init();
     }
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
-    sp::grid_dep_launch();
     if (A.mode == SP_DECODE_GAUSS_TAYLOR)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
@@ -559,7 +558,6 @@ decode_generic_kernel(const DecodeArgs A) {
     const int warp = threadIdx.x >> 5;
     const int hw = A.H * A.W;
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     if (A.mode == SP_DECODE_GAUSS_TAYLOR)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();

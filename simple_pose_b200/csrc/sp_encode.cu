@@ -28,7 +28,6 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     const int hw = H * W;
     const int total_warps = gridDim.x * kWarpsPerCta;
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
 
     for (int m = blockIdx.x * kWarpsPerCta + warp; m < nmaps; m += total_warps) {
         const float mx = __ldg(joints + 3 * (size_t)m + 0);
@@ -97,7 +96,6 @@ encode_basic_kernel(const float* __restrict__ joints, const float* __restrict__ 
                     float* __restrict__ weights, int nmaps, int H, int W, double reach, float stride, int side) {
     extern __shared__ float tab[];
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     for (int i = threadIdx.x; i < side * side; i += blockDim.x) tab[i] = __ldg(table + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;

@@ -52,7 +52,6 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
                    double inv_count, int skip_masked) {
     double block_sum = 0.0;
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
 
     for (int m = blockIdx.x; m < nmaps; m += gridDim.x) {
         const float mk = __ldg(mask + m);
@@ -124,7 +123,6 @@ mse_ring_kernel(const float* __restrict__ pred, const float* __restrict__ target
     const long long lo = (long long)blockIdx.x * nchunks / gridDim.x;
     const long long hi = (long long)(blockIdx.x + 1) * nchunks / gridDim.x;
     sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
-    sp::grid_dep_launch();
 
     long long pi = lo + warp;       // producer cursor (lane 0): next chunk to request, into slot ps
     int ps = 0;
@@ -176,7 +174,6 @@ mse_ring_kernel(const float* __restrict__ pred, const float* __restrict__ target
 __global__ void __launch_bounds__(256)
 scale_inplace_kernel(float* __restrict__ data, long long n, const float* __restrict__ scale_dev) {
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     const float s = __ldg(scale_dev);
     if (s == 1.0f) return;
     const long long n4 = n >> 2;

@@ -285,7 +285,6 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
     const int total_warps = gridDim.x * kWarps;
     double sum_sq = 0.0;
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     Joint3 jn = load_joint(io, blockIdx.x * kWarps + warp);
     for (int m = blockIdx.x * kWarps + warp; m < io.nmaps; m += total_warps) {
         const Joint3 jc = jn;
@@ -343,7 +342,6 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     }
     __syncthreads();
     sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
-    sp::grid_dep_launch();
 
     // producer (lane 0 only): copies chunk pc of map pm into slot ps; pnext = the map claimed after pm
     int pm = -1, pnext = -1, pc = 0, ps = 0, tail = 0;
@@ -726,7 +724,6 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     }
     __syncthreads();
     sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
-    sp::grid_dep_launch();
 
     if (lane == 0) {
         rg.start(rg.claim());
@@ -767,7 +764,6 @@ heatmap_acc_kernel(const float2* __restrict__ pred_xy, const float2* __restrict_
                    int B, int K, float norm_x, float norm_y, float thresh) {
     extern __shared__ int counters[];        // hit[K], valid[K]
     sp::grid_dep_wait();
-    sp::grid_dep_launch();
     int* hit = counters;
     int* valid = counters + K;
     for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) counters[k] = 0;

@@ -98,8 +98,14 @@ class ShardedPoseEvaluator(object):
         return person_range(self.seg, self.cuts, rank)
 
     @torch.no_grad()
-    def run(self, heat_map, trans_inv, box_scores, areas, heat_map_flip=None, joint_pairs=None):
-        from .datasets.naive_data import pack_keypoints, rescore_and_nms
+    def run(self, heat_map, trans_inv, box_scores, areas, heat_map_flip=None, joint_pairs=None, boxes=None,
+            input_shape=(192, 256)):
+        """``boxes`` [n,4] (x1, y1, x2, y2) may replace ``trans_inv``/``areas``: both are then derived
+        on the device exactly as ``BasicTransform`` does (``naive_data.box_affines``)."""
+        from .datasets.naive_data import pack_keypoints, rescore_and_nms, box_affines
+        if boxes is not None:
+            aff = box_affines(boxes, input_shape, (int(heat_map.shape[-1]), int(heat_map.shape[-2])))
+            trans_inv, areas = aff["trans_inv"], aff["area"].double()
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         lo, hi = person_range(self.seg, self.cuts, rank)

