@@ -364,6 +364,59 @@ def small_batch_numbers(device, height, width, batch=128, nbatch=64):
     return out
 
 
+def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5):
+    """BASELINE config 5: a COCO-val-sized eval job (~104 k person boxes in ~5 k images) through
+    ``ShardedPoseEvaluator``: per rank box -> affine, GaussTaylor decode, rescoring and OKS-NMS of its
+    image-aligned shard, then one NCCL all-gather of the packed result rows. Fixed total work
+    (strong scaling); device-timed, max over ranks."""
+    import numpy as np
+    import torch.distributed as dist
+    from simple_pose_b200 import synth
+    from simple_pose_b200.eval_shard import ShardedPoseEvaluator
+    g = torch.Generator().manual_seed(12345)
+    images = int(persons / (1.0 + mean_group))
+    sizes = 1 + torch.poisson(torch.full((images,), float(mean_group)), generator=g).long()
+    seg = np.zeros(images + 1, dtype=np.int64)
+    seg[1:] = np.cumsum(sizes.numpy())
+    total = int(seg[-1])
+    ev = ShardedPoseEvaluator()
+    ev.plan(seg)
+    lo, hi = ev.my_persons()
+    n = hi - lo
+    hm = torch.empty((n, 17, height, width), dtype=torch.float32, device=device)
+    for a in range(0, n, 8192):
+        b = min(n, a + 8192)
+        hm[a:b] = synth.heatmaps(b - a, height=height, width=width, seed=777 + lo + a, device=device)
+    boxes = synth.detection_boxes(total, seed=778)[lo:hi].to(device)
+    box_scores = ((torch.randperm(total, generator=g).double() + 0.5) / total)[lo:hi].to(device)
+    torch.cuda.synchronize(device)
+    times = []
+    for r in range(reps + 2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        table = ev.run(hm, None, box_scores, None, boxes=boxes, input_shape=(4 * width, 4 * height))
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if r >= 2:
+            times.append(ms)
+    ms = statistics.median(times)
+    kept = int(table[:, 3 * 17].sum().item())
+    del hm, table
+    torch.cuda.empty_cache()
+    return {"workload": "cfg5: box->affine + GaussTaylor decode + rescoring + OKS-NMS + all-gather of result rows",
+            "persons": total, "images": images, "n_gpus": world, "scaling": "strong", "ms": ms,
+            "persons_per_s": total / (ms * 1e-3), "kept_after_nms": kept,
+            "decode_read_GBps_per_gpu": (n * (17 * height * width * 4)) / (ms * 1e-3) / 1e9}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from simple_pose_b200 import _abi
@@ -438,6 +491,23 @@ def run_ours(args):
     op_ms = {"encode": kernel_ms(lambda i: paths[i].encode(sets[i][0]), rounds),
              "loss": kernel_ms(lambda i: paths[i].loss_fwd_bwd(sets[i][1]), rounds),
              "decode": kernel_ms(lambda i: paths[i].decode(sets[i][1], sets[i][2]), rounds)}
+    # the same persons through the fused training kernel (encode + loss + HeatMapAcc argmaxes in one
+    # pass, targets never materialised: SURVEY 8f ranks 1-2) followed by the decode
+    def fused_step():
+        for i in range(nb):
+            paths[i].train_fused(sets[i][0], sets[i][1])
+            paths[i].decode(sets[i][1], sets[i][2])
+    for _ in range(3):
+        fused_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fsteps = max(3, min(50, args.steps))
+    f0.record()
+    for _ in range(fsteps):
+        fused_step()
+    f1.record()
+    barrier()
+    fused_ms = f0.elapsed_time(f1) / fsteps
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -445,6 +515,14 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * P / (ms_per_step * 1e-3)
+    if world > 1:
+        t = torch.tensor([fused_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fused_ms = float(t.item())
+    fused = {"persons_per_s": world * P / (fused_ms * 1e-3), "ms_per_step": fused_ms, "launches_per_step": 2 * nb,
+             "algorithmic_bytes_per_person": ALGO_BYTES["train_fused"](17, H, W) + ALGO_BYTES["decode"](17, H, W),
+             "note": "same persons, loss/grad/weights/keypoints identical; encode+loss+HeatMapAcc fused into one pass "
+                     "(targets never written), then decode; no all-gather in this loop"}
 
     dominant = max(op_ms, key=op_ms.get)
     dom_bytes = ALGO_BYTES[dominant](17, H, W) * B
@@ -475,6 +553,15 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_ops:
         small = small_batch_numbers(device, H, W)
 
+    eval_job = None
+    if not args.no_ops:
+        try:
+            del paths, sets
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        eval_job = eval_job_numbers(device, world, rank, height=H, width=W)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -500,7 +587,7 @@ def run_ours(args):
                          (nb, P * (ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)) / 1e6),
                    "parallelism": "persons sharded, dp%d" % world},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
-        "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small,
+        "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small, "eval_job": eval_job, "fused_step": fused,
     }
     print(json.dumps(line), flush=True)
 
