@@ -180,16 +180,27 @@ int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps,
  * box_to_center_scale (commons/joint_utils.py:39-56) + get_affine_transform(center, scale, 0,
  * output_shape) (commons/joint_utils.py:115-152, cv.getAffineTransform = 6x6 LU in float64).
  *
- * boxes_xyxy    [P,4] f64  detection boxes (x1, y1, x2, y2), the JSON floats of :84-95
+ * boxes         [P,4] f64  detection boxes, (x1, y1, x2, y2) as stored by :84-95 (SP_BOX_XYXY)
+ *               or (x, y, w, h) as box_to_center_scale takes them (SP_BOX_XYWH)
  * center, scale [P,2] f32 out (nullable); area [P] f32 out = scale_w * scale_h (nullable)
  * trans_inv     [P,2,3] f32 out = what collate_fn ships (.float(), :114-116) (nullable)
- * trans_inv_f64 [P,2,3] f64 out = the unrounded cv result (nullable; at least one of the two)
+ * trans_inv_f64 [P,2,3] f64 out = the unrounded cv result, heatmap -> image (nullable)
+ * trans_f64     [P,2,3] f64 out = the forward (image -> heatmap) matrix, first return value of
+ *               get_affine_transform (nullable)
  * w_h_ratio = input_w / input_h; (out_w, out_h) = heatmap size; scale_mult = 1.25.
  * Bit-identical to the reference (same roundings, same LU pivoting and operation order).
  */
-int sp_box_affine_f64(const double* boxes_xyxy, float* center, float* scale, float* area,
-                      float* trans_inv, double* trans_inv_f64, int P, double w_h_ratio,
-                      int out_w, int out_h, float scale_mult, void* stream);
+#define SP_BOX_XYXY 0
+#define SP_BOX_XYWH 1
+int sp_box_affine_f64(const double* boxes, int box_format, float* center, float* scale, float* area,
+                      float* trans_inv, double* trans_inv_f64, double* trans_f64, int P,
+                      double w_h_ratio, int out_w, int out_h, float scale_mult, void* stream);
+
+/* get_affine_transform(center, scale, rot = 0, (out_w, out_h)) (commons/joint_utils.py:115-152) for
+ * P (center [P,2] f32, scale [P,2] f32) pairs; outputs as above (at least one non-null). */
+int sp_center_scale_affine_f64(const float* center, const float* scale, float* trans_inv,
+                               double* trans_inv_f64, double* trans_f64, int P, int out_w, int out_h,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,13 +97,13 @@ def affine_fixtures(ref):
         boxes[1] = [10.0, 20.0, 10.0 + 1e-3, 20.0 + 2e-3]           # tiny box
         boxes[2] = [-1.5, 7.0, -0.5, 9.0]                           # centre x == -1: scale_mult skipped
         boxes[3] = [100.0, 50.0, 100.0, 50.0]                       # degenerate: singular system
-        c, s, a, t64 = [], [], [], []
+        c, s, a, t64, f64 = [], [], [], [], []
         for x1, y1, x2, y2 in boxes.tolist():
             ci, si = ref.box_to_center_scale(x1, y1, x2 - x1, y2 - y1, inp[0] / inp[1])
-            _, ti = ref.get_affine_transform(ci, si, 0, outp)
-            c.append(ci); s.append(si); a.append(si[0] * si[1]); t64.append(ti)
+            tf, ti = ref.get_affine_transform(ci, si, 0, outp)
+            c.append(ci); s.append(si); a.append(si[0] * si[1]); t64.append(ti); f64.append(tf)
         out.update({"boxes_" + tag: boxes, "center_" + tag: np.stack(c), "scale_" + tag: np.stack(s),
-                    "area_" + tag: np.array(a, dtype=np.float32), "tinv64_" + tag: np.stack(t64),
+                    "area_" + tag: np.array(a, dtype=np.float32), "tinv64_" + tag: np.stack(t64), "fwd64_" + tag: np.stack(f64),
                     "tinv_" + tag: torch.from_numpy(np.stack(t64)).float().numpy(),
                     "shapes_" + tag: np.array([inp, outp], dtype=np.int32)})
     np.savez_compressed(os.path.join(GOLDEN, "affine.npz"), **out)

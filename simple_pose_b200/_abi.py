@@ -22,6 +22,7 @@ c_ll = ctypes.c_longlong
 
 SP_DECODE_GAUSS_TAYLOR, SP_DECODE_ARGMAX, SP_DECODE_BASIC = 0, 1, 2
 SP_MSE_SKIP_MASKED = 1
+SP_BOX_XYXY, SP_BOX_XYWH = 0, 1
 
 # name -> (restype, argtypes); mirrors include/simple_pose_b200.h one to one
 SIGNATURES = {
@@ -43,7 +44,8 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_void]),
     "sp_rescore_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_dbl, c_void]),
     "sp_pack_kps_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void]),
-    "sp_box_affine_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_dbl, c_int, c_int, c_flt, c_void]),
+    "sp_box_affine_f64": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_dbl, c_int, c_int, c_flt, c_void]),
+    "sp_center_scale_affine_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_void]),
 }
 
 _lock = threading.Lock()

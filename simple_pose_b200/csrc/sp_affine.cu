@@ -65,24 +65,9 @@ __device__ __forceinline__ void third_point(float (&tri)[3][2]) {
     tri[2][1] = __fadd_rn(tri[1][1], dx);
 }
 
-__global__ void __launch_bounds__(128)
-box_affine_kernel(const double* __restrict__ boxes, float* __restrict__ center, float* __restrict__ scale,
-                  float* __restrict__ area, float* __restrict__ trans_inv, double* __restrict__ trans_inv_f64,
-                  int P, double ratio, double dst_w, double dst_h, float scale_mult) {
-    sp::grid_dep_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const double x1 = boxes[4 * (size_t)i + 0], y1 = boxes[4 * (size_t)i + 1];
-    double w = __dsub_rn(boxes[4 * (size_t)i + 2], x1), h = __dsub_rn(boxes[4 * (size_t)i + 3], y1);
-    // box_to_center_scale
-    const float cx = __double2float_rn(__dadd_rn(x1, __dmul_rn(w, 0.5)));
-    const float cy = __double2float_rn(__dadd_rn(y1, __dmul_rn(h, 0.5)));
-    const double rh = __dmul_rn(ratio, h);
-    if (w > rh) h = __ddiv_rn(w, ratio);
-    else if (w < rh) w = __dmul_rn(h, ratio);
-    float sw = __double2float_rn(w), sh = __double2float_rn(h);
-    if (cx != -1.0f) { sw = __fmul_rn(sw, scale_mult); sh = __fmul_rn(sh, scale_mult); }
-    // the two triangles of get_affine_transform(center, scale, rot = 0, output_size)
+// get_affine_transform(center, scale, rot = 0, (dst_w, dst_h)): inv = heatmap -> image, fwd = image -> heatmap
+__device__ void affines_from_center_scale(float cx, float cy, float sw, double dst_w, double dst_h,
+                                          double (&inv)[6], double* fwd /* 6 or nullptr */) {
     float src[3][2], dst[3][2];
     src[0][0] = cx; src[0][1] = cy;
     src[1][0] = __double2float_rn(__dadd_rn((double)cx, 0.0));
@@ -93,28 +78,86 @@ box_affine_kernel(const double* __restrict__ boxes, float* __restrict__ center, 
     dst[1][0] = __double2float_rn(__dadd_rn(hw, 0.0));
     dst[1][1] = __double2float_rn(__dadd_rn(hh, (double)__double2float_rn(__dmul_rn(dst_w, -0.5))));
     third_point(dst);
-    double m[6];
-    solve_affine_lu(dst, src, m);         // heatmap -> image
+    if (fwd) {
+        double m[6];
+        solve_affine_lu(src, dst, m);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) fwd[e] = m[e];
+    }
+    solve_affine_lu(dst, src, inv);
+}
+
+__device__ __forceinline__ void store_affines(size_t i, const double (&inv)[6], float* trans_inv, double* trans_inv_f64) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        if (trans_inv) trans_inv[6 * i + e] = __double2float_rn(inv[e]);
+        if (trans_inv_f64) trans_inv_f64[6 * i + e] = inv[e];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+box_affine_kernel(const double* __restrict__ boxes, int xywh, float* __restrict__ center, float* __restrict__ scale,
+                  float* __restrict__ area, float* __restrict__ trans_inv, double* __restrict__ trans_inv_f64,
+                  double* __restrict__ trans_f64, int P, double ratio, double dst_w, double dst_h, float scale_mult) {
+    sp::grid_dep_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const double x1 = boxes[4 * (size_t)i + 0], y1 = boxes[4 * (size_t)i + 1];
+    double w = boxes[4 * (size_t)i + 2], h = boxes[4 * (size_t)i + 3];
+    if (!xywh) { w = __dsub_rn(w, x1); h = __dsub_rn(h, y1); }
+    // box_to_center_scale
+    const float cx = __double2float_rn(__dadd_rn(x1, __dmul_rn(w, 0.5)));
+    const float cy = __double2float_rn(__dadd_rn(y1, __dmul_rn(h, 0.5)));
+    const double rh = __dmul_rn(ratio, h);
+    if (w > rh) h = __ddiv_rn(w, ratio);
+    else if (w < rh) w = __dmul_rn(h, ratio);
+    float sw = __double2float_rn(w), sh = __double2float_rn(h);
+    if (cx != -1.0f) { sw = __fmul_rn(sw, scale_mult); sh = __fmul_rn(sh, scale_mult); }
     if (center) { center[2 * (size_t)i] = cx; center[2 * (size_t)i + 1] = cy; }
     if (scale) { scale[2 * (size_t)i] = sw; scale[2 * (size_t)i + 1] = sh; }
     if (area) area[i] = __fmul_rn(sw, sh);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) {
-        if (trans_inv) trans_inv[6 * (size_t)i + e] = __double2float_rn(m[e]);
-        if (trans_inv_f64) trans_inv_f64[6 * (size_t)i + e] = m[e];
+    if (trans_inv || trans_inv_f64 || trans_f64) {
+        double inv[6];
+        affines_from_center_scale(cx, cy, sw, dst_w, dst_h, inv, trans_f64 ? trans_f64 + 6 * (size_t)i : nullptr);
+        store_affines((size_t)i, inv, trans_inv, trans_inv_f64);
     }
+}
+
+__global__ void __launch_bounds__(128)
+center_scale_affine_kernel(const float* __restrict__ center, const float* __restrict__ scale, float* __restrict__ trans_inv,
+                           double* __restrict__ trans_inv_f64, double* __restrict__ trans_f64, int P, double dst_w,
+                           double dst_h) {
+    sp::grid_dep_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    double inv[6];
+    affines_from_center_scale(center[2 * (size_t)i], center[2 * (size_t)i + 1], scale[2 * (size_t)i], dst_w, dst_h, inv,
+                              trans_f64 ? trans_f64 + 6 * (size_t)i : nullptr);
+    store_affines((size_t)i, inv, trans_inv, trans_inv_f64);
 }
 
 }  // namespace
 
-extern "C" int sp_box_affine_f64(const double* boxes_xyxy, float* center, float* scale, float* area,
-                                 float* trans_inv, double* trans_inv_f64, int P, double w_h_ratio,
-                                 int out_w, int out_h, float scale_mult, void* stream) {
+extern "C" int sp_box_affine_f64(const double* boxes, int box_format, float* center, float* scale, float* area,
+                                 float* trans_inv, double* trans_inv_f64, double* trans_f64, int P,
+                                 double w_h_ratio, int out_w, int out_h, float scale_mult, void* stream) {
     SP_RETURN_IF(P < 0 || out_w <= 0 || out_h <= 0 || !(w_h_ratio > 0.0), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(box_format != SP_BOX_XYXY && box_format != SP_BOX_XYWH, SP_ERR_BAD_ARGUMENT);
     if (P == 0) return 0;                  /* empty batches carry null data pointers */
-    SP_RETURN_IF(!boxes_xyxy || (!trans_inv && !trans_inv_f64), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!boxes || (!trans_inv && !trans_inv_f64 && !trans_f64 && !center && !scale && !area), SP_ERR_BAD_ARGUMENT);
     SP_CUDA(sp_launch(box_affine_kernel, dim3((P + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
-                      boxes_xyxy, center, scale, area, trans_inv, trans_inv_f64, P, w_h_ratio, (double)out_w,
-                      (double)out_h, scale_mult));
+                      boxes, box_format == SP_BOX_XYWH ? 1 : 0, center, scale, area, trans_inv, trans_inv_f64, trans_f64, P,
+                      w_h_ratio, (double)out_w, (double)out_h, scale_mult));
+    return sp_launch_status();
+}
+
+extern "C" int sp_center_scale_affine_f64(const float* center, const float* scale, float* trans_inv,
+                                          double* trans_inv_f64, double* trans_f64, int P, int out_w, int out_h,
+                                          void* stream) {
+    SP_RETURN_IF(P < 0 || out_w <= 0 || out_h <= 0, SP_ERR_BAD_ARGUMENT);
+    if (P == 0) return 0;
+    SP_RETURN_IF(!center || !scale || (!trans_inv && !trans_inv_f64 && !trans_f64), SP_ERR_BAD_ARGUMENT);
+    SP_CUDA(sp_launch(center_scale_affine_kernel, dim3((P + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                      center, scale, trans_inv, trans_inv_f64, trans_f64, P, (double)out_w, (double)out_h));
     return sp_launch_status();
 }

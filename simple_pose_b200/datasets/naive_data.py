@@ -113,16 +113,19 @@ def rescore_and_nms(kps, box_scores, areas, seg_offsets, in_vis_thre=0.2, oks_th
     return keep, scores, rank
 
 
-def box_affines(boxes_xyxy, input_shape=(192, 256), output_shape=(48, 64), scale_mult=1.25, want_f64=False):
+def box_affines(boxes_xyxy, input_shape=(192, 256), output_shape=(48, 64), scale_mult=1.25, want_f64=False,
+                xywh=False):
     """``BasicTransform.__call__`` without the image warp (reference ``datasets/naive_data.py:44-56``)
     for all detection boxes at once: boxes [P,4] (x1, y1, x2, y2; host list/array or device tensor,
     float64) -> dict of device tensors ``center`` [P,2], ``scale`` [P,2], ``area`` [P] (float32) and
     ``trans_inv`` [P,2,3] float32, the heatmap -> image affine the decoder consumes (bit-identical to
     ``get_affine_transform(center, scale, 0, output_shape)[1]`` after ``collate_fn``'s ``.float()``).
-    ``want_f64`` adds ``trans_inv_f64``, the unrounded matrix."""
+    ``xywh=True`` reads the rows as (x, y, w, h), the arguments of ``box_to_center_scale``.
+    ``want_f64`` adds ``trans_inv_f64``, the unrounded matrix, and ``trans_f64``, the forward
+    (image -> heatmap) matrix -- the two float64 return values of ``get_affine_transform``."""
     b = _f64(np.asarray(boxes_xyxy, dtype=np.float64) if not isinstance(boxes_xyxy, torch.Tensor) else boxes_xyxy)
     if b.dim() != 2 or b.shape[1] != 4:
-        raise ValueError("boxes must be [P, 4] (x1, y1, x2, y2)")
+        raise ValueError("boxes must be [P, 4]: (x1, y1, x2, y2), or (x, y, w, h) with xywh=True")
     dev, n = b.device, int(b.shape[0])
     out = {"center": torch.empty((n, 2), dtype=torch.float32, device=dev),
            "scale": torch.empty((n, 2), dtype=torch.float32, device=dev),
@@ -130,10 +133,11 @@ def box_affines(boxes_xyxy, input_shape=(192, 256), output_shape=(48, 64), scale
            "trans_inv": torch.empty((n, 2, 3), dtype=torch.float32, device=dev)}
     if want_f64:
         out["trans_inv_f64"] = torch.empty((n, 2, 3), dtype=torch.float64, device=dev)
+        out["trans_f64"] = torch.empty((n, 2, 3), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _abi.check(_abi.lib().sp_box_affine_f64(
-            b.data_ptr(), out["center"].data_ptr(), out["scale"].data_ptr(), out["area"].data_ptr(),
-            out["trans_inv"].data_ptr(), _abi.ptr(out.get("trans_inv_f64")), n,
+            b.data_ptr(), _abi.SP_BOX_XYWH if xywh else _abi.SP_BOX_XYXY, out["center"].data_ptr(), out["scale"].data_ptr(), out["area"].data_ptr(),
+            out["trans_inv"].data_ptr(), _abi.ptr(out.get("trans_inv_f64")), _abi.ptr(out.get("trans_f64")), n,
             float(input_shape[0]) / float(input_shape[1]), int(output_shape[0]), int(output_shape[1]),
             float(scale_mult), _abi.stream_ptr(dev)))
     return out

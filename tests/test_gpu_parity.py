@@ -530,7 +530,7 @@ def test_box_affines_golden_and_oracle(api, golden):
         inp, outp = [tuple(int(v) for v in r) for r in g["shapes_" + tag]]
         out = api.naive.box_affines(g["boxes_" + tag], inp, outp, want_f64=True)
         for key, name in (("center", "center_"), ("scale", "scale_"), ("area", "area_"), ("trans_inv", "tinv_"),
-                          ("trans_inv_f64", "tinv64_")):
+                          ("trans_inv_f64", "tinv64_"), ("trans_f64", "fwd64_")):
             assert np.array_equal(bits(out[key].cpu().numpy()), bits(g[name + tag])), (tag, key)
     for inp, outp in (((192, 256), (48, 64)), ((288, 384), (72, 96)), ((256, 256), (64, 64))):
         boxes = synth.detection_boxes(3000, seed=88, ratio_exact_every=32, ratio=inp[0] / inp[1])
@@ -541,6 +541,20 @@ def test_box_affines_golden_and_oracle(api, golden):
         assert np.array_equal(bits(out["area"].cpu().numpy()), bits(a))
         assert np.array_equal(bits(out["trans_inv"].cpu().numpy()), bits(tinv))
     assert api.naive.box_affines(np.zeros((0, 4)))["trans_inv"].shape == (0, 2, 3)
+    # per-sample drop-ins of commons/joint_utils.py and the batched centre/scale form
+    from simple_pose_b200.commons import joint_utils as ju
+    boxes, inp, outp = g["boxes_a"], (192, 256), (48, 64)
+    for i in (0, 1, 2, 3, 8, 17):
+        x1, y1, x2, y2 = boxes[i].tolist()
+        c, s = ju.box_to_center_scale(x1, y1, x2 - x1, y2 - y1, inp[0] / inp[1])
+        assert c.dtype == np.float32 and s.dtype == np.float32
+        assert np.array_equal(bits(c), bits(g["center_a"][i])) and np.array_equal(bits(s), bits(g["scale_a"][i]))
+        fwd, inv = ju.get_affine_transform(c, s, 0, outp)
+        assert np.array_equal(bits(fwd), bits(g["fwd64_a"][i])) and np.array_equal(bits(inv), bits(g["tinv64_a"][i]))
+    fwd, inv = ju.get_affine_transforms(g["center_b"], g["scale_b"], (72, 96))
+    assert np.array_equal(bits(fwd.cpu().numpy()), bits(g["fwd64_b"])) and np.array_equal(bits(inv.cpu().numpy()), bits(g["tinv64_b"]))
+    with pytest.raises(NotImplementedError):
+        ju.get_affine_transform(c, s, 30, outp)
 
 
 def test_boxes_to_keypoints_device_resident(api):
