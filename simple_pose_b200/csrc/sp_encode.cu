@@ -15,8 +15,8 @@ namespace {
 using namespace sp_gauss;
 constexpr int kWarpsPerCta = 8;
 
-template <bool VEC4>
-__global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)
+template <bool VEC4, int WARPS>
+__global__ void __launch_bounds__(WARPS* SP_WARP)
 encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targets, float* __restrict__ weights,
                      int nmaps, int H, int W, float reach, double denom) {
     extern __shared__ __align__(16) double factors[];   // per warp: ex[Wpad] then ey[H]
@@ -26,10 +26,10 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     double* ex = factors + (size_t)warp * (wpad + H);
     double* ey = ex + wpad;
     const int hw = H * W;
-    const int total_warps = gridDim.x * kWarpsPerCta;
+    const int total_warps = gridDim.x * WARPS;
     sp::grid_dep_wait();
 
-    for (int m = blockIdx.x * kWarpsPerCta + warp; m < nmaps; m += total_warps) {
+    for (int m = blockIdx.x * WARPS + warp; m < nmaps; m += total_warps) {
         const float mx = __ldg(joints + 3 * (size_t)m + 0);
         const float my = __ldg(joints + 3 * (size_t)m + 1);
         const float vis = __ldg(joints + 3 * (size_t)m + 2);
@@ -137,22 +137,26 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     const float reach = (float)reach_d;            // weak Python scalar -> float32 in the cull test
     const double denom = 2.0 * (sigma * sigma);    // 2 * sigma ** 2
     const int wpad = (W + 1) & ~1;
-    const size_t smem = (size_t)kWarpsPerCta * (wpad + H) * sizeof(double);
+    // one map per warp, no persistence: the hardware backfills CTAs as they retire. Small CTAs keep
+    // the per-SM load even: 2-warp CTAs put 29.4 +- 0.5 CTAs on an SM where 8-warp CTAs put 7 or 8
+    // (96x72, 512 persons: 9 % of the launch was the SMs that drew 8). Measured 8 -> 2 warps per CTA:
+    // 0.934 -> 0.954 of the HBM peak at 64x48 x 1024, 0.862 -> 0.900 at 96x72 x 512, 10.6 -> 7.9 us at 64x48 x 128.
+    int warps = sp_env_int("SP_ENCODE_WARPS", 2);
+    if (warps != 2 && warps != 4 && warps != 8) warps = 2;
+    const size_t smem = (size_t)warps * (wpad + H) * sizeof(double);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     const bool vec4 = (W % 4 == 0) && sp_aligned16(targets);
-    // one map per warp, no persistence: with ~2 maps per resident warp a grid-stride loop leaves a
-    // ragged second wave; letting the hardware backfill 8-map CTAs balances it
-    const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid = (nmaps + warps - 1) / warps;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (vec4) {
-        if (smem > 48 * 1024)
-            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SP_CUDA(sp_launch(encode_refine_kernel<true>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom));
-    } else {
-        if (smem > 48 * 1024)
-            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SP_CUDA(sp_launch(encode_refine_kernel<false>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom));
-    }
+#define SP_LAUNCH_ENCODE(V, NW)                                                                                         \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<V, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SP_CUDA(sp_launch(encode_refine_kernel<V, NW>, dim3(grid), dim3(NW * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom)); \
+    } while (0)
+    if (vec4) { if (warps == 2) SP_LAUNCH_ENCODE(true, 2); else if (warps == 4) SP_LAUNCH_ENCODE(true, 4); else SP_LAUNCH_ENCODE(true, 8); }
+    else      { if (warps == 2) SP_LAUNCH_ENCODE(false, 2); else if (warps == 4) SP_LAUNCH_ENCODE(false, 4); else SP_LAUNCH_ENCODE(false, 8); }
+#undef SP_LAUNCH_ENCODE
     return sp_launch_status();
 }
 

@@ -74,6 +74,20 @@ def test_encode_vs_oracle(api, shape, persons):
     assert 0 < (rw == 0).mean() < 1          # both cull branches exercised
 
 
+@pytest.mark.parametrize("warps", ["2", "4", "8"])
+def test_encode_cta_sizes_agree(api, warps):
+    """Every CTA size of the encoder (SP_ENCODE_WARPS) writes the same bits, odd map counts included."""
+    joints = synth.joints(37, seed=321).to(DEV)
+    base_t, base_w = api.transforms.encode_heat_maps(joints)
+    os.environ["SP_ENCODE_WARPS"] = warps
+    try:
+        t, w = api.transforms.encode_heat_maps(joints)
+        t2, w2 = api.transforms.encode_heat_maps(joints[:, :, :], 2.0, (48, 64))
+    finally:
+        del os.environ["SP_ENCODE_WARPS"]
+    assert torch.equal(t, base_t) and torch.equal(w, base_w) and torch.equal(t2, base_t) and torch.equal(w2, base_w)
+
+
 def test_encode_per_sample_signature_and_empty(api, golden):
     g = golden("encode")
     t, w = api.transforms.RefineSimpleTransform.get_heat_map(g["joints_e"][0], sigma=2.0, shape=(48, 64))
