@@ -67,7 +67,7 @@ def hbm_peak():
 def ncu_traffic(kernel, height, width, batch):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
     (profiles/r*_traffic.json), if one exists for this exact launch shape; else None."""
-    names = {"encode": "encode_refine_kernel<1>", "loss": "mse_ring_kernel<1>", "decode": "decode_tma_kernel<0, 11>",
+    names = {"encode": "encode_refine_kernel<1, 2>", "loss": "mse_ring_kernel<1>", "decode": "decode_tma_kernel<0, 11>",
              "train_fused": "encode_mse_tile_kernel<12, 2, 1, 1>", "flip_decode": "decode_tma_kernel<1, 11>"}
     key = "%s @ %dx%d,P=%d" % (names.get(kernel, kernel), height, width, batch)
     pdir = os.path.join(ROOT, "profiles")
@@ -460,8 +460,8 @@ def run_ours(args):
 
     def kernel_ms(fn, rounds):
         """Average launch duration of one kernel: CUDA events around nb back-to-back launches
-        (one per distinct buffer set) on the launching stream, averaged over `rounds`."""
-        tot = 0.0
+        (one per distinct buffer set) on the launching stream; median over `rounds`."""
+        per_round = []
         for _ in range(rounds):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -469,8 +469,8 @@ def run_ours(args):
                 fn(i)
             b.record()
             b.synchronize()
-            tot += a.elapsed_time(b) / nb
-        return tot / rounds
+            per_round.append(a.elapsed_time(b) / nb)
+        return statistics.median(per_round)      # a round that collides with an nvidia-smi poll is an outlier
 
     for _ in range(max(3, args.warmup)):
         step()

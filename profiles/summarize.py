@@ -80,14 +80,19 @@ def main():
             skipped += 1            # torch kernels that build the synthetic inputs before the timed steps
             continue
         agg.setdefault(short(r[4]), []).append(float(r[-1]))
-    total = sum(sum(v) for v in agg.values())
+    # one step of bench.py launches each of its three kernels once per batch; the same command also
+    # runs the fused-training-step loop (encode_mse_* + decode), so shares are taken from the
+    # per-launch averages of the three step kernels, not from totals
+    step = [k for k in agg if k.startswith(("encode_refine", "mse_ring", "mse_fwd_bwd", "decode_tma", "decode_generic"))]
+    step_sum = sum(sum(agg[k]) / len(agg[k]) for k in step)
     md = ["# ncu summary %s" % tag, "",
           "Launch list (`%s_launches.csv`, `ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache and"
           " serialised: compare shares, not absolutes; %d launches of torch/NCCL setup kernels that generate the synthetic"
           " inputs before the steps are left out of the shares):" % (tag, skipped), "",
           "| kernel | launches | avg us | share of step |", "|---|---|---|---|"]
     for k, v in agg.items():
-        md.append("| `%s` | %d | %.1f | %.3f |" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / total))
+        share = ("%.3f" % (sum(v) / len(v) / step_sum)) if k in step else "- (fused step)"
+        md.append("| `%s` | %d | %.1f | %s |" % (k, len(v), sum(v) / len(v) / 1e3, share))
     md += ["", "Full capture (`ncu --set full --clock-control none --import-source on`, `profiles/prof_driver.py`;"
            " last captured launch per kernel/grid; `%s_kernels.json` has every launch):" % tag, "",
            "| kernel | grid x block | us | DRAM read MB | DRAM write MB | DRAM GB/s | dram % of ncu peak | issue % | warps active % | regs | fp64 pipe % |",
