@@ -495,12 +495,8 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         for (int s = 0; s < stages; ++s) sp::mbar_init(bars + s, 1);
         sp::mbar_fence_init();
     }
+    __syncthreads();                // work counter and barriers are visible to every warp
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
-    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
-        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
-    __syncthreads();
-    LaneTaps<(KS > 0 ? KS : 3)> taps;
-    if (KS > 0 && A.mode == SP_DECODE_GAUSS_TAYLOR) taps.load(wts, lane);
 
     // lane 0: claim the next map of this CTA and start its copy into stage s (or park -1)
     auto claim_and_issue = [&](int s) {
@@ -520,8 +516,15 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         }
     };
 
+    // first copies go out before anything else touches global memory: the blur weights (a dependent
+    // global load + block barrier, ~0.7 us) are fetched while the first maps are in flight
     if (lane == 0)
         for (int s = 0; s < stages; ++s) claim_and_issue(s);
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+        for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    __syncthreads();
+    LaneTaps<(KS > 0 ? KS : 3)> taps;
+    if (KS > 0 && A.mode == SP_DECODE_GAUSS_TAYLOR) taps.load(wts, lane);
     int s = 0;
     uint32_t parity = 0;
     for (;;) {
