@@ -34,9 +34,9 @@ def grouped(seq, n=40):
     for _ in range(n): fn()
     b.record(); b.synchronize()
     return a.elapsed_time(b) / n * 1e3
-for pdl in ("0", "1"):
+for pdl in ("0",):
     os.environ["SP_NO_PDL"] = pdl
     r = {"E": timeit([E_]), "L": timeit([L_]), "D": timeit([D_]), "EL": timeit([E_, L_]), "LD": timeit([L_, D_]), "ED": timeit([E_, D_]),
-         "DE": timeit([D_, E_]), "ELD": timeit([E_, L_, D_]), "EDL": timeit([E_, D_, L_]), "DEL": timeit([D_, E_, L_]), "grouped E*,L*,D*": grouped([E_, L_, D_])}
+         "DE": timeit([D_, E_]), "ELD": timeit([E_, L_, D_]), "EDL": timeit([E_, D_, L_]), "DEL": timeit([D_, E_, L_]), "grouped E*,L*,D*": grouped([E_, L_, D_]), "grouped D*,E*,L*": grouped([D_, E_, L_]), "grouped E*,D*,L*": grouped([E_, D_, L_])}
     print("SP_NO_PDL=" + pdl, {k: round(v, 1) for k, v in r.items()})
     print("   sums: E+L %.1f  L+D %.1f  E+D %.1f  E+L+D %.1f" % (r["E"] + r["L"], r["L"] + r["D"], r["E"] + r["D"], r["E"] + r["L"] + r["D"]))

@@ -90,3 +90,21 @@ class HeatmapHotPath(object):
         return self.loss, self.coords, self.maxval
 
     LAUNCHES_PER_STEP = 3
+
+
+def run_batches(paths, inputs, after_decode=None):
+    """One pass of the hot path over several batches: ``paths[i]`` is the ``HeatmapHotPath`` of batch i and
+    ``inputs[i] = (joints, pred, trans_inv)``. Launches are grouped by kernel -- all decodes, then
+    all encodes, then all losses -- because B200 pays ~5 us whenever two different kernels follow
+    each other on a stream (8 x 1024 persons: 1367 us grouped, 1408 us interleaved, 1354 us = sum
+    of the kernels timed alone; scratch/seq_step.py). ``after_decode`` is called once all decodes
+    are enqueued (bench.py starts the NCCL all-gather of the keypoints there, so that it overlaps
+    the encode and loss kernels). Same 3 launches per batch and the same results as ``step``."""
+    for hp, (joints, pred, trans_inv) in zip(paths, inputs):
+        hp.decode(pred, trans_inv)
+    if after_decode is not None:
+        after_decode()
+    for hp, (joints, pred, trans_inv) in zip(paths, inputs):
+        hp.encode(joints)
+    for hp, (joints, pred, trans_inv) in zip(paths, inputs):
+        hp.loss_fwd_bwd(pred)
