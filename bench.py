@@ -265,6 +265,31 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- our arm
+def bind_near_gpu(local):
+    """Pin this rank's CPU affinity to the cores next to its GPU (NVML's ideal affinity) so that the
+    pinned host buffers of the e2e leg are first-touched on the GPU's own NUMA node. Without it all
+    8 ranks of a node tend to allocate on one socket and the e2e leg is bound by that socket's memory
+    and the inter-socket link instead of 8 PCIe links. Best effort: returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local)
+        handle = None
+        try:
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if hasattr(bus, "encode") else bus)
+        except Exception:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[local]) if visible and visible.split(",")[local].isdigit() else local
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = sorted(os.sched_getaffinity(0))
+        return "cpu affinity %d -> %d cores (%d..%d)" % (before, len(after), after[0], after[-1])
+    except Exception as exc:          # not fatal: the run proceeds with the inherited affinity
+        return "unchanged (%s)" % type(exc).__name__
+
+
 def make_inputs(persons, batch, height, width, device, seed):
     """Per-batch input sets generated on the device: joints, predicted heatmaps, affines."""
     from simple_pose_b200 import synth
@@ -429,6 +454,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    numa = {"text": "not requested"}
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _abi.lib()
@@ -551,7 +577,13 @@ def run_ours(args):
     # end to end through the public Python API, host buffers in, host results out
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, device, world, rank, P, B, H, W)
+        saved_affinity = os.sched_getaffinity(0)
+        if not os.environ.get("SP_BENCH_NO_BIND"):
+            numa["text"] = bind_near_gpu(local)          # pinned host buffers land on the GPU's NUMA node
+        try:
+            e2e = run_e2e(args, device, world, rank, P, B, H, W)
+        finally:
+            os.sched_setaffinity(0, saved_affinity)      # the CPU baseline below uses every core again
 
     ops = None
     if rank == 0 and not args.no_ops and world == 1:
@@ -597,7 +629,7 @@ def run_ours(args):
                    "persons_per_gpu_per_step": P, "persons_per_launch": B,
                    "l2": "inputs larger than L2: %d distinct buffer sets, %.0f MB touched per step per GPU" %
                          (nb, P * (ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)) / 1e6),
-                   "parallelism": "persons sharded, dp%d" % world},
+                   "parallelism": "persons sharded, dp%d" % world, "e2e_host_binding": numa["text"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
         "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small, "eval_job": eval_job, "fused_step": fused,
     }
