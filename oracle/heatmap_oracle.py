@@ -381,20 +381,27 @@ def box_center_scale(x, y, w, h, aspect_ratio=1.0, scale_mult=1.25):
     return center, scale
 
 
-def affine_triangles(center, scale, output_size):
-    """The two point triples of ``get_affine_transform(center, scale, 0, output_size)``
-    (commons/joint_utils.py:115-150) for rot = 0, shift = 0, as float32 [3,2] arrays. The second
-    points are float64 sums rounded to float32 (float32 array + Python list), the third points
-    float32 arithmetic (``get_3rd_point`` :72-75)."""
+def affine_triangles(center, scale, output_size, rot=0.0):
+    """The two point triples of ``get_affine_transform(center, scale, rot, output_size)``
+    (commons/joint_utils.py:115-150) for shift = 0, as float32 [3,2] arrays. ``rot`` is a Python
+    float in degrees: ``rot_rad = np.pi * rot / 180`` and ``get_dir`` (:78-85) are float64
+    (``0 * cs - p * sn``, ``0 * sn + p * cs`` with p = float32 ``src_w * -0.5`` promoted), the
+    second points are float64 sums rounded to float32 (float32 array + list of float64), the third
+    points float32 arithmetic (``get_3rd_point`` :72-75). NumPy >= 2 promotion rules (a Python
+    scalar never widens a float32)."""
     center = np.asarray(center, dtype=np.float32)
     src_w = np.float32(scale[0])
     dst_w, dst_h = output_size[0], output_size[1]
-    half = np.float64(src_w * np.float32(-0.5))                  # get_dir([0, src_w*-0.5], 0)[1]: float32 -> float64
+    half = np.float64(src_w * np.float32(-0.5))                  # src_w * -0.5 stays float32, then float64 in get_dir
+    rot_rad = np.pi * float(rot) / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    dir_x = 0 * cs - half * sn
+    dir_y = 0 * sn + half * cs
     src = np.zeros((3, 2), dtype=np.float32)
     dst = np.zeros((3, 2), dtype=np.float32)
     src[0] = center
-    src[1, 0] = np.float64(center[0]) + 0.0
-    src[1, 1] = np.float64(center[1]) + half
+    src[1, 0] = np.float64(center[0]) + dir_x
+    src[1, 1] = np.float64(center[1]) + dir_y
     dst[0] = [dst_w * 0.5, dst_h * 0.5]
     dst[1, 0] = dst_w * 0.5 + 0.0
     dst[1, 1] = dst_h * 0.5 + np.float64(np.float32(dst_w * -0.5))
@@ -445,9 +452,9 @@ def solve_affine_lu(p_from, p_to):
     return x.reshape(2, 3)
 
 
-def affine_pair(center, scale, output_size):
-    """(trans, trans_inv) of ``get_affine_transform(center, scale, 0, output_size)``, float64 [2,3]."""
-    src, dst = affine_triangles(center, scale, output_size)
+def affine_pair(center, scale, output_size, rot=0.0):
+    """(trans, trans_inv) of ``get_affine_transform(center, scale, rot, output_size)``, float64 [2,3]."""
+    src, dst = affine_triangles(center, scale, output_size, rot)
     return solve_affine_lu(src, dst), solve_affine_lu(dst, src)
 
 
@@ -470,3 +477,55 @@ def box_affines(boxes_xyxy, input_shape=(192, 256), output_shape=(48, 64), scale
         center[i], scale[i], area[i] = c, s, s[0] * s[1]
         tinv[i] = ti.astype(np.float32)
     return center, scale, area, tinv
+
+
+# --------------------------------------------------------------------------- train-side caller of the encoder
+def flip_joints_only(joints, width, joint_pairs=COCO_JOINT_PAIRS):
+    """Joint half of ``flip_joints`` (commons/joint_utils.py:102-112): ``x -> width - x - 1`` in
+    float32 (``width`` is a Python int, so both subtractions stay float32) for EVERY row, visible or
+    not, then whole rows (x, y, vis) of each pair are swapped."""
+    out = np.array(joints, dtype=np.float32, copy=True)
+    out[:, 0] = np.float32(width) - out[:, 0] - np.float32(1)
+    for a, b in joint_pairs:
+        out[[a, b]] = out[[b, a]]
+    return out
+
+
+def affine_joints(joints, t):
+    """``affine_transform_batch`` (commons/joint_utils.py:88-99): rows with vis > 0 are mapped by
+    ``[x, y, 1] . t.T`` -- float32 operands promoted to float64, ``np.dot`` (OpenBLAS dgemm, which
+    on FMA hardware accumulates ``fma(1, t2, fma(y, t1, x*t0))``; probe in DESIGN.md) -- and rounded
+    back into the float32 joint array; the other rows are left alone."""
+    out = np.array(joints, dtype=np.float32, copy=True)
+    vis = out[:, 2] > 0
+    homog = np.concatenate([out[vis, :2], np.ones_like(out[vis, 0:1])], axis=-1)
+    out[vis, :2] = np.dot(homog, np.asarray(t).T)
+    return out
+
+
+def train_sample_geometry(box, img_w, joints, scale_ratio=1.0, rot=0.0, flip=False,
+                          joint_pairs=COCO_JOINT_PAIRS, input_shape=(192, 256), output_shape=(48, 64),
+                          sigma=2.0):
+    """``RefineSimpleTransform.__call__`` (commons/transforms.py:193-223) without the image work
+    (``cv.warpAffine``, ``np.fliplr``) and with its random draws passed in: ``box`` is the box AFTER
+    ``box_crop`` (four Python floats), ``scale_ratio`` / ``rot`` / ``flip`` are the three draws of
+    :204-211. Returns a dict with the reference's per-sample products: ``center``, ``scale``
+    (float32 [2], after augmentation), ``img_trans`` (float64 [2,3], what the image warp uses),
+    ``trans_inv`` (float64 [2,3], ``joint_info.trans_inv``), ``joints_input`` (``joint_info.joints``),
+    ``joints_hm`` (the encoder's input), ``heat_map`` [K,H,W], ``mask`` [K]."""
+    x1, y1, x2, y2 = (float(v) for v in box)
+    ratio = input_shape[0] / input_shape[1]
+    center, scale = box_center_scale(x1, y1, x2 - x1, y2 - y1, ratio)
+    scale = scale * np.float32(scale_ratio)                      # float32 array * Python float
+    joints = np.array(joints, dtype=np.float32, copy=True)
+    if flip:
+        joints = flip_joints_only(joints, img_w, joint_pairs)
+        center[0] = np.float32(img_w) - center[0] - np.float32(1)
+    img_trans, _ = affine_pair(center, scale, input_shape, rot)
+    joint_trans, trans_inv = affine_pair(center, scale, output_shape, rot)
+    joints_input = affine_joints(joints, img_trans)
+    joints_hm = affine_joints(joints, joint_trans)
+    heat_map, mask = encode_person(joints_hm, sigma, output_shape)
+    return {"center": center, "scale": scale, "img_trans": img_trans, "joint_trans": joint_trans,
+            "trans_inv": trans_inv, "joints_input": joints_input, "joints_hm": joints_hm,
+            "heat_map": heat_map, "mask": mask}

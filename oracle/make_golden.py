@@ -109,12 +109,39 @@ def affine_fixtures(ref):
     np.savez_compressed(os.path.join(GOLDEN, "affine.npz"), **out)
 
 
+def train_geometry_fixtures(ref):
+    """Train-side caller of the encoder: the reference's own ``RefineSimpleTransform.__call__``
+    (commons/transforms.py:193-223) with scripted draws (``ref_loader.run_train_transform``)."""
+    out = {}
+    for tag, inp, outp, n, keep_maps in (("a", (192, 256), (48, 64), 48, 4), ("b", (288, 384), (72, 96), 16, 1)):
+        smp = synth.train_samples(n, seed=71)
+        smp["rot"][1] = 180.0; smp["rot"][2] = -90.0; smp["rot"][3] = 1e-9     # cos < 0, cos ~ 1e-17, tiny angle
+        smp["joints"][4, :, 2] = 0.0                                             # a person with no visible joint
+        tinv, jin, hmaps, masks, boxes_out = [], [], [], [], []
+        for i in range(n):
+            kp = ref_loader.run_train_transform(ref, smp["boxes"][i].tolist(), int(smp["img_w"][i]), 480,
+                                                smp["joints"][i].numpy(), float(smp["scale_ratio"][i]),
+                                                float(smp["rot"][i]), bool(smp["flip"][i]), PAIRS, inp, outp)
+            tinv.append(kp.trans_inv); jin.append(kp.joints); masks.append(kp.mask)
+            if i < keep_maps:                                                    # maps of the first few only (size)
+                hmaps.append(kp.heat_map)
+            boxes_out.append(np.array(kp.box, dtype=np.float32))
+        out.update({"img_w_" + tag: smp["img_w"].numpy(), "boxes_" + tag: smp["boxes"].numpy(),
+                    "joints_" + tag: smp["joints"].numpy(), "scale_ratio_" + tag: smp["scale_ratio"].numpy(),
+                    "rot_" + tag: smp["rot"].numpy(), "flip_" + tag: smp["flip"].numpy(),
+                    "tinv64_" + tag: np.stack(tinv), "joints_input_" + tag: np.stack(jin),
+                    "heat_map_" + tag: np.stack(hmaps), "mask_" + tag: np.stack(masks),
+                    "box_out_" + tag: np.stack(boxes_out), "shapes_" + tag: np.array([inp, outp], dtype=np.int32)})
+    np.savez_compressed(os.path.join(GOLDEN, "train_geom.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_loader.load()
     torch.manual_seed(0)
     affine_fixtures(ref)
+    train_geometry_fixtures(ref)
     if "--only-affine" in sys.argv:
         return
 

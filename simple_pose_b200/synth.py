@@ -190,3 +190,33 @@ def detection_boxes(persons, seed=0, ratio_exact_every=0, ratio=0.75):
         h[::ratio_exact_every] = torch.floor(h[::ratio_exact_every] / 4.0) * 4.0
         w[::ratio_exact_every] = h[::ratio_exact_every] * ratio
     return torch.stack([x, y, x + w, y + h], dim=1)
+
+
+def train_samples(persons, num_joints=17, seed=0, img_w=(200, 640), img_h=(200, 480), vis_p=0.8,
+                  scale=(0.7, 1.3), rot=(-40.0, 40.0), flip_p=0.5):
+    """Inputs of the train-side transform (``RefineSimpleTransform.__call__``, commons/transforms.py:
+    193-223) after its random draws: per person an image width, a ground-truth box inside the image
+    (float64 [x1, y1, x2, y2]), image-pixel joints [K,3] float32 (x, y, vis in {0,1}; most inside the
+    box, some outside so that the encoder's cull test fires), and the three draws of :204-211 --
+    ``scale_ratio`` ~ U(scale), ``rot`` ~ U(rot) degrees (every 8th exactly 0), ``flip`` ~ B(flip_p).
+    Returns a dict of CPU tensors."""
+    g = _gen(seed + 49979687, "cpu")
+    u = torch.rand(persons, 8, generator=g, dtype=torch.float64)
+    w_img = torch.floor(img_w[0] + (img_w[1] - img_w[0]) * u[:, 0])
+    h_img = torch.floor(img_h[0] + (img_h[1] - img_h[0]) * u[:, 1])
+    bw = 20.0 + (w_img - 24.0) * u[:, 2]
+    bh = 30.0 + (h_img - 34.0) * u[:, 3]
+    x1 = (w_img - bw - 1.0).clamp(min=0.0) * u[:, 4]
+    y1 = (h_img - bh - 1.0).clamp(min=0.0) * u[:, 5]
+    boxes = torch.stack([x1, y1, x1 + bw, y1 + bh], dim=1)
+    ju = torch.rand(persons, num_joints, 3, generator=g, dtype=torch.float64)
+    jx = x1[:, None] + bw[:, None] * (1.5 * ju[..., 0] - 0.25)
+    jy = y1[:, None] + bh[:, None] * (1.5 * ju[..., 1] - 0.25)
+    vis = (ju[..., 2] < vis_p).to(torch.float64)
+    joints_img = torch.stack([jx, jy, vis], dim=-1).to(torch.float32)
+    scale_ratio = scale[0] + (scale[1] - scale[0]) * u[:, 6]
+    rot_deg = rot[0] + (rot[1] - rot[0]) * u[:, 7]
+    rot_deg[::8] = 0.0
+    flip = torch.rand(persons, generator=g, dtype=torch.float64) < flip_p
+    return {"img_w": w_img.to(torch.int32), "boxes": boxes, "joints": joints_img,
+            "scale_ratio": scale_ratio, "rot": rot_deg, "flip": flip}

@@ -95,3 +95,25 @@ def test_box_affines(ref, inp, outp):
         assert np.array_equal(bits(c[i]), bits(rc)) and np.array_equal(bits(s[i]), bits(rs))
         assert np.float32(rs[0] * rs[1]) == a[i]
         assert np.array_equal(bits(tinv[i]), bits(torch.from_numpy(rti).float().numpy()))
+
+
+@pytest.mark.parametrize("inp,outp", [((192, 256), (48, 64)), ((288, 384), (72, 96))])
+def test_train_geometry(ref, inp, outp):
+    """RefineSimpleTransform.__call__ itself (commons/transforms.py:193-223), random draws scripted,
+    against the oracle's restatement of its joint/affine/target half: bit equality."""
+    smp = synth.train_samples(120, seed=303)
+    for i in range(120):
+        args = (smp["boxes"][i].tolist(), int(smp["img_w"][i]))
+        draws = (float(smp["scale_ratio"][i]), float(smp["rot"][i]), bool(smp["flip"][i]))
+        kp = ref_loader.run_train_transform(ref, args[0], args[1], 480, smp["joints"][i].numpy(), *draws,
+                                            O.COCO_JOINT_PAIRS, inp, outp)
+        o = O.train_sample_geometry(args[0], args[1], smp["joints"][i].numpy(), *draws, input_shape=inp, output_shape=outp)
+        assert np.array_equal(bits(kp.trans_inv), bits(o["trans_inv"])), i
+        assert np.array_equal(bits(kp.joints), bits(o["joints_input"])), i
+        assert np.array_equal(bits(kp.heat_map), bits(o["heat_map"])) and np.array_equal(kp.mask, o["mask"]), i
+        rt, rti = ref.get_affine_transform(o["center"], o["scale"], draws[1], outp)
+        assert np.array_equal(bits(rt), bits(o["joint_trans"])) and np.array_equal(bits(rti), bits(o["trans_inv"]))
+        fj = ref.flip_joints(np.zeros((4, args[1], 3), np.uint8), smp["joints"][i].numpy(), [list(p) for p in O.COCO_JOINT_PAIRS])[1]
+        assert np.array_equal(bits(fj), bits(O.flip_joints_only(smp["joints"][i].numpy(), args[1])))
+        aj = ref.joint_utils.affine_transform_batch(smp["joints"][i].numpy(), rt)
+        assert np.array_equal(bits(aj), bits(O.affine_joints(smp["joints"][i].numpy(), rt)))
