@@ -202,6 +202,46 @@ int sp_center_scale_affine_f64(const float* center, const float* scale, float* t
                                double* trans_inv_f64, double* trans_f64, int P, int out_w, int out_h,
                                void* stream);
 
+/* get_affine_transform(center, scale, rot, (out_w, out_h)) with a rotation (commons/joint_utils.py:115-152;
+ * the train-side call, commons/transforms.py:212-213). rot_deg [P] f64 degrees (NULL = all zero). */
+int sp_center_scale_rot_affine_f64(const float* center, const float* scale, const double* rot_deg,
+                                   float* trans_inv, double* trans_inv_f64, double* trans_f64, int P,
+                                   int out_w, int out_h, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Train-side caller of the encoder: RefineSimpleTransform.__call__ (commons/transforms.py:193-223)
+ * without the image work (cv.warpAffine, np.fliplr), its random draws passed in:
+ *   box_to_center_scale (:200-201) -> scale * scale_ratio (:202-203, float32) -> flip_joints +
+ *   centre mirror (:207-210; commons/joint_utils.py:102-112) -> get_affine_transform for the input
+ *   and heatmap sizes (:212-213) -> affine_transform_batch (:217-218; joint_utils.py:88-99).
+ * The result joints_hm feeds sp_encode_f32 / sp_encode_mse_fwd_bwd_f32 (:219).
+ *
+ * boxes        [P,4] f64  (x1, y1, x2, y2) AFTER box_crop
+ * img_w        [P] i32    image widths (needed when flip != NULL)
+ * joints       [P,K,3] f32 (x, y, vis) in image pixels
+ * scale_ratio  [P] f64    draw of :202 (NULL = 1); rot_deg [P] f64 draw of :204 (NULL = 0)
+ * flip         [P] u8     draw of :208 (NULL = never); perm [K] i32 with flipped[k] = original[perm[k]]
+ * joints_hm    [P,K,3] f32 out  heatmap-pixel joints (rows with vis <= 0 are not mapped, as in the reference)
+ * joints_input [P,K,3] f32 out  joint_info.joints, network-input pixels (nullable)
+ * trans_inv    [P,2,3] f32 out  joint_info.trans_inv as collate_fn ships it (nullable)
+ * trans_inv_f64, img_trans_f64 [P,2,3] f64 out: unrounded trans_inv; the image-warp matrix (nullable)
+ * center, scale [P,2] f32 out after augmentation (center_scale_to_box of :220 follows from them) (nullable)
+ * Same roundings as NumPy >= 2 / OpenCV; the only non-identical step is sin/cos of the rotation
+ * (CUDA vs NumPy may differ in the last float64 bit, which the float32 rounding of the triangle
+ * points absorbs except with probability ~1e-8).
+ */
+int sp_train_geometry_f32(const double* boxes, const int* img_w, const float* joints,
+                          const double* scale_ratio, const double* rot_deg, const unsigned char* flip,
+                          const int* perm, float* joints_hm, float* joints_input, float* trans_inv,
+                          double* trans_inv_f64, double* img_trans_f64, float* center, float* scale, int P,
+                          int K, int in_w, int in_h, int out_w, int out_h, float scale_mult, void* stream);
+
+/* flip_joints (joint half, commons/joint_utils.py:102-112) and/or affine_transform_batch (:88-99) on
+ * [P,K,3] f32 joints: flip [P] u8 + img_w [P] i32 + perm [K] i32 (all NULL = no flip), then
+ * trans [P,2,3] f64 (NULL = no affine) applied to rows with vis > 0. out != joints. */
+int sp_transform_joints_f32(const float* joints, const double* trans, const unsigned char* flip,
+                            const int* img_w, const int* perm, float* out, int P, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

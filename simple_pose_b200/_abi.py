@@ -46,6 +46,9 @@ SIGNATURES = {
     "sp_pack_kps_f64": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void]),
     "sp_box_affine_f64": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_dbl, c_int, c_int, c_flt, c_void]),
     "sp_center_scale_affine_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_void]),
+    "sp_center_scale_rot_affine_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_void]),
+    "sp_train_geometry_f32": (c_int, [c_void] * 14 + [c_int, c_int, c_int, c_int, c_int, c_int, c_flt, c_void]),
+    "sp_transform_joints_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_void]),
 }
 
 _lock = threading.Lock()

@@ -568,7 +568,7 @@ def test_box_affines_golden_and_oracle(api, golden):
     fwd, inv = ju.get_affine_transforms(g["center_b"], g["scale_b"], (72, 96))
     assert np.array_equal(bits(fwd.cpu().numpy()), bits(g["fwd64_b"])) and np.array_equal(bits(inv.cpu().numpy()), bits(g["tinv64_b"]))
     with pytest.raises(NotImplementedError):
-        ju.get_affine_transform(c, s, 30, outp)
+        ju.get_affine_transform(c, s, 0, outp, shift=np.array([0.1, 0.0], dtype=np.float32))
 
 
 def test_boxes_to_keypoints_device_resident(api):
@@ -820,3 +820,120 @@ def test_decode_work_distribution_covers_every_map(api, b, k):
     assert torch.equal(got[2], want[2]) and torch.equal(got[1], want[1])
     assert (got[0] - want[0]).abs().max().item() <= 1e-5
     assert torch.equal(got[2].long().cpu(), O.argmax_index(hm.cpu()))
+
+
+# ------------------------------------------------------------------------------------ train-side caller of the encoder
+def _oracle_train_geometry(smp, inp, outp, n=None):
+    n = smp["boxes"].shape[0] if n is None else n
+    return [O.train_sample_geometry(smp["boxes"][i].tolist(), int(smp["img_w"][i]), np.asarray(smp["joints"][i]),
+                                    float(smp["scale_ratio"][i]), float(smp["rot"][i]), bool(smp["flip"][i]),
+                                    input_shape=inp, output_shape=outp) for i in range(n)]
+
+
+def _assert_joints_close(got, want):
+    """float32 joints: at most 1 ulp apart and all but a vanishing fraction identical (the float64 dot
+    is FMA-ordered on both sides; a last-bit float64 difference flips a float32 rounding ~1e-8 of the time)."""
+    d = ulp_diff(got, want)
+    assert d.max() <= 1 and (d != 0).mean() < 1e-4, (d.max(), (d != 0).mean())
+
+
+def test_train_geometry_golden(api, golden):
+    """sp_train_geometry_f32 + sp_encode_f32 against the frozen products of the reference's own
+    RefineSimpleTransform.__call__ (scripted draws): trans_inv float64 bit-identical (rot = 0) or within
+    the sin/cos last-bit allowance, input-pixel joints, masks, heat maps."""
+    g = golden("train_geom")
+    for tag in ("a", "b"):
+        inp, outp = [tuple(int(v) for v in r) for r in g["shapes_" + tag]]
+        args = (g["boxes_" + tag], g["joints_" + tag], g["img_w_" + tag], g["scale_ratio_" + tag], g["rot_" + tag],
+                g["flip_" + tag].astype(np.uint8))
+        geo = api.transforms.train_geometry(*args, input_shape=inp, output_shape=outp, want_input=True)
+        tinv = geo["trans_inv_f64"].cpu().numpy()
+        same = np.array([np.array_equal(bits(tinv[i]), bits(g["tinv64_" + tag][i])) for i in range(tinv.shape[0])])
+        assert same[g["rot_" + tag] == 0].all()
+        assert same.mean() >= 0.9 and np.allclose(tinv, g["tinv64_" + tag], rtol=1e-6, atol=1e-6)
+        assert np.array_equal(bits(geo["trans_inv"].cpu().numpy()[same]), bits(g["tinv64_" + tag].astype(np.float32)[same]))
+        _assert_joints_close(geo["joints_input"].cpu().numpy()[same], g["joints_input_" + tag][same])
+        heat_maps, masks, tinv32 = api.transforms.train_targets(*args, input_shape=inp, output_shape=outp)
+        assert np.array_equal(masks.cpu().numpy()[same], g["mask_" + tag][same])
+        assert torch.equal(tinv32, geo["trans_inv"])
+        orc = _oracle_train_geometry({k: g[k + "_" + tag] for k in ("boxes", "img_w", "joints", "scale_ratio", "rot", "flip")},
+                                     inp, outp, n=g["heat_map_" + tag].shape[0])
+        for i, o in enumerate(orc):
+            assert np.array_equal(bits(o["heat_map"]), bits(g["heat_map_" + tag][i]))         # the oracle is pinned ...
+            if np.array_equal(bits(geo["joints_hm"][i].cpu().numpy()), bits(o["joints_hm"])):  # ... and so is the kernel
+                assert_targets_match(heat_maps[i].cpu().numpy(), g["heat_map_" + tag][i])
+            else:
+                assert (not same[i]) or ulp_diff(geo["joints_hm"][i].cpu().numpy(), o["joints_hm"]).max() <= 1
+
+
+@pytest.mark.parametrize("inp,outp", [((192, 256), (48, 64)), ((288, 384), (72, 96))])
+def test_train_geometry_vs_oracle(api, inp, outp):
+    n = 1500
+    smp = synth.train_samples(n, seed=404)
+    orc = _oracle_train_geometry(smp, inp, outp)
+    geo = api.transforms.train_geometry(smp["boxes"], smp["joints"], smp["img_w"], smp["scale_ratio"], smp["rot"],
+                                        smp["flip"], input_shape=inp, output_shape=outp, want_input=True)
+    torch.cuda.synchronize()
+    tinv = geo["trans_inv_f64"].cpu().numpy()
+    fwd_in = geo["img_trans_f64"].cpu().numpy()
+    same = np.array([np.array_equal(bits(tinv[i]), bits(orc[i]["trans_inv"])) and
+                     np.array_equal(bits(fwd_in[i]), bits(orc[i]["img_trans"])) for i in range(n)])
+    assert same.mean() >= 0.999, "persons with a non-identical float64 affine: %d of %d" % ((~same).sum(), n)
+    assert np.allclose(tinv, np.stack([o["trans_inv"] for o in orc]), rtol=1e-6, atol=1e-6)
+    for key in ("center", "scale"):
+        assert np.array_equal(bits(geo[key].cpu().numpy()), bits(np.stack([o[key] for o in orc]))), key
+    _assert_joints_close(geo["joints_hm"].cpu().numpy()[same], np.stack([o["joints_hm"] for o in orc])[same])
+    _assert_joints_close(geo["joints_input"].cpu().numpy()[same], np.stack([o["joints_input"] for o in orc])[same])
+    # the composed product the solvers consume: masks exact, maps as the encoder's gate
+    heat_maps, masks, _ = api.transforms.train_targets(smp["boxes"][:96], smp["joints"][:96], smp["img_w"][:96],
+                                                       smp["scale_ratio"][:96], smp["rot"][:96], smp["flip"][:96],
+                                                       input_shape=inp, output_shape=outp)
+    jh = geo["joints_hm"].cpu().numpy()
+    for i in range(96):
+        if np.array_equal(bits(jh[i]), bits(orc[i]["joints_hm"])):
+            assert np.array_equal(masks[i].cpu().numpy(), orc[i]["mask"])
+            assert_targets_match(heat_maps[i].cpu().numpy(), orc[i]["heat_map"])
+    assert 0 < masks.sum().item() < masks.numel()
+
+
+def test_train_geometry_drop_ins_and_edges(api):
+    """Per-sample drop-ins of commons/joint_utils.py (flip_joints, affine_transform_batch,
+    get_affine_transform with a rotation) and the degenerate batches."""
+    from simple_pose_b200.commons import joint_utils as ju
+    smp = synth.train_samples(12, seed=505)
+    pairs = [list(p) for p in O.COCO_JOINT_PAIRS]
+    for i in range(12):
+        j = smp["joints"][i].numpy()
+        w = int(smp["img_w"][i])
+        img = np.arange(2 * w * 3, dtype=np.uint8).reshape(2, w, 3)
+        fimg, fj = ju.flip_joints(img, j, pairs)
+        assert np.array_equal(fimg, img[:, ::-1]) and np.array_equal(bits(fj), bits(O.flip_joints_only(j, w)))
+        o = O.train_sample_geometry(smp["boxes"][i].tolist(), w, j, float(smp["scale_ratio"][i]), float(smp["rot"][i]), False)
+        fwd, inv = ju.get_affine_transform(o["center"], o["scale"], float(smp["rot"][i]), (48, 64))
+        assert np.allclose(fwd, o["joint_trans"], rtol=1e-12, atol=1e-12) and np.allclose(inv, o["trans_inv"], rtol=1e-12, atol=1e-12)
+        aj = ju.affine_transform_batch(j, o["joint_trans"])
+        assert aj.dtype == np.float32
+        _assert_joints_close(aj, O.affine_joints(j, o["joint_trans"]))
+    # no flip / no rotation / no scale draw == the eval-side transform, bit for bit
+    boxes = synth.detection_boxes(300, seed=606)
+    j = synth.train_samples(300, seed=606)["joints"]
+    geo = api.transforms.train_geometry(boxes, j)
+    ref = api.naive.box_affines(boxes.to(DEV), want_f64=True)
+    assert torch.equal(geo["trans_inv_f64"], ref["trans_inv_f64"]) and torch.equal(geo["center"], ref["center"])
+    assert torch.equal(geo["scale"], ref["scale"])
+    # invisible rows are never mapped; K = 1; empty batch
+    j1 = torch.tensor([[[5.0, 6.0, 0.0]], [[5.0, 6.0, 1.0]]])
+    g1 = api.transforms.train_geometry(boxes[:2], j1)
+    assert g1["joints_hm"][0].cpu().tolist() == [[5.0, 6.0, 0.0]] and g1["joints_hm"][1, 0, 2].item() == 1.0
+    assert g1["joints_hm"][1, 0, 0].item() != 5.0
+    empty = api.transforms.train_geometry(np.zeros((0, 4)), np.zeros((0, 17, 3), dtype=np.float32))
+    assert empty["joints_hm"].shape == (0, 17, 3) and empty["trans_inv"].shape == (0, 2, 3)
+    with pytest.raises(ValueError):
+        api.transforms.train_geometry(boxes[:2], j1, flip=[1, 0])
+    lib = api.abi.lib()
+    d = torch.zeros(64, device=DEV, dtype=torch.float64)
+    f = torch.zeros(64, device=DEV)
+    u8 = torch.ones(8, device=DEV, dtype=torch.uint8)
+    assert lib.sp_train_geometry_f32(d.data_ptr(), None, f.data_ptr(), None, None, u8.data_ptr(), None, f.data_ptr(), None,
+                                     None, None, None, None, None, 1, 1, 192, 256, 48, 64, 1.25, None) == -1
+    assert lib.sp_transform_joints_f32(f.data_ptr(), None, None, None, None, f.data_ptr(), 1, 1, None) == -1
