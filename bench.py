@@ -342,6 +342,44 @@ def time_ops(device, height, width, persons, batch, peak_gbs):
     return out
 
 
+def train_side_numbers(device, persons=8192, reps=20, cpu_sample=256):
+    """Train-side caller of the encoder (RefineSimpleTransform.__call__ minus the image work): boxes +
+    image-pixel joints + augmentation draws -> heatmap-pixel joints + trans_inv in one launch
+    (latency-bound, 240 B in / 280 B out per person: persons/s only), next to the oracle port on one core."""
+    import numpy as np
+    from simple_pose_b200 import synth
+    from simple_pose_b200.commons.transforms import train_geometry
+    smp = {k: v.to(device) for k, v in synth.train_samples(persons, seed=77).items()}
+    args = (smp["boxes"], smp["joints"], smp["img_w"], smp["scale_ratio"], smp["rot"], smp["flip"].to(torch.uint8))
+    for _ in range(3):
+        train_geometry(*args)
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        train_geometry(*args)
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / reps
+    from oracle import heatmap_oracle as O          # CPU baseline leg only
+    cpu = synth.train_samples(cpu_sample, seed=77)
+    t0 = time.perf_counter()
+    for i in range(cpu_sample):
+        box, w = cpu["boxes"][i].tolist(), int(cpu["img_w"][i])
+        c, sc = O.box_center_scale(box[0], box[1], box[2] - box[0], box[3] - box[1], 0.75)
+        sc = sc * np.float32(float(cpu["scale_ratio"][i]))
+        j = cpu["joints"][i].numpy()
+        if bool(cpu["flip"][i]):
+            j = O.flip_joints_only(j, w)
+        fwd, _ = O.affine_pair(c, sc, (48, 64), float(cpu["rot"][i]))
+        O.affine_joints(j, fwd)
+    cpu_s = time.perf_counter() - t0
+    return {"persons": persons, "ms_per_launch": ms, "persons_per_s": persons / (ms * 1e-3), "launches": 1,
+            "cpu_port_persons_per_s": cpu_sample / cpu_s, "cpu_cores": 1,
+            "note": "sp_train_geometry_f32 (Python call included); CPU = oracle restatement of box_to_center_scale + "
+                    "flip_joints + get_affine_transform(rot) + affine_transform_batch on %d persons" % cpu_sample}
+
+
 def small_batch_numbers(device, height, width, batch=128, nbatch=64):
     """The literal cfg-1/cfg-2 shape (batch 128 = 26.7 MB per tensor, launch-latency bound): the step
     replayed as ONE CUDA graph over `nbatch` distinct buffer sets (working set >> L2), plus the
@@ -592,9 +630,10 @@ def run_ours(args):
         ops = {"64x48": time_ops(device, 64, 48, 8192, 1024, peak_gbs),
                "96x72": time_ops(device, 96, 72, 4096, 512, peak_gbs)}
 
-    small = None
+    small = train_side = None
     if rank == 0 and world == 1 and not args.no_ops:
         small = small_batch_numbers(device, H, W)
+        train_side = train_side_numbers(device)
 
     eval_job = None
     if not args.no_ops:
@@ -632,6 +671,7 @@ def run_ours(args):
                    "parallelism": "persons sharded, dp%d" % world, "e2e_host_binding": numa["text"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
         "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small, "eval_job": eval_job, "fused_step": fused,
+        "train_side": train_side,
     }
     print(json.dumps(line), flush=True)
 

@@ -3,10 +3,13 @@
 //
 // Latency-bound, not bandwidth-bound (408 B per person). One CTA owns one image (segment):
 // persons are ranked by descending score with a counting rank (stable; ties -> higher index
-// first, i.e. argsort()[::-1] of a stable sort), then the greedy loop visits them in that
-// order; for each surviving pick the remaining candidates are scored in parallel, one thread
-// per candidate. The per-pair arithmetic keeps the reference's operation order, including
-// NumPy's 8-accumulator pairwise summation, so that the `oks > thresh` decisions agree.
+// first, i.e. argsort()[::-1] of a stable sort). Images of up to 64 persons (every COCO image)
+// then score all n(n-1)/2 ordered pairs at once, one thread per pair, into 64-bit suppression
+// rows, and the greedy pass is n bit operations (cfg 5, 4952 images / 104 k persons: 0.26 ms
+// instead of 1.09 ms). Larger images run the greedy loop itself: for each surviving pick the
+// remaining candidates are scored in parallel, one thread per candidate. The per-pair arithmetic
+// keeps the reference's operation order, including NumPy's 8-accumulator pairwise summation,
+// so that the `oks > thresh` decisions agree.
 #include "sp_common.cuh"
 
 namespace {
@@ -106,7 +109,7 @@ oks_iou_kernel(const double* __restrict__ pick_kps, const double* __restrict__ c
 __global__ void __launch_bounds__(kNmsThreads)
 oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores, const double* __restrict__ areas,
                const int* __restrict__ seg, unsigned char* __restrict__ keep, int* __restrict__ rank,
-               int max_seg, double thresh, OksParams P) {
+               int max_seg, double thresh, OksParams P, int force_serial) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     int* order = reinterpret_cast<int*>(nms_smem);
     unsigned char* alive = nms_smem + (size_t)max_seg * sizeof(int);
@@ -131,6 +134,40 @@ oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores
     __syncthreads();
 
     const size_t stride = (size_t)3 * P.K;
+    if (n <= 64 && !force_serial) {
+        // Small image (the COCO case: ~20 boxes): score ALL n(n-1)/2 (earlier, later) pairs of the
+        // visiting order at once, one thread per pair, into 64-bit suppression rows; the greedy pass
+        // is then n bit operations. Same decisions as the loop below (oks_pair is evaluated with the
+        // earlier person as the pick, exactly as the loop would), but one exp-chain deep instead of
+        // one per surviving pick.
+        unsigned long long* rows = reinterpret_cast<unsigned long long*>(nms_smem + (((size_t)max_seg * 5 + 15) & ~(size_t)15));
+        for (int i = tid; i < n; i += kNmsThreads) rows[i] = 0ull;
+        __syncthreads();
+        const int total = n * (n - 1) / 2;
+        for (int idx = tid; idx < total; idx += kNmsThreads) {
+            // row p of the strict upper triangle starts at S(p) = p*n - p*(p+1)/2
+            const float b = (float)(2 * n - 1);
+            int p = (int)((b - sqrtf(fmaxf(b * b - 8.0f * (float)idx, 0.0f))) * 0.5f);
+            p = min(max(p, 0), n - 2);
+            while (p + 1 <= n - 2 && (p + 1) * n - (p + 1) * (p + 2) / 2 <= idx) ++p;
+            while (p > 0 && p * n - p * (p + 1) / 2 > idx) --p;
+            const int c = p + 1 + (idx - (p * n - p * (p + 1) / 2));
+            const int i = order[p], j = order[c];
+            const double oks = oks_pair(P, kps + (size_t)(lo + i) * stride, kps + (size_t)(lo + j) * stride,
+                                        areas[lo + i], areas[lo + j]);
+            if (oks > thresh) atomicOr(&rows[p], 1ull << c);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long alive_bits = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
+            for (int p = 0; p < n; ++p) {
+                if (!((alive_bits >> p) & 1ull)) continue;
+                keep[lo + order[p]] = 1;
+                alive_bits &= ~rows[p];
+            }
+        }
+        return;
+    }
     for (int p = 0; p < n; ++p) {
         if (!alive[p]) continue;                       // uniform: everyone reads the same byte
         const int i = order[p];
@@ -201,12 +238,14 @@ extern "C" int sp_oks_nms_f64(const double* kps, const double* scores, const dou
     SP_RETURN_IF(N < 0 || I < 0 || K <= 0 || K > kMaxJoints || max_seg < 0, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
     if (N == 0 || I == 0) return 0;
-    const size_t smem = (size_t)max_seg * (sizeof(int) + 1) + 16;
+    // order[max_seg] int + alive[max_seg] bytes, then (16-byte aligned) 64 suppression rows for small images
+    const size_t smem = (((size_t)max_seg * (sizeof(int) + 1) + 15) & ~(size_t)15) + 64 * sizeof(unsigned long long);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     if (smem > 48 * 1024)
         SP_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OksParams P{sigmas, K, use_vis_thresh ? 1 : 0, vis_thresh};
-    oks_nms_kernel<<<I, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(kps, scores, areas, seg, keep, rank, max_seg, thresh, P);
+    oks_nms_kernel<<<I, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(kps, scores, areas, seg, keep, rank, max_seg, thresh, P,
+                                                                                sp_env_int("SP_NMS_SERIAL", 0));
     return sp_launch_status();
 }
 

@@ -399,6 +399,35 @@ def test_oks_nms_vs_oracle_large(api):
         assert order == o_picks[s]
 
 
+@pytest.mark.parametrize("mean_group", [3.0, 30.0, 62.0, 90.0])
+def test_oks_nms_pair_matrix_path_equals_greedy_loop(api, mean_group):
+    """Images of up to 64 persons take the all-pairs bit-matrix path, larger ones the per-pick loop;
+    SP_NMS_SERIAL=1 forces the loop everywhere. Keep sets, ranks and the oracle agree, with a score
+    tie (visiting order = descending index) and segments of exactly 1, 2, 63, 64 and 65 persons."""
+    kps, box, area, seg = synth.nms_groups(60, mean_group=mean_group, seed=int(mean_group))
+    n = kps.shape[0]
+    box[2] = box[1]                                             # a score tie inside the 2-person image (NumPy's argsort is
+                                                                # only order-stable for such small inputs: insertion sort)
+    cuts = sorted(set([0, 1, 3, 66, 130, 195] + [int(v) for v in seg.tolist() if v > 195] + [n]))
+    cuts = [c for c in cuts if c <= n]
+    seg2 = np.array(cuts, dtype=np.int32)
+    keep, rank = api.naive.oks_nms_batched(kps, box, area, seg2, 0.9)
+    os.environ["SP_NMS_SERIAL"] = "1"
+    try:
+        keep_s, rank_s = api.naive.oks_nms_batched(kps, box, area, seg2, 0.9)
+    finally:
+        del os.environ["SP_NMS_SERIAL"]
+    assert torch.equal(keep, keep_s) and torch.equal(rank, rank_s)
+    sizes = np.diff(seg2)
+    assert sizes.min() <= 2 and (sizes == 63).any() and (sizes == 64).any() and (sizes == 65).any()
+    keep_np = keep.cpu().numpy().astype(bool)
+    for s_i in range(len(seg2) - 1):
+        lo, hi = int(seg2[s_i]), int(seg2[s_i + 1])
+        o = O.oks_greedy_nms(kps.numpy()[lo:hi], box.numpy()[lo:hi], area.numpy()[lo:hi], 0.9)
+        assert sorted(int(i) + lo for i in o) == [int(i) for i in np.nonzero(keep_np)[0] if lo <= i < hi], s_i
+    assert 0 < keep_np.sum() < n
+
+
 def test_oks_nms_edge_cases(api):
     kps, box, area, seg = synth.nms_groups(3, mean_group=5.0, seed=2)
     # empty segment in the middle, single-person image, and one big image
