@@ -10,7 +10,8 @@ constexpr int kMaxPartials = 4096;
 
 struct MseWorkspace {
     unsigned int ticket;          // blocks finished so far (returns to 0 at the end of a call)
-    unsigned int pad[3];
+    unsigned int next_work;       // grid-wide work counter of kernels that deal work dynamically (returns to 0 likewise)
+    unsigned int pad[2];
     double partial[kMaxPartials];
 };
 
@@ -47,6 +48,7 @@ __device__ __forceinline__ void finish_loss(double block_sum, MseWorkspace* __re
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_part[w];
         *loss = (float)(0.5 * tot * inv_count);
         ws->ticket = 0u;      // restore the zero state for the next call on this stream
+        ws->next_work = 0u;
     }
 }
 

@@ -18,6 +18,21 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#ifdef SP_TRAIN_TRACE
+// scratch instrumentation (never compiled into the product library): per-warp timestamps of the
+// period-tiled kernel, 8 x int64 per warp: [globaltimer at entry, after griddepcontrol.wait, first
+// chunk landed, last map done, after the loss reduction, maps processed, clock64 span of the map loop, 0]
+__device__ long long* g_trace_ptr = nullptr;
+extern "C" int sp_debug_set_trace(void* p) {
+    return (int)cudaMemcpyToSymbol(g_trace_ptr, &p, sizeof(p));
+}
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 namespace {
 
 using namespace sp_gauss;
@@ -463,16 +478,30 @@ struct TileRing {
     int left;                    // chunks of the current map still to request (0: no map)
     int pnext;                   // map claimed after the current one (-1: none)
     uint32_t ps;
-    int tail, range_hi;
+    int tail, nmaps;
+    int inflight, depth;         // copies in flight / copies kept in flight while there are unclaimed maps
+    int static_next, static_left, static_stride, dyn_base;
     volatile int* fifo;
-    int* next_map;
+    unsigned int* next_work;     // grid-wide counter in the caller's workspace
     const char* pred;
     size_t map_bytes;
     int chunks_per_map;
 
+    // Maps are dealt GRID-WIDE: the first two of every warp are fixed (no atomic storm at launch), the
+    // rest come from one counter in the caller's workspace, one map ahead of the copies being issued.
+    // A per-CTA range would make the slowest SM the critical path, and the SMs are far from equal once
+    // the memory system queues: at 96x72 half the TPCs finished equal ranges in ~58 us and the other
+    // half in ~86 us (per-warp timestamps, profiles/r1f_fused_timeline.md).
     __device__ __forceinline__ int claim() {
-        const int m = atomicAdd(next_map, 1);
-        const int got = (m < range_hi) ? m : -1;
+        int m;
+        if (static_left > 0) {
+            m = static_next;
+            static_next += static_stride;
+            --static_left;
+        } else {
+            m = dyn_base + (int)atomicAdd(next_work, 1u);
+        }
+        const int got = (m >= 0 && m < nmaps) ? m : -1;
         fifo[tail & (kFifo - 1)] = got;
         ++tail;
         return got;
@@ -493,12 +522,21 @@ struct TileRing {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(src), "n"(CHUNK_BYTES), "r"(bar) : "memory");
         src += CHUNK_BYTES;
+        ++inflight;
         if (--left == 0 && pnext >= 0) {
             src = pred + (size_t)pnext * map_bytes;
             left = chunks_per_map;
             pnext = claim();
         }
         if (RING > 1) ps = (ps + 1 == RING) ? 0u : ps + 1;
+    }
+    // Keep `depth` copies in flight while the CTA has maps left to hand out; once this warp is on its
+    // last map (nothing claimed behind it) use every slot: the SM's other warps are running dry, a
+    // lone warp at depth 1 pulls ~1.3 KB/us of the SM's 22 KB/us, and the deeper ring that is slower
+    // under full load (HBM read/write turnarounds) is what shortens the launch tail.
+    __device__ __forceinline__ void top_up() {               // lane 0
+        const int want = (pnext < 0) ? RING : depth;
+        while (inflight < want && left > 0) issue_next();
     }
     __device__ __forceinline__ uint32_t wait() {             // returns the shared address of the chunk
         const uint32_t bar = bar0 + cs * 8u;
@@ -510,7 +548,8 @@ struct TileRing {
         __syncwarp();
         if (lane == 0) {
             sp::fence_proxy_async_smem();
-            issue_next();                                    // refills the slot just drained
+            --inflight;
+            top_up();                                        // refills the slot just drained (and more in the tail)
         }
         if (RING > 1) {
             if (++cs == RING) { cs = 0; parity ^= 1u; }
@@ -694,16 +733,19 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
 // dynamic smem: same layout as variant B
 template <int QPR, int PPC, int RING, bool ACC>
 __global__ void __launch_bounds__(512, 1)
-encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count, int nwarps) {
+encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count, int nwarps,
+                       int depth) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int CHUNK_BYTES = PPC * 32 * Tile<QPR>::PERIOD * 16;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+#ifdef SP_TRAIN_TRACE
+    long long tr[8] = {gtime(), 0, 0, 0, 0, 0, 0, 0};
+#endif
     const int hw = io.H * io.W;
     const int wpad = (io.W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
     volatile int* fifo = reinterpret_cast<int*>(smem_raw + 1024) + warp * kFifo;
-    int* next_map = reinterpret_cast<int*>(smem_raw + 1024 + 2048);
     double* ex = reinterpret_cast<double*>(smem_raw + kRingHeader + warp * fac_bytes);
     double* ey = ex + wpad;
     TileRing<RING, CHUNK_BYTES> rg;
@@ -711,25 +753,36 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     rg.bar0 = base + (uint32_t)(warp * RING * 8);
     rg.slot0 = base + (uint32_t)(kRingHeader + (size_t)nwarps * fac_bytes + (size_t)warp * RING * CHUNK_BYTES);
     rg.cs = 0; rg.parity = 0; rg.ps = 0; rg.tail = 0; rg.left = 0; rg.pnext = -1; rg.src = nullptr;
-    rg.fifo = fifo; rg.next_map = next_map;
+    rg.inflight = 0; rg.depth = depth;
+    rg.fifo = fifo; rg.next_work = &ws->next_work;
+    rg.nmaps = io.nmaps;
+    rg.static_stride = (int)gridDim.x * nwarps;
+    rg.static_next = (int)blockIdx.x * nwarps + warp;
+    rg.static_left = 2;
+    rg.dyn_base = 2 * rg.static_stride;
     rg.pred = reinterpret_cast<const char*>(io.pred);
     rg.map_bytes = (size_t)hw * 4;
     rg.chunks_per_map = hw * 4 / CHUNK_BYTES;
-    const int range_lo = (int)((long long)blockIdx.x * io.nmaps / gridDim.x);
-    rg.range_hi = (int)((long long)(blockIdx.x + 1) * io.nmaps / gridDim.x);
-    if (threadIdx.x == 0) *next_map = range_lo;
     if (lane == 0) {
         for (int r = 0; r < RING; ++r) sp::mbar_init(reinterpret_cast<uint64_t*>(smem_raw) + warp * RING + r, 1);
         sp::mbar_fence_init();
     }
     __syncthreads();
     sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
+#ifdef SP_TRAIN_TRACE
+    tr[1] = gtime();
+#endif
 
     if (lane == 0) {
         rg.start(rg.claim());
-        for (int r = 0; r < RING; ++r) rg.issue_next();
+        rg.top_up();
     }
     __syncwarp();
+#ifdef SP_TRAIN_TRACE
+    if (fifo[0] >= 0) { while (!mbar_try_wait_a(rg.bar0, 0)) { } }
+    tr[2] = gtime();
+    const long long c0 = clock64();
+#endif
 
     double sum_sq = 0.0;
     PendingAxis pd;
@@ -755,7 +808,18 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         m = m_next;
     }
     if (ACC) flush_pending(io, pd, lane);
+#ifdef SP_TRAIN_TRACE
+    tr[3] = gtime(); tr[5] = head; tr[6] = clock64() - c0;
+    { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid; }
+#endif
     finish_loss<512>(sum_sq, ws, loss, inv_count);
+#ifdef SP_TRAIN_TRACE
+    tr[4] = gtime();
+    if (lane == 0 && g_trace_ptr) {
+        long long* t = g_trace_ptr + ((size_t)blockIdx.x * 16 + warp) * 8;
+        for (int i = 0; i < 8; ++i) t[i] = tr[i];
+    }
+#endif
 }
 
 // HeatMapAcc epilogue (metrics/pose_metrics.py:227-245) on the [B,K] argmax coordinates.
@@ -849,17 +913,27 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         const int cfg = sp_env_int("SP_TRAIN_TILE_CFG", 0);
         int ppc = 1, ring = 2;
         if (qpr == 12) {
-            if (cfg == 1) { ppc = 1; ring = 2; } else if (cfg == 2) { ppc = 2; ring = 2; } else if (cfg == 3) { ppc = 4; ring = 1; } else { ppc = 2; ring = 1; }
+            if (cfg == 1) { ppc = 1; ring = 2; } else if (cfg == 2) { ppc = 2; ring = 2; } else if (cfg == 3) { ppc = 4; ring = 1; }
+            else if (cfg == 4) { ppc = 2; ring = 3; } else if (cfg == 5) { ppc = 2; ring = 4; } else { ppc = 2; ring = 1; }
         } else {
-            if (cfg == 1) { ppc = 1; ring = 1; } else { ppc = 1; ring = 2; }
+            if (cfg == 1) { ppc = 1; ring = 1; } else if (cfg == 2) { ppc = 1; ring = 3; } else if (cfg == 3) { ppc = 1; ring = 4; } else { ppc = 1; ring = 2; }
         }
+        // copies kept in flight per warp in steady state (the whole ring is used once a warp is on its last map)
+        int depth = sp_env_int("SP_TRAIN_DEPTH", ring);
+        if (depth < 1) depth = 1;
+        if (depth > ring) depth = ring;
         const int periods = nq / (32 * period);
         if (H % rows == 0 && periods % ppc == 0) {
             const size_t chunk_bytes = (size_t)ppc * 32 * period * 16;
             const size_t budget = 226 * 1024 - kRingHeader;
             int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
             if (nwarps > 16) nwarps = 16;
-            { const int w = sp_env_int("SP_TRAIN_WARPS", 16); if (w < nwarps) nwarps = w; }
+            // 96x72 maps are 27 KB: with 16 warps a map takes ~20 us and the launch ends with a long,
+            // thin tail; 8 warps (74 KB in flight per SM) halve it (512 persons: 88 -> 83 us) once there
+            // are enough maps to keep the warps fed. Small launches keep 16 warps (more maps in flight).
+            int want_warps = (qpr == 18 && nmaps >= 2 * 16 * sp_sm_count()) ? 8 : 16;
+            want_warps = sp_env_int("SP_TRAIN_WARPS", want_warps);
+            if (want_warps < nwarps) nwarps = want_warps;
             if (nwarps >= 1) {
                 const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
                 int grid = sp_sm_count();
@@ -869,17 +943,19 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     do {                                                                                                                     \
         if (pred_xy) {                                                                                                       \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth)); \
         } else {                                                                                                             \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth)); \
         }                                                                                                                    \
     } while (0)
                 if (qpr == 12) {
                     if (ppc == 1) SP_LAUNCH_TILE(12, 1, 2); else if (ppc == 2 && ring == 2) SP_LAUNCH_TILE(12, 2, 2);
+                    else if (ppc == 2 && ring == 3) SP_LAUNCH_TILE(12, 2, 3); else if (ppc == 2 && ring == 4) SP_LAUNCH_TILE(12, 2, 4);
                     else if (ppc == 4) SP_LAUNCH_TILE(12, 4, 1); else SP_LAUNCH_TILE(12, 2, 1);
                 } else {
-                    if (ring == 1) SP_LAUNCH_TILE(18, 1, 1); else SP_LAUNCH_TILE(18, 1, 2);
+                    if (ring == 1) SP_LAUNCH_TILE(18, 1, 1); else if (ring == 3) SP_LAUNCH_TILE(18, 1, 3);
+                    else if (ring == 4) SP_LAUNCH_TILE(18, 1, 4); else SP_LAUNCH_TILE(18, 1, 2);
                 }
 #undef SP_LAUNCH_TILE
                 return sp_launch_status();
