@@ -140,6 +140,18 @@ int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
                   float* coords, float* maxval, int* argmax,
                   int B, int K, int H, int W, int ksize, int mode, void* stream);
 
+/* Same decoders, same results, with a scratch word the kernel deals its maps from GRID-WIDE (fast SMs
+ * take more maps than slow ones; sp_decode_f32 gives every SM an equal range instead). workspace:
+ * sp_decode_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED ONCE by the caller; every call
+ * returns it to the zero state, so it can be reused by later calls ON THE SAME STREAM (calls that may
+ * run concurrently need separate workspaces). */
+size_t sp_decode_workspace_bytes(void);
+int sp_decode_ws_f32(const float* hm, const float* hm_flip, const int* perm,
+                     const float* trans_inv, const float* blur_w,
+                     float* coords, float* maxval, int* argmax,
+                     int B, int K, int H, int W, int ksize, int mode,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * A7  oks_iou(pick_kps, candi_kps, pick_area, candi_area, sigmas=None, in_vis_thresh=None)
  *     datasets/naive_data.py:120-150.  All float64.

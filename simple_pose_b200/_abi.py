@@ -39,6 +39,9 @@ SIGNATURES = {
     "sp_scale_inplace_f32": (c_int, [c_void, c_ll, c_void, c_void]),
     "sp_decode_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_void]),
+    "sp_decode_workspace_bytes": (c_size, []),
+    "sp_decode_ws_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_size, c_void]),
     "sp_oks_iou_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_dbl, c_void]),
     "sp_oks_nms_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                                c_int, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_void]),
@@ -134,6 +137,21 @@ def to_device(x, dtype, device=None):
         device = device or default_device()
         x = x.to(device=device, dtype=dtype, non_blocking=True)
     return dense(x, dtype)
+
+
+_scratch = {}
+
+
+def scratch(device, stream_id, nbytes, tag):
+    """Zero-initialised device scratch per (tag, device, stream) for the kernels that keep a work
+    counter / reduction workspace there; the kernels restore the zero state, calls on one stream
+    are ordered, so one buffer per stream is enough."""
+    key = (tag, device.index, stream_id)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.zeros((int(nbytes) + 7) // 8, dtype=torch.int64, device=device)
+        _scratch[key] = buf
+    return buf
 
 
 def device_info(device=None):

@@ -48,6 +48,7 @@ struct DecodeArgs {
     float* maxval;
     int* argmax;
     int nmaps, K, H, W, ksize, mode;
+    unsigned int* work;        // caller's workspace {next map, CTAs finished}; nullptr = equal per-CTA ranges
 };
 
 // 13 stencil points (dy, dx): centre, x+-1, y+-1, x+-2, y+-2, four diagonals.
@@ -498,10 +499,17 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
     __syncthreads();                // work counter and barriers are visible to every warp
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
 
-    // lane 0: claim the next map of this CTA and start its copy into stage s (or park -1)
-    auto claim_and_issue = [&](int s) {
-        const int m = atomicAdd(&next_map, 1);
-        if (m >= range_hi) {
+    // Work distribution. Without a workspace: the CTA's own range, claimed from shared memory. With one
+    // (sp_decode_ws_f32): maps are dealt GRID-WIDE -- the first `stages` maps of every warp are fixed,
+    // the rest come from the counter in the workspace -- because the SMs do not drain HBM at equal
+    // rates once the memory system queues (profiles/r1f_fused_timeline.md) and equal ranges make the
+    // slowest SM the critical path. The global atomic is issued one map ahead (`ahead` holds its raw
+    // result while the current map is processed), so its round trip is never waited for.
+    const bool grid_wide = (A.work != nullptr);
+    const int round = (int)gridDim.x * nwarps;
+    unsigned int ahead = 0;
+    auto issue = [&](int s, int m) {                // lane 0: start the copy of map m into stage s (or park -1)
+        if (m < 0) {
             claimed[s] = -1;
             return;
         }
@@ -515,11 +523,24 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
             sp::bulk_g2s(dst + hw, A.hm_flip + (size_t)src * hw, map_bytes, bars + s);
         }
     };
+    auto claim_local = [&]() {
+        const int m = atomicAdd(&next_map, 1);
+        return (m < range_hi) ? m : -1;
+    };
 
     // first copies go out before anything else touches global memory: the blur weights (a dependent
     // global load + block barrier, ~0.7 us) are fetched while the first maps are in flight
-    if (lane == 0)
-        for (int s = 0; s < stages; ++s) claim_and_issue(s);
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            if (grid_wide) {
+                const long long m = (long long)s * round + (long long)blockIdx.x * nwarps + warp;
+                issue(s, m < A.nmaps ? (int)m : -1);
+            } else {
+                issue(s, claim_local());
+            }
+        }
+        if (grid_wide) ahead = atomicAdd(A.work, 1u);
+    }
     if (A.mode == SP_DECODE_GAUSS_TAYLOR)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
@@ -543,9 +564,25 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         __syncwarp();
         if (lane == 0) {
             sp::fence_proxy_async_smem();
-            claim_and_issue(s);
+            if (grid_wide) {
+                const long long nm = (long long)stages * round + (long long)ahead;
+                issue(s, nm < A.nmaps ? (int)nm : -1);
+                if (nm < A.nmaps) ahead = atomicAdd(A.work, 1u);
+            } else {
+                issue(s, claim_local());
+            }
         }
         if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+    if (grid_wide) {                 // the last CTA to finish restores the workspace's zero state
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(A.work + 1, 1u) == gridDim.x - 1) {
+                A.work[0] = 0u;
+                A.work[1] = 0u;
+            }
+        }
     }
 }
 
@@ -592,10 +629,12 @@ int env_int(const char* name, int fallback) {
 
 }  // namespace
 
-extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
-                             const float* trans_inv, const float* blur_w,
-                             float* coords, float* maxval, int* argmax,
-                             int B, int K, int H, int W, int ksize, int mode, void* stream) {
+extern "C" size_t sp_decode_workspace_bytes(void) { return 16; }
+
+static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
+                         const float* trans_inv, const float* blur_w,
+                         float* coords, float* maxval, int* argmax,
+                         int B, int K, int H, int W, int ksize, int mode, unsigned int* work, void* stream) {
     SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(B > 0 && (!hm || !coords || !maxval), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_BASIC, SP_ERR_BAD_ARGUMENT);
@@ -614,6 +653,7 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
     A.hm = hm; A.hm_flip = hm_flip; A.perm = perm; A.trans_inv = trans_inv; A.blur_w = blur_w;
     A.coords = coords; A.maxval = maxval; A.argmax = argmax;
     A.nmaps = B * K; A.K = K; A.H = H; A.W = W; A.ksize = ksize; A.mode = mode;
+    A.work = work;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool flip = hm_flip != nullptr;
 
@@ -641,6 +681,14 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
         int grid = sp_sm_count();
         const int need = (A.nmaps + nwarps - 1) / nwarps;
         if (grid > need) grid = need;
+        // Grid-wide dealing costs one global atomic per map, all on one address (~3 ns each): it pays when
+        // a map is long enough to hide that -- the flip decode of 96x72 maps (55 KB per item: 81.5 -> 78.2 us
+        // for 512 persons) -- and loses below (64x48: 36 -> 61 us), so smaller items keep the equal ranges.
+        // SP_DECODE_GRID_WIDE=1/0 forces either.
+        {
+            const int force = env_int("SP_DECODE_GRID_WIDE", -1);
+            if (force == 0 || (force < 0 && stage_bytes < 40 * 1024)) A.work = nullptr;
+        }
 #define SP_LAUNCH_DECODE(F, KS)                                                                                     \
     do {                                                                                                            \
         SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<F, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -658,4 +706,23 @@ extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* p
     if (flip) SP_CUDA(sp_launch(decode_generic_kernel<true>, dim3(grid), dim3(256), 0, st, A));
     else      SP_CUDA(sp_launch(decode_generic_kernel<false>, dim3(grid), dim3(256), 0, st, A));
     return sp_launch_status();
+}
+
+extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
+                             const float* trans_inv, const float* blur_w,
+                             float* coords, float* maxval, int* argmax,
+                             int B, int K, int H, int W, int ksize, int mode, void* stream) {
+    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, B, K, H, W, ksize, mode, nullptr, stream);
+}
+
+extern "C" int sp_decode_ws_f32(const float* hm, const float* hm_flip, const int* perm,
+                                const float* trans_inv, const float* blur_w,
+                                float* coords, float* maxval, int* argmax,
+                                int B, int K, int H, int W, int ksize, int mode,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    SP_RETURN_IF(!workspace, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(workspace_bytes < sp_decode_workspace_bytes(), SP_ERR_WORKSPACE);
+    SP_RETURN_IF(!sp_aligned16(workspace), SP_ERR_BAD_ALIGNMENT);
+    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, B, K, H, W, ksize, mode,
+                         static_cast<unsigned int*>(workspace), stream);
 }

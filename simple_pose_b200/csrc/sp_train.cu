@@ -734,7 +734,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
 template <int QPR, int PPC, int RING, bool ACC>
 __global__ void __launch_bounds__(512, 1)
 encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count, int nwarps,
-                       int depth) {
+                       int depth, int static_maps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int CHUNK_BYTES = PPC * 32 * Tile<QPR>::PERIOD * 16;
     const int lane = threadIdx.x & 31;
@@ -758,8 +758,8 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     rg.nmaps = io.nmaps;
     rg.static_stride = (int)gridDim.x * nwarps;
     rg.static_next = (int)blockIdx.x * nwarps + warp;
-    rg.static_left = 2;
-    rg.dyn_base = 2 * rg.static_stride;
+    rg.static_left = static_maps;
+    rg.dyn_base = static_maps * rg.static_stride;
     rg.pred = reinterpret_cast<const char*>(io.pred);
     rg.map_bytes = (size_t)hw * 4;
     rg.chunks_per_map = hw * 4 / CHUNK_BYTES;
@@ -939,14 +939,19 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
                 int grid = sp_sm_count();
                 const int need = (nmaps + nwarps - 1) / nwarps;
                 if (grid > need) grid = need;
+                // maps per warp that are assigned up front (no atomic); the rest are dealt from the grid-wide
+                // counter. All atomics hit one address (~3.5 ns each on B200), so the dynamic share is kept to
+                // what the spread of SM speeds needs: half of a warp's expected maps, at least 2 fixed.
+                int static_maps = (int)((long long)nmaps * sp_env_int("SP_TRAIN_STATIC_PCT", 50) / 100 / ((long long)grid * nwarps));
+                if (static_maps < 2) static_maps = 2;
 #define SP_LAUNCH_TILE(Q, P, R)                                                                                              \
     do {                                                                                                                     \
         if (pred_xy) {                                                                                                       \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
         } else {                                                                                                             \
             SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth)); \
+            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
         }                                                                                                                    \
     } while (0)
                 if (qpr == 12) {

@@ -50,11 +50,13 @@ def _decode(heat_map, heat_map_flip, perm, trans_inv, blur_w, ksize, mode, want_
     coords = torch.empty((b, k, 2), dtype=torch.float32, device=dev)
     maxval = torch.empty((b, k, 1), dtype=torch.float32, device=dev)
     index = torch.empty((b, k), dtype=torch.int32, device=dev) if want_index else None
+    stream = _abi.stream_ptr(dev)
+    ws = _abi.scratch(dev, stream, 16, "decode")
     with torch.cuda.device(dev):
-        _abi.check(_abi.lib().sp_decode_f32(hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), _abi.ptr(ti),
-                                            _abi.ptr(blur_w), coords.data_ptr(), maxval.data_ptr(),
-                                            _abi.ptr(index), b, k, h, w, int(ksize), int(mode),
-                                            _abi.stream_ptr(dev)))
+        _abi.check(_abi.lib().sp_decode_ws_f32(hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), _abi.ptr(ti),
+                                               _abi.ptr(blur_w), coords.data_ptr(), maxval.data_ptr(),
+                                               _abi.ptr(index), b, k, h, w, int(ksize), int(mode),
+                                               ws.data_ptr(), ws.numel() * 8, stream))
     if want_index:
         return coords, maxval, index
     return coords, maxval

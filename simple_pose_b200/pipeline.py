@@ -75,10 +75,13 @@ class HeatmapHotPath(object):
             self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream))
 
     def decode(self, pred, trans_inv, pred_flip=None, perm=None):
-        _abi.check(self._lib.sp_decode_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
-                                           _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
-                                           self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
-                                           self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, _abi.stream_ptr(self.device)))
+        stream = _abi.stream_ptr(self.device)
+        ws = _abi.scratch(self.device, stream, 16, "decode")
+        _abi.check(self._lib.sp_decode_ws_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
+                                              _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
+                                              self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
+                                              self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
+                                              stream))
 
     def step(self, joints, pred, trans_inv):
         """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches. The decode is

@@ -851,6 +851,37 @@ def test_decode_work_distribution_covers_every_map(api, b, k):
     assert torch.equal(got[2].long().cpu(), O.argmax_index(hm.cpu()))
 
 
+@pytest.mark.parametrize("b,hw,flip", [(300, (64, 48), False), (64, (96, 72), True), (2, (64, 48), True), (700, (32, 24), False)])
+def test_decode_grid_wide_dealing_equals_equal_ranges(api, b, hw, flip):
+    """sp_decode_ws_f32 (maps dealt grid-wide from the workspace counter, what the Python API calls) and
+    sp_decode_f32 (equal per-CTA ranges) return identical bits; the workspace is back at zero after
+    every call, also after many back-to-back launches on one stream."""
+    h, w = hw
+    hm = synth.heatmaps(b, height=h, width=w, seed=91).to(DEV)
+    hf = synth.heatmaps(b, height=h, width=w, seed=92).to(DEV) if flip else None
+    tinv = synth.inverse_affines(b, height=h, width=w, seed=91)[0].to(DEV)
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    run = (lambda: dec.flip_call(hm, hf, tinv)) if flip else (lambda: dec(hm, tinv))
+    os.environ["SP_DECODE_GRID_WIDE"] = "1"              # by default only items >= 40 KB are dealt grid-wide
+    try:
+        got = [run() for _ in range(6)]
+        os.environ["SP_DECODE_GRID_WIDE"] = "0"
+        want = run()
+    finally:
+        del os.environ["SP_DECODE_GRID_WIDE"]
+    got.append(run())                                    # the default policy
+    for c, m in got:
+        assert torch.equal(c, want[0]) and torch.equal(m, want[1])
+    ws = api.abi.scratch(torch.device(DEV), api.abi.stream_ptr(torch.device(DEV)), 16, "decode")
+    torch.cuda.synchronize()
+    assert int(ws.abs().sum().item()) == 0
+    lib = api.abi.lib()
+    assert lib.sp_decode_ws_f32(hm.data_ptr(), None, None, None, dec._weights_on(hm.device).data_ptr(), got[0][0].data_ptr(),
+                                got[0][1].data_ptr(), None, b, 17, h, w, 11, 0, None, 16, None) == -1
+    assert lib.sp_decode_ws_f32(hm.data_ptr(), None, None, None, dec._weights_on(hm.device).data_ptr(), got[0][0].data_ptr(),
+                                got[0][1].data_ptr(), None, b, 17, h, w, 11, 0, ws.data_ptr(), 8, None) == -3
+
+
 # ------------------------------------------------------------------------------------ train-side caller of the encoder
 def _oracle_train_geometry(smp, inp, outp, n=None):
     n = smp["boxes"].shape[0] if n is None else n
