@@ -30,6 +30,11 @@ for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):  # summarize.py labels lau
         hp.decode(pred, tinv, flip, perm)
         hp.train_fused(joints, pred)
     torch.cuda.synchronize()
+from simple_pose_b200.commons.transforms import train_geometry  # noqa: E402
+smp = {k: v.to(dev) for k, v in synth.train_samples(8192, seed=5).items()}
+for _ in range(reps):
+    train_geometry(smp["boxes"], smp["joints"], smp["img_w"], smp["scale_ratio"], smp["rot"], smp["flip"].to(torch.uint8))
+torch.cuda.synchronize()
 kps, box, area, seg = synth.nms_groups(512, mean_group=20.0, seed=3)
 for _ in range(reps):
     rescore_and_nms(kps.to(dev), box.to(dev), area.to(dev), seg)

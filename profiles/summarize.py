@@ -30,7 +30,7 @@ UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e-6,
               "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}
 
 
-OURS = re.compile(r"(encode_|mse_|decode_|oks_|rescore_|pack_|heatmap_acc|scale_inplace)\w*kernel")
+OURS = re.compile(r"(encode_|mse_|decode_|oks_|rescore_|pack_|heatmap_acc|scale_inplace|train_geometry|transform_joints|box_affine|center_scale_affine)\w*kernel")
 
 
 def short(name):
@@ -111,6 +111,8 @@ def main():
             shape = "64x48,P=1024" if k["kernel"].startswith("encode_mse_tile_kernel<12") else "96x72,P=512"
         if k["kernel"].split("<")[0] in ("rescore_kernel", "oks_nms_kernel"):
             shape = "512 images, ~10.7k persons"
+        if k["kernel"].split("<")[0] in ("train_geometry_kernel",):
+            shape = "8192 persons"
         k["config"] = shape
         last[(k["kernel"], shape, 0, 0)] = k
         traffic["%s @ %s" % (k["kernel"], shape)] = {"dram_bytes_per_launch": k["dram_traffic_bytes"],
