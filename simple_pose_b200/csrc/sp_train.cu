@@ -270,7 +270,17 @@ __device__ __forceinline__ Joint3 load_joint(const MapIo& io, int m) {
     return j;
 }
 
+// Position of x factor i in the period-tiled kernel's layout: the four factors of a quad are split
+// into two planes of (e0, e1) and (e2, e3) pairs, so that the 16-byte shared loads of eight
+// consecutive lanes (consecutive quads of a row) cover 128 contiguous bytes. With the four doubles
+// of a quad contiguous (32-byte lane stride) every such load was a 2-way bank conflict.
+template <int QPR>
+__device__ __forceinline__ int ex_slot(int i) {
+    return QPR > 0 ? (((i >> 2) << 1) + (i & 1) + ((i & 2) ? 2 * QPR : 0)) : i;
+}
+
 // joint -> verdict, weight store, float64 factors into this warp's shared-memory slice
+template <int QPR = 0>
 __device__ __forceinline__ JointVerdict prepare_map(const MapIo& io, int m, const Joint3 j, double* ex, double* ey, int lane) {
     const float mx = j.x, my = j.y, vis = j.v;
     const JointVerdict jv = judge_joint(mx, my, vis, io.reach, io.H, io.W);
@@ -278,7 +288,7 @@ __device__ __forceinline__ JointVerdict prepare_map(const MapIo& io, int m, cons
     __syncwarp();
     if (jv.draw) {
         for (int i = lane; i < io.W + io.H; i += 32) {
-            if (i < io.W) ex[i] = gauss_factor(i, mx, io.denom);
+            if (i < io.W) ex[ex_slot<QPR>(i)] = gauss_factor(i, mx, io.denom);
             else          ey[i - io.W] = gauss_factor(i - io.W, my, io.denom);
         }
     }
@@ -600,13 +610,13 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
         const int q = lane + 32 * j;
         const int y = q / QPR;
         eya[j] = ey_a + 8u * (uint32_t)y;
-        exa[j] = ex_a + 32u * (uint32_t)(q - y * QPR);
+        exa[j] = ex_a + 16u * (uint32_t)(q - y * QPR);           // (e0, e1) plane; (e2, e3) is 16*QPR bytes further
     }
     double exr[T::EX_IN_REGS ? PERIOD : 1][4];
     if (T::EX_IN_REGS && draw) {
 #pragma unroll
         for (int j = 0; j < PERIOD; ++j) {
-            const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u);
+            const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u * QPR);
             exr[j][0] = a.x; exr[j][1] = a.y; exr[j][2] = b.x; exr[j][3] = b.y;
         }
     }
@@ -636,7 +646,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
                     if (T::EX_IN_REGS) {
                         e0 = exr[j][0]; e1 = exr[j][1]; e2 = exr[j][2]; e3 = exr[j][3];
                     } else {
-                        const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u);
+                        const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u * QPR);
                         e0 = a.x; e1 = a.y; e2 = b.x; e3 = b.y;
                     }
                     t.x = __double2float_rn(__dmul_rn(e0, fy));
@@ -708,7 +718,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
                 const int yy = yn - 1 + lane / 3, xx = xn - 1 + lane % 3;
                 const bool in = lane < 9 && yy >= 0 && yy < io.H && xx >= 0 && xx < W;
                 float v = -CUDART_INF_F;
-                if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[xx], ey[yy])));
+                if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[ex_slot<QPR>(xx)], ey[yy])));
                 const float gmax = warp_max_f32(v);
                 const unsigned gi = __reduce_min_sync(SP_FULL, (in && v == gmax) ? (unsigned)(yy * W + xx) : 0x7fffffffu);
                 lxy = axis_of(gmax, (int)gi, W);
@@ -719,7 +729,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
                 int sub = 3;
 #pragma unroll
                 for (int e = 2; e >= 0; --e)
-                    if (__fmul_rn(mk, __double2float_rn(__dmul_rn(ex[x4 + e], ey[y]))) == gmax) sub = e;
+                    if (__fmul_rn(mk, __double2float_rn(__dmul_rn(ex[ex_slot<QPR>(x4 + e)], ey[y]))) == gmax) sub = e;
                 lxy = axis_of(gmax, 4 * gq + sub, io.W);
             }
         } else if (lane == 0) {
@@ -794,7 +804,7 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         const Joint3 jc = jn;
         const int m_next = fifo[(head + 1) & (kFifo - 1)];   // claimed before this map's first chunk was issued
         jn = load_joint(io, m_next >= 0 ? m_next : io.nmaps);
-        const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);
+        const JointVerdict jv = prepare_map<QPR>(io, m, jc, ex, ey, lane);
         float acc;
         if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
             acc = tile_map<QPR, PPC, RING, ACC, 0>(io, m, jv, ex, ey, rg, pd, lane);
