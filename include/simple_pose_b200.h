@@ -40,6 +40,7 @@ extern "C" {
 #define SP_DECODE_GAUSS_TAYLOR 0    /* GaussTaylorKeyPointDecoder.__call__                  */
 #define SP_DECODE_ARGMAX       1    /* BasicKeyPointDecoder.heat_map_to_axis (no affine)    */
 #define SP_DECODE_BASIC        2    /* BasicKeyPointDecoder.__call__ (quarter-pixel shift)  */
+#define SP_DECODE_DARK_ORIGINAL 3   /* DarkPoseOriginalKeyPointDecoder.__call__ (no clamp)  */
 
 /* flags of sp_mse_fwd_bwd_f32 */
 #define SP_MSE_SKIP_MASKED 1        /* do not read pred/target of joints whose mask is 0    */
@@ -123,6 +124,9 @@ int sp_scale_inplace_f32(float* data, long long n, const float* scale_dev, void*
  *   mode SP_DECODE_GAUSS_TAYLOR: GaussTaylorKeyPointDecoder.__call__ (:62-107)
  *   mode SP_DECODE_ARGMAX:       BasicKeyPointDecoder.heat_map_to_axis (:11-24); trans_inv unused
  *   mode SP_DECODE_BASIC:        BasicKeyPointDecoder.__call__ (:26-52)
+ *   mode SP_DECODE_DARK_ORIGINAL: DarkPoseOriginalKeyPointDecoder.__call__ (:110-169), the reference's
+ *                                NumPy/OpenCV per-joint decoder: same blur / log / Taylor step, the refined
+ *                                coordinates are NOT clamped at 0; blur_w/ksize as for GAUSS_TAYLOR
  *
  * hm        [B,K,H,W] f32 (not modified)
  * hm_flip   NULL, or [B,K,H,W] f32: the network output for the horizontally mirrored image.

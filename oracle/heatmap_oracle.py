@@ -245,6 +245,47 @@ def basic_decode(heat_map, trans_inv):
     return back_project(out.reshape(b, k, 2), trans_inv), peak
 
 
+def dark_original_decode(heat_map, trans_inv, kernel_size=11):
+    """``DarkPoseOriginalKeyPointDecoder.__call__`` (metrics/pose_metrics.py:110-169), the reference's
+    NumPy/OpenCV decoder: argmax on the original map; per joint a zero-padded ``cv.GaussianBlur`` in
+    float64 written back to the float32 map, ``*= origin_max / blurred_max`` in float32,
+    ``log(maximum(., 1e-10))``; Taylor step with float32 scalars and ``np.matrix`` inverse when
+    ``1 < px < W-2 and 1 < py < H-2`` and the determinant is non-zero; NO clamp at 0; float32
+    ``einsum`` with ``trans_inv``. Works on a copy (the reference overwrites its input).
+    heat_map [B,K,H,W] float32 tensor -> (coords [B,K,2] float32 tensor, max_val [B,K,1])."""
+    import cv2 as cv
+    coords, max_val = argmax_coords(heat_map)
+    coords = coords.detach().cpu().numpy().copy()
+    hm = heat_map.detach().cpu().numpy().copy()
+    border = (kernel_size - 1) // 2
+    b, k, h, w = hm.shape
+    for i in range(b):
+        for j in range(k):
+            origin_max = np.max(hm[i, j])
+            dr = np.zeros((h + 2 * border, w + 2 * border))
+            dr[border:-border, border:-border] = hm[i, j].copy()
+            dr = cv.GaussianBlur(dr, (kernel_size, kernel_size), 0)
+            hm[i, j] = dr[border:-border, border:-border].copy()
+            hm[i, j] *= origin_max / np.max(hm[i, j])
+    hm = np.log(np.maximum(hm, 1e-10))
+    for n in range(b):
+        for p in range(k):
+            m, c = hm[n][p], coords[n][p]
+            px, py = int(c[0]), int(c[1])
+            if 1 < px < w - 2 and 1 < py < h - 2:
+                dx = 0.5 * (m[py][px + 1] - m[py][px - 1])
+                dy = 0.5 * (m[py + 1][px] - m[py - 1][px])
+                dxx = 0.25 * (m[py][px + 2] - 2 * m[py][px] + m[py][px - 2])
+                dxy = 0.25 * (m[py + 1][px + 1] - m[py - 1][px + 1] - m[py + 1][px - 1] + m[py - 1][px - 1])
+                dyy = 0.25 * (m[py + 2][px] - 2 * m[py][px] + m[py - 2][px])
+                if dxx * dyy - dxy ** 2 != 0:
+                    offset = -np.matrix([[dxx, dxy], [dxy, dyy]]).I * np.matrix([[dx], [dy]])
+                    c += np.squeeze(np.array(offset.T), axis=0)
+    xyz = np.concatenate([coords, np.ones_like(coords[..., [0]])], axis=-1)
+    out = np.einsum("bcd,bad->bca", xyz, trans_inv.detach().cpu().numpy())
+    return torch.from_numpy(out), max_val.detach().cpu()
+
+
 # --------------------------------------------------------------------------- flip test
 def swap_permutation(num_joints=17, joint_pairs=COCO_JOINT_PAIRS):
     """Channel permutation equivalent to the pair swap in ``flip_joints``

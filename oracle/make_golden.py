@@ -135,6 +135,56 @@ def train_geometry_fixtures(ref):
     np.savez_compressed(os.path.join(GOLDEN, "train_geom.npz"), **out)
 
 
+def dark_fixtures(ref, dec_out):
+    """Outputs of the reference's DarkPoseOriginalKeyPointDecoder (image space) on the decode fixtures'
+    inputs (stored in decode.npz) plus a map whose Taylor step leaves the map on the negative side."""
+    dark = ref.DarkPoseOriginalKeyPointDecoder()
+    out = {}
+    for tag in ("a", "b", "e"):
+        c, m = dark(torch.from_numpy(dec_out["hm_" + tag]).clone(), torch.from_numpy(dec_out["tinv_" + tag]))
+        out["img_" + tag], out["max_" + tag] = c.numpy(), m.numpy()
+    hm_n = negative_step_maps()
+    c, m = dark(torch.from_numpy(hm_n).clone(), synth.identity_affines(1))
+    out["hm_n"], out["hsp_n"], out["max_n"] = hm_n, c.numpy(), m.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "dark_original.npz"), **out)
+
+
+def negative_step_maps(h=64, w=48, want=17):
+    """One person whose Taylor steps land at NEGATIVE coordinates (GaussTaylor clamps them to 0,
+    DarkPoseOriginal keeps them): seeded search over smooth two-blob maps with a spike two pixels from a
+    border, keeping joints whose DarkPoseOriginal result moves < 2e-5 px under a 1e-7 relative
+    perturbation of the map (i.e. well-conditioned ones). Takes about a minute."""
+    from oracle import heatmap_oracle as O
+    rng = np.random.default_rng(3)
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    eye = torch.eye(2, 3)[None]
+    keep = []
+    while len(keep) < want:
+        hm = np.zeros((1, 17, h, w), np.float32)
+        for k in range(17):
+            cx, cy, s, amp = rng.uniform(-6, 1), rng.uniform(8, 50), rng.uniform(2.5, 6), rng.uniform(0.4, 0.9)
+            if k % 2 == 0:
+                f = amp * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * s * s))
+            else:
+                f = amp * np.exp(-((ys - cx) ** 2 + (xs - min(cy, 40)) ** 2) / (2 * s * s))
+            f = f.astype(np.float32)
+            f += (rng.uniform(0.0, 0.3) * np.exp(-((xs - rng.uniform(0, 10)) ** 2 + (ys - rng.uniform(0, 60)) ** 2) /
+                                                 (2 * rng.uniform(2, 5) ** 2))).astype(np.float32)
+            py, px = (int(rng.integers(10, 50)), 2) if k % 2 == 0 else (2, int(rng.integers(10, 40)))
+            f[py, px] = f.max() * 1.02 + 1e-3
+            hm[0, k] = f
+        c = O.dark_original_decode(torch.from_numpy(hm), eye)[0].numpy()[0]
+        neg = np.nonzero((c < 0).any(axis=1) & (np.abs(c).max(axis=1) < 60))[0]
+        if len(neg) == 0:
+            continue
+        pert = hm * (1 + 1e-7 * rng.standard_normal(hm.shape)).astype(np.float32)
+        c2 = O.dark_original_decode(torch.from_numpy(pert), eye)[0].numpy()[0]
+        for k in neg:
+            if np.abs(c2[k] - c[k]).max() < 2e-5 and len(keep) < want:
+                keep.append(hm[0, k].copy())
+    return np.stack(keep)[None]
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(GOLDEN, exist_ok=True)
@@ -143,6 +193,10 @@ def main():
     affine_fixtures(ref)
     train_geometry_fixtures(ref)
     if "--only-affine" in sys.argv:
+        return
+    if "--only-dark" in sys.argv:
+        dec = np.load(os.path.join(GOLDEN, "decode.npz"))
+        dark_fixtures(ref, dec)
         return
 
     # ---------------------------------------------------------------- encode
@@ -191,6 +245,7 @@ def main():
     c2, _ = dark(torch.from_numpy(hm_a).clone(), torch.from_numpy(synth.identity_affines(3).numpy()))
     out["hsp_a_darkpose"] = c2.numpy().astype(np.float64)
     np.savez_compressed(os.path.join(GOLDEN, "decode.npz"), **out)
+    dark_fixtures(ref, out)
 
     # ---------------------------------------------------------------- flip-average + decode
     hm, hf = synth.flip_pair(2, height=64, width=48, seed=21, noise=0.01)

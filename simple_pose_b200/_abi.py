@@ -20,7 +20,7 @@ c_flt = ctypes.c_float
 c_size = ctypes.c_size_t
 c_ll = ctypes.c_longlong
 
-SP_DECODE_GAUSS_TAYLOR, SP_DECODE_ARGMAX, SP_DECODE_BASIC = 0, 1, 2
+SP_DECODE_GAUSS_TAYLOR, SP_DECODE_ARGMAX, SP_DECODE_BASIC, SP_DECODE_DARK_ORIGINAL = 0, 1, 2, 3
 SP_MSE_SKIP_MASKED = 1
 SP_BOX_XYXY, SP_BOX_XYWH = 0, 1
 

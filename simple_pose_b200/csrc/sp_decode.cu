@@ -420,14 +420,19 @@ __device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map,
     const int ix = positive ? pk.index - iy * W : 0;
     float x = (float)ix, y = (float)iy;
 
-    if (A.mode == SP_DECODE_GAUSS_TAYLOR) {
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR || A.mode == SP_DECODE_DARK_ORIGINAL) {
         const bool inner = (ix > 1) && (ix < W - 2) && (iy > 1) && (iy < H - 2);
         if (inner) {
             float ox = 0.f, oy = 0.f;
             if (refine(ix, iy, pk.value, ox, oy)) {
                 const float nx = __fadd_rn(x, ox), ny = __fadd_rn(y, oy);
-                x = (nx < 0.f) ? 0.f : nx;                // clamp(min=0) that keeps NaN
-                y = (ny < 0.f) ? 0.f : ny;
+                if (A.mode == SP_DECODE_GAUSS_TAYLOR) {
+                    x = (nx < 0.f) ? 0.f : nx;            // clamp(min=0) that keeps NaN
+                    y = (ny < 0.f) ? 0.f : ny;
+                } else {                                  // DarkPoseOriginalKeyPointDecoder.taylor: coord += offset
+                    x = nx;
+                    y = ny;
+                }
             }
         }
     } else if (A.mode == SP_DECODE_BASIC) {
@@ -541,11 +546,11 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         }
         if (grid_wide) ahead = atomicAdd(A.work, 1u);
     }
-    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR || A.mode == SP_DECODE_DARK_ORIGINAL)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
     LaneTaps<(KS > 0 ? KS : 3)> taps;
-    if (KS > 0 && A.mode == SP_DECODE_GAUSS_TAYLOR) taps.load(wts, lane);
+    if (KS > 0 && (A.mode == SP_DECODE_GAUSS_TAYLOR || A.mode == SP_DECODE_DARK_ORIGINAL)) taps.load(wts, lane);
     int s = 0;
     uint32_t parity = 0;
     for (;;) {
@@ -598,7 +603,7 @@ decode_generic_kernel(const DecodeArgs A) {
     const int warp = threadIdx.x >> 5;
     const int hw = A.H * A.W;
     sp::grid_dep_wait();
-    if (A.mode == SP_DECODE_GAUSS_TAYLOR)
+    if (A.mode == SP_DECODE_GAUSS_TAYLOR || A.mode == SP_DECODE_DARK_ORIGINAL)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
     const int total = gridDim.x * 8;
@@ -637,9 +642,9 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
                          int B, int K, int H, int W, int ksize, int mode, unsigned int* work, void* stream) {
     SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(B > 0 && (!hm || !coords || !maxval), SP_ERR_BAD_ARGUMENT);
-    SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_BASIC, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_DARK_ORIGINAL, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(hm_flip && !perm, SP_ERR_BAD_ARGUMENT);
-    if (mode == SP_DECODE_GAUSS_TAYLOR) {
+    if (mode == SP_DECODE_GAUSS_TAYLOR || mode == SP_DECODE_DARK_ORIGINAL) {
         SP_RETURN_IF(!blur_w, SP_ERR_BAD_ARGUMENT);
         SP_RETURN_IF(ksize < 3 || ksize > kMaxKsize || (ksize & 1) == 0, SP_ERR_UNSUPPORTED);
     } else {

@@ -126,6 +126,24 @@ class GaussTaylorKeyPointDecoder(BasicKeyPointDecoder):
                        self.kernel_size, _abi.SP_DECODE_GAUSS_TAYLOR, want_index=True)
 
 
+class DarkPoseOriginalKeyPointDecoder(GaussTaylorKeyPointDecoder):
+    """Drop-in for the reference's third decoder (``metrics/pose_metrics.py:110-169``), its NumPy/OpenCV
+    per-joint loop: zero-padded ``cv.GaussianBlur`` (float64), rescale by ``origin_max / blurred_max``,
+    ``log(max(., 1e-10))``, the same Taylor step, and -- the one semantic difference to
+    ``GaussTaylorKeyPointDecoder`` -- no ``clamp(min=0)`` of the refined coordinates. Same kernel, mode
+    ``SP_DECODE_DARK_ORIGINAL``; agrees with the reference class to ~1e-5 px (it blurs in float64, the
+    kernel in float32). Unlike the reference it returns tensors on the input's device and does not
+    overwrite ``heat_map`` with its blurred copy (the reference does, through the shared NumPy view)."""
+
+    def __init__(self, kernel_size=11):
+        super().__init__(kernel_size=kernel_size, num_joints=17)
+
+    @torch.no_grad()
+    def __call__(self, heat_map, trans_inv):
+        return _decode(heat_map, None, None, trans_inv, self._weights_on(heat_map.device),
+                       self.kernel_size, _abi.SP_DECODE_DARK_ORIGINAL)
+
+
 def heatmap_acc_from_axes(pred_xy, label_xy, height, width, distance_thresh=0.5, norm_frac=10.):
     """HeatMapAcc epilogue on [B,K,2] argmax coordinates -> 0-d float32 tensor (no host sync)."""
     dev = _abi.require_cuda(pred_xy, label_xy)

@@ -9,6 +9,7 @@ Gates (BASELINE.json north_star / SURVEY.md section 8d):
   separable evaluation, one rounding); weights, NMS keep sets and pick order exact.
 """
 import os
+import warnings
 
 import numpy as np
 import pytest
@@ -310,6 +311,37 @@ def test_basic_decoder(api, golden):
 
 
 # ------------------------------------------------------------------------------------ flip test
+def test_dark_original_decoder(api, golden):
+    """Mode SP_DECODE_DARK_ORIGINAL against the reference's NumPy/OpenCV decoder (frozen outputs and the
+    pinned restatement): argmax-level outputs exact, coordinates within 1e-4 px in heatmap space (the
+    reference blurs in float64, the kernel in float32), negative Taylor results kept, input not modified."""
+    g, d = golden("dark_original"), golden("decode")
+    dec = api.metrics.DarkPoseOriginalKeyPointDecoder()
+    for tag in ("a", "b", "e"):
+        hm = torch.from_numpy(d["hm_" + tag]).to(DEV)
+        keep = hm.clone()
+        tinv = torch.from_numpy(d["tinv_" + tag]).to(DEV)
+        c, m = dec(hm, tinv)
+        mag = tinv[:, :, :2].abs().sum(-1).max().item()
+        assert np.array_equal(bits(m.cpu().numpy()), bits(g["max_" + tag]))
+        assert np.abs(c.cpu().numpy() - g["img_" + tag]).max() <= 1e-4 * mag + 1e-4
+        assert torch.equal(hm, keep)
+    eye = synth.identity_affines(1, device=DEV)
+    c, m = dec(torch.from_numpy(g["hm_n"]).to(DEV), eye)
+    got = c.cpu().numpy()
+    assert (got < 0).any(axis=-1).all()
+    assert np.abs(got - g["hsp_n"]).max() <= 2e-3          # float32 vs float64 blur with |offset| up to 23 px
+    gt, _ = api.metrics.GaussTaylorKeyPointDecoder()(torch.from_numpy(g["hm_n"]).to(DEV), eye)
+    assert gt.min().item() == 0.0
+    # seeded maps against the restatement
+    hm = synth.heatmaps(64, seed=35, noise=0.01)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oc, om = O.dark_original_decode(hm, synth.identity_affines(64))
+    c, m = dec(hm.to(DEV), synth.identity_affines(64, device=DEV))
+    assert torch.equal(m.cpu(), om) and (c.cpu() - oc).abs().max().item() <= 1e-4
+
+
 def test_flip_decode_golden(api, golden):
     g = golden("flip")
     dec = api.metrics.GaussTaylorKeyPointDecoder()

@@ -117,3 +117,17 @@ def test_train_geometry(ref, inp, outp):
         assert np.array_equal(bits(fj), bits(O.flip_joints_only(smp["joints"][i].numpy(), args[1])))
         aj = ref.joint_utils.affine_transform_batch(smp["joints"][i].numpy(), rt)
         assert np.array_equal(bits(aj), bits(O.affine_joints(smp["joints"][i].numpy(), rt)))
+
+
+def test_dark_original_decoder(ref):
+    """DarkPoseOriginalKeyPointDecoder itself (on a clone: it overwrites its input) vs the restatement."""
+    import warnings
+    for hw, seed in (((64, 48), 31), ((96, 72), 32), ((40, 36), 33)):
+        h, w = hw
+        hm = synth.heatmaps(6, height=h, width=w, seed=seed, noise=0.02)
+        tinv = synth.inverse_affines(6, height=h, width=w, seed=seed)[0]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rc, rm = ref.DarkPoseOriginalKeyPointDecoder()(hm.clone(), tinv)
+            oc, om = O.dark_original_decode(hm, tinv)
+        assert rc.dtype == oc.dtype and torch.equal(rc, oc) and torch.equal(rm, om)
