@@ -546,7 +546,7 @@ def affine_joints(joints, t):
 
 def train_sample_geometry(box, img_w, joints, scale_ratio=1.0, rot=0.0, flip=False,
                           joint_pairs=COCO_JOINT_PAIRS, input_shape=(192, 256), output_shape=(48, 64),
-                          sigma=2.0):
+                          sigma=2.0, basic=False):
     """``RefineSimpleTransform.__call__`` (commons/transforms.py:193-223) without the image work
     (``cv.warpAffine``, ``np.fliplr``) and with its random draws passed in: ``box`` is the box AFTER
     ``box_crop`` (four Python floats), ``scale_ratio`` / ``rot`` / ``flip`` are the three draws of
@@ -566,7 +566,10 @@ def train_sample_geometry(box, img_w, joints, scale_ratio=1.0, rot=0.0, flip=Fal
     joint_trans, trans_inv = affine_pair(center, scale, output_shape, rot)
     joints_input = affine_joints(joints, img_trans)
     joints_hm = affine_joints(joints, joint_trans)
-    heat_map, mask = encode_person(joints_hm, sigma, output_shape)
+    if basic:       # BasicSimpleTransform.__call__ (:118-148): quantised encoder on the INPUT-pixel joints, stride 4
+        heat_map, mask = encode_person_basic(joints_input, sigma, output_shape, 4)
+    else:
+        heat_map, mask = encode_person(joints_hm, sigma, output_shape)
     return {"center": center, "scale": scale, "img_trans": img_trans, "joint_trans": joint_trans,
             "trans_inv": trans_inv, "joints_input": joints_input, "joints_hm": joints_hm,
             "heat_map": heat_map, "mask": mask}

@@ -94,7 +94,7 @@ def load():
 
 
 def run_train_transform(ns, box, img_w, img_h, joints, scale_ratio, rot, flip, joint_pairs,
-                        input_shape=(192, 256), output_shape=(48, 64)):
+                        input_shape=(192, 256), output_shape=(48, 64), basic=False):
     """The reference's own ``RefineSimpleTransform.__call__`` (commons/transforms.py:193-223) on one
     sample with its three ``np.random.uniform`` draws scripted (``rand_crop=False``: the box is taken
     as already cropped) and a blank image (the warp result is not looked at). Returns the mutated
@@ -103,8 +103,9 @@ def run_train_transform(ns, box, img_w, img_h, joints, scale_ratio, rot, flip, j
     import unittest.mock as mock
     import numpy as np
     T = ns.transforms
-    tr = T.RefineSimpleTransform(joint_pairs=[list(p) for p in joint_pairs], input_shape=tuple(input_shape),
-                                 output_shape=tuple(output_shape), rand_crop=False)
+    cls = T.BasicSimpleTransform if basic else T.RefineSimpleTransform       # ``basic``: :118-148 instead of :193-223
+    tr = cls(joint_pairs=[list(p) for p in joint_pairs], input_shape=tuple(input_shape),
+             output_shape=tuple(output_shape), rand_crop=False)
     kp = T.KeyPoints("0.jpg", (int(img_w), int(img_h)), [float(v) for v in box], np.array(joints, dtype=np.float32))
     kp.img = np.zeros((int(img_h), int(img_w), 3), np.uint8)
     draws = iter([float(scale_ratio), float(rot), 0.0 if flip else 0.9])

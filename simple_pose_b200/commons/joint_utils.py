@@ -27,6 +27,13 @@ def box_to_center_scale(x, y, w, h, aspect_ratio=1.0, scale_mult=1.25):
     return out["center"][0].cpu().numpy(), out["scale"][0].cpu().numpy()
 
 
+def center_scale_to_box(center, scale):
+    """``commons/joint_utils.py:59-69`` (host arithmetic on two 2-vectors, kept for drop-in completeness)."""
+    w, h = scale[0], scale[1]
+    xmin, ymin = center[0] - w * 0.5, center[1] - h * 0.5
+    return (xmin, ymin, xmin + w, ymin + h)
+
+
 def get_affine_transforms(center, scale, output_size, device=None, rot=None):
     """Batched ``get_affine_transform(center[i], scale[i], rot[i], output_size)``: center, scale [P,2]
     float32, rot [P] float64 degrees (None = 0) -> (trans [P,2,3], trans_inv [P,2,3]) float64 device

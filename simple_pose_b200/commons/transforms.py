@@ -176,8 +176,35 @@ def encode_heat_maps_basic(joints, sigma=2.0, shape=(48, 64), stride=4):
     return targets, weights
 
 
+def train_targets_basic(boxes, joints, img_w=None, scale_ratio=None, rot=None, flip=None, joint_pairs=None,
+                        input_shape=(192, 256), output_shape=(48, 64), sigma=2.0, stride=4):
+    """``BasicSimpleTransform.__call__`` (reference ``commons/transforms.py:118-148``) without the image work:
+    as ``train_targets`` but the quantised 13x13 encoder runs on the INPUT-pixel joints (``:141-143``).
+    Returns ``(heat_maps, masks, trans_invs)`` device tensors."""
+    geo = train_geometry(boxes, joints, img_w, scale_ratio, rot, flip, joint_pairs, input_shape, output_shape, want_input=True)
+    heat_maps, masks = encode_heat_maps_basic(geo["joints_input"], sigma, output_shape, stride)
+    return heat_maps, masks, geo["trans_inv"]
+
+
 class BasicSimpleTransform(object):
-    """Hot-path member of the reference's ``BasicSimpleTransform`` (commons/transforms.py:64-116)."""
+    """Hot-path members of the reference's ``BasicSimpleTransform`` (commons/transforms.py:64-148)."""
+
+    def __init__(self, joint_pairs=None, input_shape=(192, 256), output_shape=(48, 64),
+                 scale=(0.7, 1.3), ratio=(-40, 40), rand_crop=True):
+        self.input_shape = input_shape
+        self.output_shape = output_shape
+        self.joint_pairs = joint_pairs
+        self.w_h_ratio = self.input_shape[0] / self.input_shape[1]
+        self.scale = scale
+        self.ratio = ratio
+        self.rand_crop = rand_crop
+
+    def joint_targets(self, boxes, joints, img_w=None, scale_ratio=None, rot=None, flip=None, sigma=2.0):
+        """Batched ``__call__`` (reference :118-148) without ``box_crop`` and the image warp."""
+        if self.joint_pairs is None:
+            flip = None
+        return train_targets_basic(boxes, joints, img_w, scale_ratio, rot, flip, self.joint_pairs, self.input_shape,
+                                   self.output_shape, sigma)
 
     @staticmethod
     def get_heat_map(joints, sigma=2.0, shape=(48, 64), stride=4):

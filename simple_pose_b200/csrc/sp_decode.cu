@@ -31,6 +31,19 @@
 #include "sp_common.cuh"
 #include <math_constants.h>
 
+#ifdef SP_TRAIN_TRACE
+// scratch instrumentation (never compiled into the product library): per-CTA [release, finish, smid, maps]
+__device__ long long* g_decode_trace_ptr = nullptr;
+extern "C" int sp_debug_set_decode_trace(void* p) {
+    return (int)cudaMemcpyToSymbol(g_decode_trace_ptr, &p, sizeof(p));
+}
+__device__ __forceinline__ long long decode_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 namespace {
 
 constexpr int kMaxKsize = 15;
@@ -503,6 +516,10 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
     }
     __syncthreads();                // work counter and barriers are visible to every warp
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
+#ifdef SP_TRAIN_TRACE
+    const long long trace_t0 = decode_gtime();
+    int trace_maps = 0;
+#endif
 
     // Work distribution. Without a workspace: the CTA's own range, claimed from shared memory. With one
     // (sp_decode_ws_f32): maps are dealt GRID-WIDE -- the first `stages` maps of every warp are fixed,
@@ -578,7 +595,18 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
             }
         }
         if (++s == stages) { s = 0; parity ^= 1u; }
+#ifdef SP_TRAIN_TRACE
+        ++trace_maps;
+#endif
     }
+#ifdef SP_TRAIN_TRACE
+    if (lane == 0 && g_decode_trace_ptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long* t = g_decode_trace_ptr + ((size_t)blockIdx.x * 16 + warp) * 4;
+        t[0] = trace_t0; t[1] = decode_gtime(); t[2] = smid; t[3] = trace_maps;
+    }
+#endif
     if (grid_wide) {                 // the last CTA to finish restores the workspace's zero state
         __syncthreads();
         if (threadIdx.x == 0) {

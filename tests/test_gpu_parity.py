@@ -988,6 +988,26 @@ def test_train_geometry_vs_oracle(api, inp, outp):
     assert 0 < masks.sum().item() < masks.numel()
 
 
+def test_train_targets_basic_transform(api):
+    """BasicSimpleTransform.joint_targets (train_geometry -> input-pixel joints -> quantised encoder) vs the
+    pinned restatement of the reference's BasicSimpleTransform.__call__."""
+    n = 200
+    smp = synth.train_samples(n, seed=707)
+    tr = api.transforms.BasicSimpleTransform(joint_pairs=[list(p) for p in O.COCO_JOINT_PAIRS])
+    hm, mk, tinv = tr.joint_targets(smp["boxes"], smp["joints"], smp["img_w"], smp["scale_ratio"], smp["rot"], smp["flip"])
+    geo = api.transforms.train_geometry(smp["boxes"], smp["joints"], smp["img_w"], smp["scale_ratio"], smp["rot"], smp["flip"],
+                                        want_input=True)
+    checked = 0
+    for i in range(n):
+        o = O.train_sample_geometry(smp["boxes"][i].tolist(), int(smp["img_w"][i]), smp["joints"][i].numpy(),
+                                    float(smp["scale_ratio"][i]), float(smp["rot"][i]), bool(smp["flip"][i]), basic=True)
+        if np.array_equal(bits(geo["joints_input"][i].cpu().numpy()), bits(o["joints_input"])):
+            assert np.array_equal(bits(hm[i].cpu().numpy()), bits(o["heat_map"])) and np.array_equal(mk[i].cpu().numpy(), o["mask"]), i
+            assert np.array_equal(bits(tinv[i].cpu().numpy()), bits(o["trans_inv"].astype(np.float32)))
+            checked += 1
+    assert checked >= n - 2
+
+
 def test_train_geometry_drop_ins_and_edges(api):
     """Per-sample drop-ins of commons/joint_utils.py (flip_joints, affine_transform_batch,
     get_affine_transform with a rotation) and the degenerate batches."""

@@ -131,3 +131,16 @@ def test_dark_original_decoder(ref):
             rc, rm = ref.DarkPoseOriginalKeyPointDecoder()(hm.clone(), tinv)
             oc, om = O.dark_original_decode(hm, tinv)
         assert rc.dtype == oc.dtype and torch.equal(rc, oc) and torch.equal(rm, om)
+
+
+def test_train_geometry_basic_transform(ref):
+    """BasicSimpleTransform.__call__ (commons/transforms.py:118-148), draws scripted: the quantised encoder
+    runs on the input-pixel joints; trans_inv and targets bit-identical."""
+    smp = synth.train_samples(60, seed=304)
+    for i in range(60):
+        box, w = smp["boxes"][i].tolist(), int(smp["img_w"][i])
+        draws = (float(smp["scale_ratio"][i]), float(smp["rot"][i]), bool(smp["flip"][i]))
+        kp = ref_loader.run_train_transform(ref, box, w, 480, smp["joints"][i].numpy(), *draws, O.COCO_JOINT_PAIRS, basic=True)
+        o = O.train_sample_geometry(box, w, smp["joints"][i].numpy(), *draws, basic=True)
+        assert np.array_equal(bits(kp.trans_inv), bits(o["trans_inv"])) and np.array_equal(bits(kp.joints), bits(o["joints_input"]))
+        assert np.array_equal(bits(kp.heat_map), bits(o["heat_map"])) and np.array_equal(kp.mask, o["mask"]), i
