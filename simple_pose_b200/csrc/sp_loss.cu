@@ -25,6 +25,16 @@
 #include "sp_common.cuh"
 #include "sp_reduce.cuh"
 
+#ifdef SP_TRAIN_TRACE
+__device__ long long* g_loss_trace_ptr = nullptr;     // scratch instrumentation, trace build only
+extern "C" int sp_debug_set_loss_trace(void* p) { return (int)cudaMemcpyToSymbol(g_loss_trace_ptr, &p, sizeof(p)); }
+__device__ __forceinline__ long long loss_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 namespace {
 
 using namespace sp_reduce;
@@ -123,6 +133,9 @@ mse_ring_kernel(const float* __restrict__ pred, const float* __restrict__ target
     const long long lo = (long long)blockIdx.x * nchunks / gridDim.x;
     const long long hi = (long long)(blockIdx.x + 1) * nchunks / gridDim.x;
     sp::grid_dep_wait();            // the prologue above overlapped the previous kernel's tail
+#ifdef SP_TRAIN_TRACE
+    const long long trace_t0 = loss_gtime();
+#endif
 
     long long pi = lo + warp;       // producer cursor (lane 0): next chunk to request, into slot ps
     int ps = 0;
@@ -168,6 +181,14 @@ mse_ring_kernel(const float* __restrict__ pred, const float* __restrict__ target
         }
         if (++cs == ring) { cs = 0; parity ^= 1u; }
     }
+#ifdef SP_TRAIN_TRACE
+    if (lane == 0 && g_loss_trace_ptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long* t = g_loss_trace_ptr + ((size_t)blockIdx.x * 32 + warp) * 4;
+        t[0] = trace_t0; t[1] = loss_gtime(); t[2] = smid; t[3] = (long long)(hi - lo);
+    }
+#endif
     finish_loss<1024>(sum_sq, ws, loss, inv_count);
 }
 
