@@ -64,12 +64,8 @@ class HeatmapHotPath(object):
             self.label_xy = torch.empty_like(self.pred_xy)
         stream = _abi.stream_ptr(self.device)
         ws = _workspace(self.device, stream)
-        import os
-        exp = os.environ.get("SP_EXP_TRAIN", "")
-        if "noacc" in exp:
-            with_acc = False
         _abi.check(self._lib.sp_encode_mse_fwd_bwd_f32(
-            joints.data_ptr(), pred.data_ptr(), None if "nograd" in exp else self.grad.data_ptr(), None, self.weights.data_ptr(),
+            joints.data_ptr(), pred.data_ptr(), self.grad.data_ptr(), None, self.weights.data_ptr(),
             self.loss.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
             _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
             self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream))
