@@ -18,7 +18,7 @@ constexpr int kWarpsPerCta = 8;
 template <bool VEC4, int WARPS>
 __global__ void __launch_bounds__(WARPS* SP_WARP)
 encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targets, float* __restrict__ weights,
-                     int nmaps, int H, int W, float reach, double denom) {
+                     int nmaps, int H, int W, float reach, double denom, int parts) {
     extern __shared__ __align__(16) double factors[];   // per warp: ex[Wpad] then ey[H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -26,44 +26,49 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     double* ex = factors + (size_t)warp * (wpad + H);
     double* ey = ex + wpad;
     const int hw = H * W;
-    const int total_warps = gridDim.x * WARPS;
+    const long long total_warps = (long long)gridDim.x * WARPS;
+    const long long units = (long long)nmaps * parts;     // a unit = rows [r0, r1) of one map, one warp
+    const int rows_per_part = (H + parts - 1) / parts;
     sp::grid_dep_wait();
 
-    for (int m = blockIdx.x * WARPS + warp; m < nmaps; m += total_warps) {
+    for (long long u = (long long)blockIdx.x * WARPS + warp; u < units; u += total_warps) {
+        const int m = (int)(u / parts);
+        const int part = (int)(u - (long long)m * parts);
+        const int r0 = part * rows_per_part, r1 = min(H, r0 + rows_per_part);
         const float mx = __ldg(joints + 3 * (size_t)m + 0);
         const float my = __ldg(joints + 3 * (size_t)m + 1);
         const float vis = __ldg(joints + 3 * (size_t)m + 2);
         const JointVerdict jv = judge_joint(mx, my, vis, reach, H, W);
-        if (lane == 0) weights[m] = jv.weight;
+        if (lane == 0 && part == 0) weights[m] = jv.weight;
         float* out = targets + (size_t)m * hw;
 
         if (!jv.draw) {
             if (VEC4) {
                 float4* o4 = reinterpret_cast<float4*>(out);
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int q = lane; q < (hw >> 2); q += 32) o4[q] = z;
+                for (int q = (r0 * W >> 2) + lane; q < (r1 * W >> 2); q += 32) o4[q] = z;
             } else {
-                for (int i = lane; i < hw; i += 32) out[i] = 0.f;
+                for (int i = r0 * W + lane; i < r1 * W; i += 32) out[i] = 0.f;
             }
             continue;
         }
 
-        __syncwarp();   // previous map's readers are done with ex/ey
-        for (int i = lane; i < W + H; i += 32) {
+        __syncwarp();   // previous unit's readers are done with ex/ey
+        for (int i = lane; i < W + (r1 - r0); i += 32) {
             if (i < W) ex[i] = gauss_factor(i, mx, denom);
-            else       ey[i - W] = gauss_factor(i - W, my, denom);
+            else       ey[r0 + i - W] = gauss_factor(r0 + i - W, my, denom);
         }
         __syncwarp();
 
         if (VEC4) {
             // W % 4 == 0: a quad never straddles rows. Track (row, quad-in-row) incrementally.
             const int qpr = W >> 2;
-            const int nq = hw >> 2;
-            int y = lane / qpr;
-            int xq = lane - y * qpr;
+            const int q0 = r0 * qpr + lane, nq = r1 * qpr;
+            int y = q0 / qpr;
+            int xq = q0 - y * qpr;
             const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
             float4* o4 = reinterpret_cast<float4*>(out);
-            for (int q = lane; q < nq; q += 32) {
+            for (int q = q0; q < nq; q += 32) {
                 const double2 a = *reinterpret_cast<const double2*>(ex + 4 * xq);
                 const double2 b = *reinterpret_cast<const double2*>(ex + 4 * xq + 2);
                 const double fy = ey[y];
@@ -78,7 +83,7 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
                 if (xq >= qpr) { xq -= qpr; ++y; }
             }
         } else {
-            for (int i = lane; i < hw; i += 32) {
+            for (int i = r0 * W + lane; i < r1 * W; i += 32) {
                 const int y = i / W, x = i - y * W;
                 out[i] = __double2float_rn(__dmul_rn(ex[x], ey[y]));
             }
@@ -146,13 +151,27 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     const size_t smem = (size_t)warps * (wpad + H) * sizeof(double);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     const bool vec4 = (W % 4 == 0) && sp_aligned16(targets);
-    const int grid = (nmaps + warps - 1) / warps;
+    // A unit of work is a range of ~32 rows of one map, one warp each (parts = H / 32 per map). Whole
+    // maps per warp leave a launch of 512 persons at 96x72 with 29 CTAs per SM, all resident at once:
+    // ONE wave in which every warp first evaluates its float64 factors and then stores, the two
+    // phases never overlapping across CTAs. Shorter units give several waves and an even finish:
+    // 96x72 x 512: 41.3 -> 39.0 us (0.89 -> 0.945 of the HBM peak), x 1024: 0.96 -> 1.00;
+    // 64x48 x 1024: 35.0 -> 33.7 us (0.94 -> 0.97). 16-row units lose again (the W factors are
+    // re-evaluated per unit: 64x48 x 1024 40.9 us).
+    int parts = H / 32;
+    if (parts < 1) parts = 1;
+    parts = sp_env_int("SP_ENCODE_PARTS", parts);
+    if (parts < 1) parts = 1;
+    if (parts > H) parts = H;
+    const long long units = (long long)nmaps * parts;
+    SP_RETURN_IF((units + warps - 1) / warps > 0x7fffffffLL, SP_ERR_UNSUPPORTED);
+    const int grid = (int)((units + warps - 1) / warps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define SP_LAUNCH_ENCODE(V, NW)                                                                                         \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
             SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<V, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SP_CUDA(sp_launch(encode_refine_kernel<V, NW>, dim3(grid), dim3(NW * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom)); \
+        SP_CUDA(sp_launch(encode_refine_kernel<V, NW>, dim3(grid), dim3(NW * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom, parts)); \
     } while (0)
     if (vec4) { if (warps == 2) SP_LAUNCH_ENCODE(true, 2); else if (warps == 4) SP_LAUNCH_ENCODE(true, 4); else SP_LAUNCH_ENCODE(true, 8); }
     else      { if (warps == 2) SP_LAUNCH_ENCODE(false, 2); else if (warps == 4) SP_LAUNCH_ENCODE(false, 4); else SP_LAUNCH_ENCODE(false, 8); }

@@ -89,6 +89,24 @@ def test_encode_cta_sizes_agree(api, warps):
     assert torch.equal(t, base_t) and torch.equal(w, base_w) and torch.equal(t2, base_t) and torch.equal(w2, base_w)
 
 
+@pytest.mark.parametrize("parts", ["1", "2", "3", "4", "64", "200"])
+@pytest.mark.parametrize("shape", [(48, 64), (72, 96), (50, 30), (132, 20)])
+def test_encode_row_parts_agree(api, parts, shape):
+    """A map may be split into row ranges, one warp each (small launches do so by default): every split,
+    including uneven ones and more parts than rows, writes the same bits as one warp per map."""
+    w, h = shape
+    joints = synth.joints(21, height=h, width=w, seed=654).to(DEV)
+    os.environ["SP_ENCODE_PARTS"] = "1"
+    try:
+        base_t, base_w = api.transforms.encode_heat_maps(joints, 2.0, shape)
+        os.environ["SP_ENCODE_PARTS"] = parts
+        t, wt = api.transforms.encode_heat_maps(joints, 2.0, shape)
+    finally:
+        del os.environ["SP_ENCODE_PARTS"]
+    auto_t, auto_w = api.transforms.encode_heat_maps(joints, 2.0, shape)
+    assert torch.equal(t, base_t) and torch.equal(wt, base_w) and torch.equal(auto_t, base_t) and torch.equal(auto_w, base_w)
+
+
 def test_encode_per_sample_signature_and_empty(api, golden):
     g = golden("encode")
     t, w = api.transforms.RefineSimpleTransform.get_heat_map(g["joints_e"][0], sigma=2.0, shape=(48, 64))
