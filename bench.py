@@ -418,11 +418,36 @@ def small_batch_numbers(device, height, width, batch=128, nbatch=64):
         paths[i].step(*sets[i])
         torch.cuda.synchronize(device)
         lat.append(time.perf_counter() - t0)
+    # the same batches through the fused training kernel + decode (2 launches per batch, targets never written)
+    def fused_all():
+        for i in range(nbatch):
+            paths[i].train_fused(sets[i][0], sets[i][1])
+            paths[i].decode(sets[i][1], sets[i][2])
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        fused_all()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    fgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(fgraph, stream=side):
+        fused_all()
+    for _ in range(3):
+        fgraph.replay()
+    torch.cuda.synchronize(device)
+    a.record()
+    for _ in range(reps):
+        fgraph.replay()
+    b.record()
+    b.synchronize()
+    fused_ms = a.elapsed_time(b) / reps
     out = {"batch": batch, "batches_per_graph": nbatch, "launches_per_graph": nbatch * 3,
            "graph_persons_per_s": batch * nbatch / (graph_ms * 1e-3), "graph_us_per_batch_step": 1e3 * graph_ms / nbatch,
            "single_batch_step_latency_us": 1e6 * statistics.median(lat[5:]),
-           "note": "batch-128 steps are launch-latency bound (26.7 MB per tensor = 4 us at the HBM roofline)"}
-    del graph, paths, sets
+           "fused_graph_us_per_batch_step": 1e3 * fused_ms / nbatch,
+           "fused_graph_persons_per_s": batch * nbatch / (fused_ms * 1e-3),
+           "note": "batch-128 steps are launch-latency bound (26.7 MB per tensor = 4 us at the HBM roofline); "
+                   "fused_* = fused encode+loss+acc kernel + decode, 2 launches per batch"}
+    del graph, fgraph, paths, sets
     torch.cuda.empty_cache()
     return out
 
