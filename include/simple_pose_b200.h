@@ -86,7 +86,9 @@ int sp_encode_basic_f32(const float* joints, const float* table, float* targets,
  * One pass over pred/target; deterministic two-stage reduction in float64.
  * workspace: sp_mse_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED ONCE by the caller
  * before first use (the kernel restores the zero state before it finishes, so the same
- * buffer can be reused by later calls on the same stream without re-zeroing).
+ * buffer can be reused by later calls on the same stream without re-zeroing). It holds the
+ * block partials, a completion ticket and -- for sp_encode_mse_fwd_bwd_f32 -- the grid-wide work
+ * counter, so calls that may run CONCURRENTLY (different streams) need separate workspaces.
  */
 size_t sp_mse_workspace_bytes(void);
 int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const float* mask,
