@@ -72,6 +72,23 @@ def test_argument_errors_without_gpu(lib):
     assert lib.sp_decode_f32(16, None, None, None, 16, 24, 16, None, 1, 17, 64, 48, 11, 0, None) == -2   # misaligned coords
     assert lib.sp_mse_fwd_bwd_f32(16, 16, 16, 16, 16, 16, 8, 1, 17, 3072, 1.0, 0, None) == -3             # workspace too small
     assert lib.sp_oks_nms_f64(16, 16, 16, 16, None, 16, 16, 4, 1, 16, 4, 0.9, 0, 0.0, None) == -1         # K != 17 w/o sigmas
+    # the entry points added for the callers either side of the path and the workspace decode
+    assert lib.sp_decode_workspace_bytes() == 16
+    assert lib.sp_decode_ws_f32(16, None, None, None, 16, 16, 16, None, 1, 17, 64, 48, 11, 0, None, 16, None) == -1    # no workspace
+    assert lib.sp_decode_ws_f32(16, None, None, None, 16, 16, 16, None, 1, 17, 64, 48, 11, 0, 16, 8, None) == -3       # too small
+    assert lib.sp_decode_ws_f32(16, None, None, None, 16, 16, 16, None, 1, 17, 64, 48, 11, 0, 24, 16, None) == -2      # misaligned
+    assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 1, 17, 64, 48, 11, 4, None) == -1                  # unknown mode
+    assert lib.sp_train_geometry_f32(None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                     1, 17, 192, 256, 48, 64, 1.25, None) == -1
+    assert lib.sp_train_geometry_f32(16, None, 16, None, None, 16, None, 16, None, None, None, None, None, None,
+                                     1, 17, 192, 256, 48, 64, 1.25, None) == -1                                        # flip w/o img_w / perm
+    assert lib.sp_train_geometry_f32(16, None, 16, None, None, None, None, 16, None, None, None, None, None, None,
+                                     1, 17, 192, 0, 48, 64, 1.25, None) == -1
+    assert lib.sp_train_geometry_f32(None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                     0, 17, 192, 256, 48, 64, 1.25, None) == 0
+    assert lib.sp_transform_joints_f32(16, None, None, None, None, 16, 1, 17, None) == -1                              # in place
+    assert lib.sp_transform_joints_f32(16, None, 16, None, None, 32, 1, 17, None) == -1                                # flip w/o img_w / perm
+    assert lib.sp_center_scale_rot_affine_f64(16, 16, None, None, None, None, 1, 48, 64, None) == -1                   # no output
     # empty batches are a no-op success
     assert lib.sp_encode_f32(None, None, None, 0, 17, 64, 48, 2.0, None) == 0
     assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 0, 17, 64, 48, 11, 0, None) == 0
@@ -93,6 +110,24 @@ def test_no_cpu_fallback():
         JointsMSELoss()(torch.zeros(1, 17, 8, 8), torch.zeros(1, 17, 8, 8), torch.ones(1, 17))
     with pytest.raises(RuntimeError, match="no CPU path"):
         oks_nms(np.zeros((2, 17, 3)), np.array([.5, .4]), np.ones(2), 0.9)
+    from simple_pose_b200.commons.transforms import train_geometry, train_targets, BasicSimpleTransform
+    from simple_pose_b200.commons import joint_utils as ju
+    from simple_pose_b200.metrics.pose_metrics import DarkPoseOriginalKeyPointDecoder
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        train_geometry(np.zeros((2, 4)), np.zeros((2, 17, 3), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        train_targets(np.zeros((2, 4)), np.zeros((2, 17, 3), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        BasicSimpleTransform().joint_targets(np.zeros((2, 4)), np.zeros((2, 17, 3), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ju.get_affine_transform(np.zeros(2, np.float32), np.ones(2, np.float32), 30.0, (48, 64))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ju.flip_joints(np.zeros((4, 8, 3), np.uint8), np.zeros((17, 3), np.float32), [[1, 2]])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ju.affine_transform_batch(np.zeros((17, 3), np.float32), np.zeros((2, 3)))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DarkPoseOriginalKeyPointDecoder()(torch.zeros(1, 17, 64, 48), torch.zeros(1, 2, 3))
+    assert ju.center_scale_to_box(np.array([10.0, 20.0], np.float32), np.array([4.0, 8.0], np.float32)) == (8.0, 16.0, 12.0, 24.0)
 
 
 def test_missing_extension_is_loud(monkeypatch, tmp_path):
