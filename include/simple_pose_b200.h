@@ -192,6 +192,12 @@ int sp_rescore_f64(const double* kps, const double* box_scores, double* scores,
 int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps,
                     int N, int K, void* stream);
 
+/* Result table of the sharded evaluation (eval.py:186-196 as one array instead of per-person dicts):
+ * rows [N, 3K+2] f32 = (x, y, conf) * K from coords [N,K,2] / maxval [N,K], then the keep flag
+ * (keep [N] u8, NULL = 0) and the rescored score (scores [N] f64, NULL = 0). */
+int sp_pack_rows_f32(const float* coords, const float* maxval, const unsigned char* keep, const double* scores,
+                     float* rows, int N, int K, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Eval-side caller of the decoder ("next": the data either side of the path):
  * BasicTransform.__call__ without the image warp, datasets/naive_data.py:44-56 =

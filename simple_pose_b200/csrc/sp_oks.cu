@@ -216,7 +216,43 @@ pack_kps_kernel(const float* __restrict__ coords, const float* __restrict__ maxv
     out[3 * i + 2] = (double)maxval[i];
 }
 
+// ShardedPoseEvaluator result rows: [n, 3K+2] f32 = (x, y, conf) * K, keep flag, rescored score
+// (what eval.py:186-196 writes per kept person, kept as one table for the all-gather)
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ coords, const float* __restrict__ maxval, const unsigned char* __restrict__ keep,
+                 const double* __restrict__ scores, float* __restrict__ rows, long long n, int K) {
+    const int width = 3 * K + 2;
+    const long long total = n * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / width;
+        const int c = (int)(i - p * width);
+        float v;
+        if (c < 3 * K) {
+            const int k = c / 3, e = c - 3 * k;
+            v = (e < 2) ? coords[(p * K + k) * 2 + e] : maxval[p * K + k];
+        } else if (c == 3 * K) {
+            v = keep ? (float)keep[p] : 0.f;
+        } else {
+            v = scores ? (float)scores[p] : 0.f;
+        }
+        rows[i] = v;
+    }
+}
+
 }  // namespace
+
+extern "C" int sp_pack_rows_f32(const float* coords, const float* maxval, const unsigned char* keep, const double* scores,
+                                float* rows, int N, int K, void* stream) {
+    SP_RETURN_IF(N < 0 || K <= 0, SP_ERR_BAD_ARGUMENT);
+    if (N == 0) return 0;
+    SP_RETURN_IF(!coords || !maxval || !rows, SP_ERR_BAD_ARGUMENT);
+    const long long total = (long long)N * (3 * K + 2);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sp_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pack_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords, maxval, keep, scores, rows, N, K);
+    return sp_launch_status();
+}
 
 extern "C" int sp_oks_iou_f64(const double* pick_kps, const double* cand_kps, const double* pick_area,
                               const double* cand_area, const double* sigmas, double* out,

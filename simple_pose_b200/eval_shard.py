@@ -8,8 +8,9 @@ person count), decodes and NMS-filters its own persons with the CUDA kernels, an
 exchange is one ``all_gather_into_tensor`` of the packed per-person results
 (K*3 + 2 float32 = 212 B per person at K = 17) over NCCL/NVLink.
 
-One process per GPU (``torchrun``); the same code runs under ``gloo`` on CPU tensors for the
-host-side logic tests (sharding, padding, ordering) -- the kernels themselves need CUDA.
+One process per GPU (``torchrun``); the sharding / padding / ordering logic (``shard_images``,
+``person_range``, ``gather_rows``) is device-agnostic and runs under ``gloo`` on CPU tensors in the
+host-side tests -- the kernels themselves (decode, NMS, ``pack_results``) need CUDA.
 """
 import numpy as np
 import torch
@@ -42,12 +43,19 @@ def person_range(seg_offsets, cuts, rank):
 
 
 def pack_results(coords, max_val, keep, scores):
-    """[n,K,2], [n,K,1], [n] uint8, [n] float -> float32 [n, 3K+2] rows (x,y,conf)*K, keep, score."""
-    n, k = coords.shape[0], coords.shape[1]
-    row = torch.empty((n, 3 * k + 2), dtype=torch.float32, device=coords.device)
-    row[:, :3 * k] = torch.cat([coords, max_val], dim=-1).reshape(n, 3 * k)
-    row[:, 3 * k] = keep.to(torch.float32)
-    row[:, 3 * k + 1] = scores.to(torch.float32)
+    """[n,K,2], [n,K,1], [n] uint8, [n] float -> float32 [n, 3K+2] rows (x,y,conf)*K, keep, score:
+    one launch of ``sp_pack_rows_f32`` (CUDA tensors only, like every kernel of the path)."""
+    from . import _abi
+    dev = _abi.require_cuda(coords, max_val, keep, scores)
+    n, k = int(coords.shape[0]), int(coords.shape[1])
+    row = torch.empty((n, 3 * k + 2), dtype=torch.float32, device=dev)
+    c = _abi.dense(coords, torch.float32)
+    m = _abi.dense(max_val, torch.float32)
+    kp = _abi.dense(keep, torch.uint8)
+    sc = _abi.dense(scores, torch.float64)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_pack_rows_f32(c.data_ptr(), m.data_ptr(), kp.data_ptr(), sc.data_ptr(), row.data_ptr(),
+                                               n, k, _abi.stream_ptr(dev)))
     return row
 
 

@@ -54,7 +54,9 @@ def _worker(rank, world, port, seg, table, out):
         conf = table[lo:hi, :, 2:].contiguous()
         keep = (torch.arange(lo, hi) % 3 == 0).to(torch.uint8)
         scores = torch.arange(lo, hi, dtype=torch.float64) * 0.5
-        rows = eval_shard.pack_results(coords, conf, keep, scores)
+        # row layout of eval_shard.pack_results (a CUDA kernel): (x, y, conf) * K, keep, score
+        rows = torch.cat([torch.cat([coords, conf], dim=-1).reshape(hi - lo, 3 * k), keep.float()[:, None],
+                          scores.float()[:, None]], dim=1)
         counts = [eval_shard.person_range(seg, cuts, r) for r in range(world)]
         full = eval_shard.gather_rows(rows, [b - a for a, b in counts])
         out[rank] = full.clone()

@@ -511,6 +511,21 @@ def test_pack_and_end_to_end_eval_chain(api):
     assert np.allclose(scores.cpu().numpy(), o_scores, rtol=1e-15, atol=0)
 
 
+def test_pack_rows_equals_torch_composition(api):
+    from simple_pose_b200.eval_shard import pack_results
+    g = torch.Generator().manual_seed(3)
+    for n, k in ((0, 17), (1, 17), (777, 17), (40, 5)):
+        coords = torch.randn(n, k, 2, generator=g).to(DEV)
+        conf = torch.rand(n, k, 1, generator=g).to(DEV)
+        keep = (torch.rand(n, generator=g) < 0.5).to(torch.uint8).to(DEV)
+        scores = torch.rand(n, generator=g, dtype=torch.float64).to(DEV)
+        rows = pack_results(coords, conf, keep, scores)
+        want = torch.cat([torch.cat([coords, conf], dim=-1).reshape(n, 3 * k), keep.float()[:, None], scores.float()[:, None]], dim=1)
+        assert rows.shape == (n, 3 * k + 2) and torch.equal(rows, want)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pack_results(coords.cpu(), conf.cpu(), keep.cpu(), scores.cpu())
+
+
 def test_errors_are_loud(api):
     with pytest.raises(RuntimeError):
         api.metrics.GaussTaylorKeyPointDecoder()(torch.zeros(1, 17, 64, 48), torch.zeros(1, 2, 3))   # CPU tensors
