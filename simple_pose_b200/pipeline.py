@@ -80,12 +80,21 @@ class HeatmapHotPath(object):
                                               stream))
 
     def step(self, joints, pred, trans_inv):
-        """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches. The decode is
-        issued between the two kernels that touch ``targets``: measured 2.5 % faster than
-        encode -> loss -> decode (1418 vs 1455 us for 8 x 1024 persons), same results."""
-        self.encode(joints)
-        self.decode(pred, trans_inv)
-        self.loss_fwd_bwd(pred)
+        """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches, two orders.
+        Large batches (targets do not fit in L2): encode, decode, loss -- the decode between the two
+        kernels that touch ``targets`` measured 2.5 % faster than encode -> loss -> decode (1418 vs
+        1455 us for 8 x 1024 persons). Small batches (targets <= 64 MB, e.g. the reference's batch 128 =
+        26.7 MB): decode, encode, loss -- the loss then finds the targets the encoder just wrote in the
+        126 MB L2 (encode + loss per 1024 persons: 199.9 -> 182.7 us at batch 128, 163.3 -> 155.5 us at
+        batch 256; no difference from batch 512 up, scratch/l2_pairs.py). Same results either way."""
+        if self.targets.numel() * 4 <= (64 << 20):
+            self.decode(pred, trans_inv)
+            self.encode(joints)
+            self.loss_fwd_bwd(pred)
+        else:
+            self.encode(joints)
+            self.decode(pred, trans_inv)
+            self.loss_fwd_bwd(pred)
         return self.loss, self.coords, self.maxval
 
     LAUNCHES_PER_STEP = 3
