@@ -151,13 +151,25 @@ def argmax_index(heat_map):
     return heat_map.reshape(b, k, h * w).max(dim=-1)[1]
 
 
+# cv::getGaussianKernel's fixed tables for sigma <= 0 and small odd sizes (OpenCV 4.x, imgproc/smooth;
+# the 9-tap row exists since 4.5). The reference only ever uses 11, which takes the closed form.
+_OPENCV_SMALL_GAUSSIAN = {
+    1: [1.0],
+    3: [0.25, 0.5, 0.25],
+    5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+    7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+    9: [4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256, 51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256],
+}
+
+
 def gaussian_taps(kernel_size=11):
-    """1-D taps of ``cv.getGaussianKernel(kernel_size, 0)`` for kernel_size >= 9
-    (metrics/pose_metrics.py:57): sigma = 0.3*((n-1)*0.5-1)+0.8, normalised
-    ``exp(-x^2/(2 sigma^2))`` in float64. For n = 11 (sigma = 2.0) the float32 outer
-    product is bit-equal to OpenCV 4.13's (checked in tests when cv2 is importable).
-    OpenCV uses fixed tables for n <= 7; the reference only ever uses 11."""
+    """1-D taps of ``cv.getGaussianKernel(kernel_size, 0)`` (metrics/pose_metrics.py:57): OpenCV's fixed
+    tables for n <= 9, else sigma = 0.3*((n-1)*0.5-1)+0.8 and the normalised ``exp(-x^2/(2 sigma^2))``
+    in float64. For n = 11 (sigma = 2.0) the float32 outer product is bit-equal to OpenCV 4.13's
+    (checked in the tests; the fuzzer compares 3..13)."""
     n = int(kernel_size)
+    if n in _OPENCV_SMALL_GAUSSIAN:
+        return np.array(_OPENCV_SMALL_GAUSSIAN[n], dtype=np.float64)
     sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8
     x = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
     g = np.exp(-(x * x) / (2.0 * sigma * sigma))

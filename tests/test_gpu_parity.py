@@ -234,6 +234,22 @@ def test_decode_vs_oracle(api, b, hw, noise):
     check_decode(api, hm, tinv, ref_img.numpy(), ref_hsp.numpy(), ref_max.numpy(), O.argmax_index(hm).numpy())
 
 
+@pytest.mark.parametrize("ksize", [3, 5, 7, 9, 13, 15])
+@pytest.mark.parametrize("hw", [(64, 48), (40, 36)])
+def test_decode_other_kernel_sizes(api, ksize, hw):
+    """GaussTaylorKeyPointDecoder(kernel_size != 11): OpenCV's fixed Gaussian tables (n <= 9) and the closed
+    form (n >= 13) through the run-time-ksize kernel path, against the restatement (itself pinned to the
+    reference for these sizes by oracle/fuzz_vs_reference.py)."""
+    h, w = hw
+    hm = synth.heatmaps(24, height=h, width=w, seed=700 + ksize, noise=0.01)
+    dec = api.metrics.GaussTaylorKeyPointDecoder(kernel_size=ksize)
+    assert np.array_equal(bits(dec.blur_weights.cpu().numpy()), bits(O.blur_weights(ksize)))
+    c, m, idx = dec.decode_with_index(hm.to(DEV))
+    oc, om = O.gauss_taylor_decode(hm, None, ksize, return_heatmap_space=True)
+    assert torch.equal(idx.cpu().long(), O.argmax_index(hm)) and torch.equal(m.cpu(), om)
+    assert (c.cpu() - oc).abs().max().item() <= 1e-4
+
+
 def test_decode_generic_path_matches_fast_path(api):
     hm = synth.heatmaps(16, seed=5).to(DEV)
     dec = api.metrics.GaussTaylorKeyPointDecoder()

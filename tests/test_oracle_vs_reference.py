@@ -144,3 +144,15 @@ def test_train_geometry_basic_transform(ref):
         o = O.train_sample_geometry(box, w, smp["joints"][i].numpy(), *draws, basic=True)
         assert np.array_equal(bits(kp.trans_inv), bits(o["trans_inv"])) and np.array_equal(bits(kp.joints), bits(o["joints_input"]))
         assert np.array_equal(bits(kp.heat_map), bits(o["heat_map"])) and np.array_equal(kp.mask, o["mask"]), i
+
+
+def test_randomised_pin_short():
+    """A short run of the randomised pin (oracle/fuzz_vs_reference.py: random shapes, sigmas, blur sizes
+    3-13, masks, NMS thresholds, visibility thresholds, rotations incl. 90 / -179.5 degrees): bit equality
+    on every row. The long form found the fixed OpenCV tables behind ``cv.getGaussianKernel(n <= 9, 0)``."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, "-m", "oracle.fuzz_vs_reference", "--seconds", "8", "--seed", "7"],
+                       capture_output=True, text=True, timeout=300,
+                       cwd=__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    assert p.returncode == 0 and "fuzz ok" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
