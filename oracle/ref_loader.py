@@ -111,3 +111,31 @@ def run_train_transform(ns, box, img_w, img_h, joints, scale_ratio, rot, flip, j
     draws = iter([float(scale_ratio), float(rot), 0.0 if flip else 0.9])
     with mock.patch.object(np.random, "uniform", side_effect=lambda *a, **k: next(draws)):
         return tr(kp)
+
+
+def run_eval_filter(kps, box_scores, areas, img_ids, in_vis_thre=0.2, oks_thre=0.9):
+    """The reference's own ``temp_read_in_and_filter`` (eval.py:153-197): writes the per-person records
+    the way ``predicts_by_pred`` does (eval.py:139-149: ``img_id``, ``score`` = box score, ``area``,
+    ``kps`` = 51 floats) into a scratch directory, runs the function there with the pycocotools
+    evaluation stubbed out, and returns the list of dicts it dumped (``image_id``, ``score``,
+    ``keypoints``) in its output order."""
+    import json
+    import tempfile
+    import numpy as np
+    load()                                           # sys.path + pycocotools stub
+    ev = importlib.import_module("eval")
+    records = [{"img_id": int(i), "score": float(s), "area": float(a), "kps": np.asarray(k, dtype=np.float64).reshape(-1).tolist()}
+               for k, s, a, i in zip(kps, box_scores, areas, img_ids)]
+    keep_eval, cwd = ev.eval_kps, os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        try:
+            os.chdir(tmp)
+            with open("predicts_kps_temp.json", "w") as fh:
+                json.dump(records, fh)
+            ev.eval_kps = lambda *a, **k: None
+            ev.temp_read_in_and_filter(in_vis_thre=in_vis_thre, oks_thre=oks_thre)
+            with open("filter_kps_predicts.json") as fh:
+                return json.load(fh)
+        finally:
+            ev.eval_kps = keep_eval
+            os.chdir(cwd)

@@ -156,3 +156,35 @@ def test_randomised_pin_short():
                        capture_output=True, text=True, timeout=300,
                        cwd=__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
     assert p.returncode == 0 and "fuzz ok" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
+
+
+@pytest.mark.parametrize("vis,thr", [(0.2, 0.9), (0.5, 0.8), (0.05, 0.95)])
+def test_eval_rescoring_and_nms_through_the_reference_function(ref, vis, thr):
+    """A9: the reference's own temp_read_in_and_filter (eval.py:153-197, JSON in / JSON out, COCO evaluation
+    stubbed) against the restatement's rescore_and_nms: kept persons, their order, scores and keypoints."""
+    kps, box, area, seg = synth.nms_groups(25, mean_group=9.0, seed=int(vis * 100))
+    kps, box, area, seg = kps.numpy(), box.numpy(), area.numpy(), seg.numpy()
+    img_ids = np.repeat(np.arange(25) * 7 + 3, np.diff(seg))
+    out = ref_loader.run_eval_filter(kps, box, area, img_ids, vis, thr)
+    keep, scores, picks = O.rescore_and_nms(kps, box, area, seg, vis, thr)
+    flat = [i for p in picks for i in p]
+    assert len(out) == len(flat) == int(keep.sum())
+    for rec, i in zip(out, flat):
+        assert rec["image_id"] == int(img_ids[i]) and rec["category_id"] == 1
+        assert rec["score"] == scores[i]
+        assert rec["keypoints"] == kps[i].reshape(-1).tolist()
+
+
+def test_kps_to_dict_host_formatting(ref):
+    """A10: the drop-in's batched formatting (one device->host copy) against the reference's per-person
+    loop (metrics/pose_metrics.py:172-179) on host tensors: identical lists of dicts."""
+    from simple_pose_b200.metrics.pose_metrics import kps_to_dict_
+    g = torch.Generator().manual_seed(0)
+    for _ in range(50):
+        n = 9
+        pred = torch.randn(n, 17, 2, generator=g) * 100
+        sc = torch.rand(n, 17, 1, generator=g)
+        a, b = [], []
+        ref.kps_to_dict_(pred, sc, list(range(100, 100 + n)), a)
+        kps_to_dict_(pred, sc, list(range(100, 100 + n)), b)
+        assert a == b
