@@ -23,7 +23,7 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpad = (W + 1) & ~1;                        // keeps ey 16-byte aligned
-    double* ex = factors + (size_t)warp * (wpad + H);
+    double* ex = factors + (size_t)warp * (wpad + ((H + 1) & ~1));   // even stride: every warp's ex stays 16-byte aligned (odd H)
     double* ey = ex + wpad;
     const int hw = H * W;
     const long long total_warps = (long long)gridDim.x * WARPS;
@@ -148,7 +148,7 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     // 0.934 -> 0.954 of the HBM peak at 64x48 x 1024, 0.862 -> 0.900 at 96x72 x 512, 10.6 -> 7.9 us at 64x48 x 128.
     int warps = sp_env_int("SP_ENCODE_WARPS", 2);
     if (warps != 2 && warps != 4 && warps != 8) warps = 2;
-    const size_t smem = (size_t)warps * (wpad + H) * sizeof(double);
+    const size_t smem = (size_t)warps * (wpad + ((H + 1) & ~1)) * sizeof(double);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
     const bool vec4 = (W % 4 == 0) && sp_aligned16(targets);
     // A unit of work is a range of ~32 rows of one map, one warp each (parts = H / 32 per map). Whole

@@ -304,7 +304,7 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpad = (io.W + 1) & ~1;
-    double* ex = factors + (size_t)warp * (wpad + io.H);
+    double* ex = factors + (size_t)warp * (wpad + ((io.H + 1) & ~1));   // even stride: 16-byte aligned ex for every warp (odd H)
     double* ey = ex + wpad;
     const int hw = io.H * io.W;
     const int total_warps = gridDim.x * kWarps;
@@ -351,7 +351,7 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     const int chunks_per_map = nq / chunk_quads;                 // host guarantees divisibility
     const uint32_t chunk_bytes = (uint32_t)chunk_quads * 16u;
     const int wpad = (io.W + 1) & ~1;
-    const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
+    const size_t fac_bytes = (size_t)(wpad + ((io.H + 1) & ~1)) * sizeof(double);   // multiple of 16 (odd H too)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * ring;
     volatile int* fifo = reinterpret_cast<int*>(smem_raw + 1024) + warp * kFifo;
     int& next_map = *reinterpret_cast<int*>(smem_raw + 1024 + 2048);
@@ -754,7 +754,7 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
 #endif
     const int hw = io.H * io.W;
     const int wpad = (io.W + 1) & ~1;
-    const size_t fac_bytes = (size_t)(wpad + io.H) * sizeof(double);
+    const size_t fac_bytes = (size_t)(wpad + ((io.H + 1) & ~1)) * sizeof(double);   // multiple of 16 (odd H too)
     volatile int* fifo = reinterpret_cast<int*>(smem_raw + 1024) + warp * kFifo;
     double* ex = reinterpret_cast<double*>(smem_raw + kRingHeader + warp * fac_bytes);
     double* ey = ex + wpad;
@@ -892,7 +892,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     const float norm = (float)(2.0 / count);
     const float half_scale = 0.5f * grad_scale;
     const int wpad = (W + 1) & ~1;
-    const size_t fac_bytes = (size_t)(wpad + H) * sizeof(double);
+    const size_t fac_bytes = (size_t)(wpad + ((H + 1) & ~1)) * sizeof(double);          // multiple of 16 (odd H too)
     MapIo io;
     io.joints = joints; io.pred = pred; io.grad = grad; io.targets = targets; io.weights = weights;
     io.pred_xy = reinterpret_cast<float2*>(pred_xy); io.label_xy = reinterpret_cast<float2*>(label_xy);

@@ -64,7 +64,8 @@ def test_encode_golden(api, golden):
             assert np.array_equal(bits(t.cpu().numpy()), bits(g["targets_e"]))
 
 
-@pytest.mark.parametrize("shape,persons", [((48, 64), 128), ((72, 96), 32), ((50, 30), 8), ((4, 4), 3), ((132, 20), 4)])
+@pytest.mark.parametrize("shape,persons", [((48, 64), 128), ((72, 96), 32), ((50, 30), 8), ((4, 4), 3), ((132, 20), 4),
+                                           ((48, 63), 5), ((20, 7), 3), ((36, 33), 4)])      # odd H: per-warp factor slices stay 16-byte aligned
 def test_encode_vs_oracle(api, shape, persons):
     w, h = shape
     joints = synth.joints(persons, height=h, width=w, seed=123)
@@ -90,7 +91,7 @@ def test_encode_cta_sizes_agree(api, warps):
 
 
 @pytest.mark.parametrize("parts", ["1", "2", "3", "4", "64", "200"])
-@pytest.mark.parametrize("shape", [(48, 64), (72, 96), (50, 30), (132, 20)])
+@pytest.mark.parametrize("shape", [(48, 64), (72, 96), (50, 30), (132, 20), (48, 63)])
 def test_encode_row_parts_agree(api, parts, shape):
     """A map may be split into row ranges, one warp each (small launches do so by default): every split,
     including uneven ones and more parts than rows, writes the same bits as one warp per map."""
@@ -591,7 +592,8 @@ def test_heat_map_acc_golden_and_oracle(api, golden):
     assert api.metrics.HeatMapAcc()(z, z).item() == 0.0
 
 
-@pytest.mark.parametrize("b,hw,noise", [(128, (64, 48), 0.05), (24, (96, 72), 0.3), (6, (16, 12), 0.5), (5, (10, 6), 0.2)])
+@pytest.mark.parametrize("b,hw,noise", [(128, (64, 48), 0.05), (24, (96, 72), 0.3), (6, (16, 12), 0.5), (5, (10, 6), 0.2),
+                                        (4, (31, 24), 0.2), (3, (63, 48), 0.1), (5, (9, 64), 0.2)])     # odd H
 def test_fused_encode_loss_acc(api, b, hw, noise):
     """EncodeJointsMSELoss(pred, joints) == reference loss/grad on reference-encoded targets, and its
     accuracy == HeatMapAcc()(pred*mask, target*mask) (solver :106-107,123-124)."""
