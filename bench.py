@@ -452,31 +452,47 @@ def small_batch_numbers(device, height, width, batch=128, nbatch=64):
     return out
 
 
+def single_device_rows(es, lo, hi, device, height, width):
+    """Result rows of global persons [lo, hi) (image-aligned) computed on ONE device with NO collective,
+    through the stand-alone kernels (box affine, decode, float64 pack, rescore, NMS) -- a different code
+    path from the fused rows kernels ``ShardedPoseEvaluator`` runs. Returns (keypoints f32 [n, 3K],
+    keep bool [n], scores f64 [n])."""
+    import numpy as np
+    from simple_pose_b200.datasets.naive_data import box_affines, pack_keypoints, rescore_and_nms
+    from simple_pose_b200.metrics.pose_metrics import GaussTaylorKeyPointDecoder
+    i0, i1 = int(np.searchsorted(es.seg, lo)), int(np.searchsorted(es.seg, hi))
+    assert es.seg[i0] == lo and es.seg[i1] == hi
+    hm = es.heatmaps(lo, hi, device)
+    aff = box_affines(es.boxes[lo:hi].to(device), (4 * width, 4 * height), (width, height))
+    xy, conf = GaussTaylorKeyPointDecoder()(hm, aff["trans_inv"])
+    kps = pack_keypoints(xy, conf)
+    seg = (es.seg[i0:i1 + 1] - lo).astype(np.int32)
+    keep, scores, _ = rescore_and_nms(kps, es.box_scores[lo:hi].to(device), aff["area"].double(), seg)
+    return torch.cat([xy, conf], dim=-1).reshape(hi - lo, -1), keep.bool(), scores
+
+
 def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5):
-    """BASELINE config 5: a COCO-val-sized eval job (~104 k person boxes in ~5 k images) through
-    ``ShardedPoseEvaluator``: per rank box -> affine, GaussTaylor decode, rescoring and OKS-NMS of its
-    image-aligned shard, then one NCCL all-gather of the packed result rows. Fixed total work
-    (strong scaling); device-timed, max over ranks."""
+    """BASELINE config 5: a COCO-val-sized eval job (~104 k person boxes in ~5 k images, 30 % of them
+    near-duplicate detections) through ``ShardedPoseEvaluator``: per rank box -> affine, then per chunk
+    GaussTaylor decode into the result rows, rescoring + OKS-NMS on the rows, NCCL all-gather of the chunk
+    (in place, overlapped with the next chunk's decode). Fixed total work (strong scaling); device-timed,
+    max over ranks. The content of the job depends on the person index only, so ``table_checksum`` must be
+    the same number at every N, and ``matches_single_device`` reports a bit-for-bit comparison of the
+    gathered table with a collective-free recompute (this rank's first and last image and a fixed slice
+    of >= 512 persons around the middle of the global table) through the stand-alone kernels."""
     import numpy as np
     import torch.distributed as dist
     from simple_pose_b200 import synth
-    from simple_pose_b200.eval_shard import ShardedPoseEvaluator
-    g = torch.Generator().manual_seed(12345)
-    images = int(persons / (1.0 + mean_group))
-    sizes = 1 + torch.poisson(torch.full((images,), float(mean_group)), generator=g).long()
-    seg = np.zeros(images + 1, dtype=np.int64)
-    seg[1:] = np.cumsum(sizes.numpy())
-    total = int(seg[-1])
+    from simple_pose_b200.eval_shard import ShardedPoseEvaluator, row_keep, row_keypoints, row_scores
+    es = synth.EvalSet(persons=persons, mean_group=mean_group, height=height, width=width)
+    total, images = es.persons, es.images
     ev = ShardedPoseEvaluator()
-    ev.plan(seg)
+    ev.plan(es.seg)
     lo, hi = ev.my_persons()
     n = hi - lo
-    hm = torch.empty((n, 17, height, width), dtype=torch.float32, device=device)
-    for a in range(0, n, 8192):
-        b = min(n, a + 8192)
-        hm[a:b] = synth.heatmaps(b - a, height=height, width=width, seed=777 + lo + a, device=device)
-    boxes = synth.detection_boxes(total, seed=778)[lo:hi].to(device)
-    box_scores = ((torch.randperm(total, generator=g).double() + 0.5) / total)[lo:hi].to(device)
+    hm = es.heatmaps(lo, hi, device)
+    boxes = es.boxes[lo:hi].to(device)
+    box_scores = es.box_scores[lo:hi].to(device)
     torch.cuda.synchronize(device)
     times = []
     for r in range(reps + 2):
@@ -485,7 +501,7 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
         torch.cuda.synchronize(device)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        table = ev.run(hm, None, box_scores, None, boxes=boxes, input_shape=(4 * width, 4 * height))
+        raw = ev.run(hm, None, box_scores, None, boxes=boxes, input_shape=(4 * width, 4 * height), compact=False)
         b.record()
         b.synchronize()
         ms = a.elapsed_time(b)
@@ -496,12 +512,47 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
         if r >= 2:
             times.append(ms)
     ms = statistics.median(times)
-    kept = int(table[:, 3 * 17].sum().item())
-    del hm, table
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    table = raw.rows()
+    b.record()
+    b.synchronize()
+    compact_ms = a.elapsed_time(b)
+    kept = int(row_keep(table).sum().item())
+    checksum = synth.table_checksum(table)
+    del hm
+    torch.cuda.empty_cache()
+    # ---- parity of the sharded, NCCL-gathered table against a collective-free recompute on this device
+    seg = es.seg
+    mid = int(np.searchsorted(seg, total // 2)) - 12
+    mid = max(0, min(mid, images - 1))
+    end = mid
+    while end < images and seg[end] - seg[mid] < 512:
+        end += 1
+    i_first, i_last = int(ev.cuts[rank]), int(ev.cuts[rank + 1]) - 1
+    ranges = [(int(seg[mid]), int(seg[end]))]
+    if i_last >= i_first:
+        ranges += [(int(seg[i_first]), int(seg[i_first + 1])), (int(seg[i_last]), int(seg[i_last + 1]))]
+    ok, checked = True, 0
+    for (p0, p1) in ranges:
+        kp, keep, scores = single_device_rows(es, p0, p1, device, height, width)
+        part = table[p0:p1]
+        ok = ok and torch.equal(row_keypoints(part).reshape(p1 - p0, -1), kp) and torch.equal(row_keep(part), keep) \
+            and torch.equal(row_scores(part), scores)
+        checked += p1 - p0
+    flag = torch.tensor([1 if ok else 0, checksum & 0x7fffffff, (checksum >> 31) & 0x7fffffff], dtype=torch.int64, device=device)
+    if world > 1:
+        lo_f, hi_f = flag.clone(), flag.clone()
+        dist.all_reduce(lo_f, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_f, op=dist.ReduceOp.MAX)
+        ok = bool(lo_f[0].item() == 1) and bool(torch.equal(lo_f[1:], hi_f[1:]))      # every rank matches AND holds the same table
+    del table
     torch.cuda.empty_cache()
     return {"workload": "cfg5: box->affine + GaussTaylor decode + rescoring + OKS-NMS + all-gather of result rows",
-            "persons": total, "images": images, "n_gpus": world, "scaling": "strong", "ms": ms,
-            "persons_per_s": total / (ms * 1e-3), "kept_after_nms": kept,
+            "persons": total, "images": images, "duplicate_detections": es.duplicates, "n_gpus": world, "scaling": "strong",
+            "ms": ms, "persons_per_s": total / (ms * 1e-3), "kept_after_nms": kept, "chunks_per_rank": int(ev.ccuts.shape[1] - 1),
+            "compact_ms": compact_ms, "table_checksum": "%016x" % (checksum & 0xffffffffffffffff),
+            "matches_single_device": bool(ok), "persons_rechecked_per_rank": checked,
             "decode_read_GBps_per_gpu": (n * (17 * height * width * 4)) / (ms * 1e-3) / 1e9}
 
 
@@ -682,6 +733,8 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
+        if eval_job is not None and not eval_job["matches_single_device"]:
+            raise SystemExit(3)
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -699,6 +752,8 @@ def run_ours(args):
         "train_side": train_side,
     }
     print(json.dumps(line), flush=True)
+    if eval_job is not None and not eval_job["matches_single_device"]:
+        raise SystemExit("bench.py: the sharded eval table differs from the single-device recompute")
 
 
 def run_e2e(args, device, world, rank, P, B, H, W):

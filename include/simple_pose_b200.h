@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 1
+#define SP_ABI_VERSION 2
 
 #define SP_ERR_BAD_ARGUMENT  (-1)   /* null pointer, non-positive size, unsupported value  */
 #define SP_ERR_BAD_ALIGNMENT (-2)   /* a base pointer is not 16-byte aligned                */
@@ -49,6 +49,10 @@ int sp_abi_version(void);
 const char* sp_error_string(int code);
 /* SM count and compute capability of the current device (host-side query). */
 int sp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* The SP_* tuning variables (DESIGN.md "Tuning knobs") are read from the environment once per process,
+ * at the first call into the library -- a launch never calls getenv. This re-reads them (tests and
+ * parameter sweeps change a variable and reload). None of them changes results. */
+int sp_reload_tuning(void);
 
 /* ------------------------------------------------------------------------------------------
  * A1  RefineSimpleTransform.get_heat_map(joints, sigma=2.0, shape=(48, 64))
@@ -158,6 +162,16 @@ int sp_decode_ws_f32(const float* hm, const float* hm_flip, const int* perm,
                      int B, int K, int H, int W, int ksize, int mode,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Decoder writing straight into the eval result table (eval.py:138-149 without the per-person
+ * tolist()/JSON round trip): rows[b * row_stride + 3*k + {0,1,2}] = (x, y, peak value) of joint k of
+ * person b; row_stride >= 3K floats (sp_eval_rows_nms_f32 wants >= 3K+3 and fills the remaining three).
+ * coords / maxval (layouts as above) may be given as well or be NULL. Workspace as sp_decode_ws_f32. */
+int sp_decode_rows_f32(const float* hm, const float* hm_flip, const int* perm,
+                       const float* trans_inv, const float* blur_w,
+                       float* rows, int row_stride, float* coords, float* maxval,
+                       int B, int K, int H, int W, int ksize, int mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * A7  oks_iou(pick_kps, candi_kps, pick_area, candi_area, sigmas=None, in_vis_thresh=None)
  *     datasets/naive_data.py:120-150.  All float64.
@@ -197,6 +211,24 @@ int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps,
  * (keep [N] u8, NULL = 0) and the rescored score (scores [N] f64, NULL = 0). */
 int sp_pack_rows_f32(const float* coords, const float* maxval, const unsigned char* keep, const double* scores,
                      float* rows, int N, int K, void* stream);
+
+/* A9 + A8 + result packing in ONE launch, the whole of eval.py:153-197 after the decoder: rows [N, row_stride]
+ * f32 hold (x, y, conf) * K per person (sp_decode_rows_f32); per image (seg [I+1] i32) every person is
+ * rescored (box_scores [N] f64 * mean(conf > in_vis_thre)), the greedy OKS-NMS of datasets/naive_data.py:153-173
+ * runs on those scores with the float32 keypoints widened to float64 (exactly the doubles the reference
+ * reads back from its JSON file), and the rows are completed in place:
+ *   rows[i, 3K] = 1.0f if kept else 0.0f;  rows[i, 3K+1], rows[i, 3K+2] = low, high 32 bits of the float64
+ *   score (reinterpret the two floats as one little-endian double: the score is NOT narrowed to float32).
+ * areas: float64 [N] (areas_f64) or float32 [N] (areas_f32, what sp_box_affine_f64 writes); one non-NULL.
+ * rank [N] i32 out (nullable) as in sp_oks_nms_f64. max_seg >= largest image. in_vis_thresh=None semantics. */
+int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                         const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                         int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, void* stream);
+
+/* A10 kps_to_dict_ (metrics/pose_metrics.py:172-179) as one table for a single device->host copy:
+ * rows [N, 3K+1] f32 = (x, y, conf) * K from coords [N,K,2] / maxval [N,K], then the person score
+ * mean(conf) + max(conf) (mean accumulated in float64, rounded once; NaN propagates). */
+int sp_person_rows_f32(const float* coords, const float* maxval, float* rows, int N, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Eval-side caller of the decoder ("next": the data either side of the path):

@@ -585,3 +585,12 @@ def train_sample_geometry(box, img_w, joints, scale_ratio=1.0, rot=0.0, flip=Fal
     return {"center": center, "scale": scale, "img_trans": img_trans, "joint_trans": joint_trans,
             "trans_inv": trans_inv, "joints_input": joints_input, "joints_hm": joints_hm,
             "heat_map": heat_map, "mask": mask}
+
+
+def kps_to_dict(predicts, scores, img_ids, out_list):
+    """``kps_to_dict_`` (metrics/pose_metrics.py:172-179): per person, score = mean + max of the joint peaks
+    (float32 torch reductions over the [K,1] slice), keypoints = (x, y, peak) * K as Python floats."""
+    for pd, sc, img_id in zip(predicts, scores, img_ids):
+        out_list.append({"image_id": img_id, "score": float((sc.mean() + sc.max()).item()), "category_id": 1,
+                         "keypoints": torch.cat([pd, sc], dim=-1).reshape(-1).cpu().tolist()})
+

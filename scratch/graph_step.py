@@ -37,6 +37,8 @@ for name, fn in (("3-kernel", step), ("fused+decode", step_fused)):
         fn()
     graph = timeit(g.replay)
     os.environ["SP_NO_PDL"] = "1"
+    __import__("simple_pose_b200")._abi.reload_tuning()
     nopdl = timeit(fn)
     del os.environ["SP_NO_PDL"]
+    __import__("simple_pose_b200")._abi.reload_tuning()
     print("%-14s eager %.1f us  graph %.1f us  eager-no-PDL %.1f us  -> %.2f M persons/s (graph)" % (name, eager * 1e3, graph * 1e3, nopdl * 1e3, P / graph / 1e3))

@@ -36,6 +36,7 @@ def grouped(seq, n=40):
     return a.elapsed_time(b) / n * 1e3
 for pdl in ("0",):
     os.environ["SP_NO_PDL"] = pdl
+    __import__("simple_pose_b200")._abi.reload_tuning()
     r = {"E": timeit([E_]), "L": timeit([L_]), "D": timeit([D_]), "EL": timeit([E_, L_]), "LD": timeit([L_, D_]), "ED": timeit([E_, D_]),
          "DE": timeit([D_, E_]), "ELD": timeit([E_, L_, D_]), "EDL": timeit([E_, D_, L_]), "DEL": timeit([D_, E_, L_]), "grouped E*,L*,D*": grouped([E_, L_, D_]), "grouped D*,E*,L*": grouped([D_, E_, L_]), "grouped E*,D*,L*": grouped([E_, D_, L_])}
     print("SP_NO_PDL=" + pdl, {k: round(v, 1) for k, v in r.items()})

@@ -13,7 +13,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from simple_pose_b200 import synth  # noqa: E402
+from simple_pose_b200 import synth, _abi  # noqa: E402
 from simple_pose_b200.pipeline import HeatmapHotPath, ALGO_BYTES  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -60,6 +60,7 @@ for hw in args.hw.split(","):
                 k, v = kv.split("=")
                 saved[k] = os.environ.get(k)
                 os.environ[k] = v
+            _abi.reload_tuning()
             for name in args.ops.split(","):
                 fn = ops[name]
                 for i in range(nb):
@@ -85,5 +86,6 @@ for hw in args.hw.split(","):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+            _abi.reload_tuning()
         del sets, flips, paths
         torch.cuda.empty_cache()

@@ -20,6 +20,7 @@ c_flt = ctypes.c_float
 c_size = ctypes.c_size_t
 c_ll = ctypes.c_longlong
 
+ABI_VERSION = 2
 SP_DECODE_GAUSS_TAYLOR, SP_DECODE_ARGMAX, SP_DECODE_BASIC, SP_DECODE_DARK_ORIGINAL = 0, 1, 2, 3
 SP_MSE_SKIP_MASKED = 1
 SP_BOX_XYXY, SP_BOX_XYWH = 0, 1
@@ -29,6 +30,7 @@ SIGNATURES = {
     "sp_abi_version": (c_int, []),
     "sp_error_string": (ctypes.c_char_p, [c_int]),
     "sp_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "sp_reload_tuning": (c_int, []),
     "sp_encode_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_dbl, c_void]),
     "sp_encode_basic_f32": (c_int, [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int, c_void]),
     "sp_mse_workspace_bytes": (c_size, []),
@@ -42,6 +44,11 @@ SIGNATURES = {
     "sp_decode_workspace_bytes": (c_size, []),
     "sp_decode_ws_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_size, c_void]),
+    "sp_decode_rows_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_void, c_void,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_size, c_void]),
+    "sp_eval_rows_nms_f32": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_void,
+                                     c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
+    "sp_person_rows_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void]),
     "sp_oks_iou_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_dbl, c_void]),
     "sp_oks_nms_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void,
                                c_int, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_void]),
@@ -81,10 +88,15 @@ def lib():
             fn = getattr(handle, name)      # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.sp_abi_version() != 1:
+        if handle.sp_abi_version() != ABI_VERSION:
             raise ExtensionMissing("simple_pose_b200: ABI version mismatch, rebuild the library")
         _lib = handle
         return _lib
+
+
+def reload_tuning():
+    """Re-read the SP_* tuning variables from ``os.environ`` (the library reads them once per process)."""
+    check(lib().sp_reload_tuning())
 
 
 def check(code):
@@ -146,13 +158,29 @@ _scratch = {}
 def scratch(device, stream_id, nbytes, tag):
     """Zero-initialised device scratch per (tag, device, stream) for the kernels that keep a work
     counter / reduction workspace there; the kernels restore the zero state, calls on one stream
-    are ordered, so one buffer per stream is enough."""
+    are ordered, so one buffer per stream is enough. Callers that may run concurrently on ONE stream id
+    (two host threads sharing a stream) must serialise themselves -- the C ABI documents the same rule."""
     key = (tag, device.index, stream_id)
     buf = _scratch.get(key)
     if buf is None or buf.numel() * 8 < nbytes:
         buf = torch.zeros((int(nbytes) + 7) // 8, dtype=torch.int64, device=device)
         _scratch[key] = buf
     return buf
+
+
+def drop_scratch(device, stream_id=None):
+    """Forget the cached workspaces of a device (one stream or all). Called when a launch that uses one
+    fails: the "kernel restores the zero state" invariant assumes the kernel ran, so the next call must
+    start from a freshly zeroed buffer instead of stale tickets / work counters."""
+    for key in [k for k in _scratch if k[1] == device.index and (stream_id is None or k[2] == stream_id)]:
+        del _scratch[key]
+
+
+def check_ws(code, device, stream_id):
+    """``check`` for calls that were handed a cached workspace."""
+    if code != 0:
+        drop_scratch(device, stream_id)
+    check(code)
 
 
 def device_info(device=None):

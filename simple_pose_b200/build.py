@@ -49,6 +49,8 @@ def find_nvcc():
 
 
 def build(force=False, verbose=False):
+    """Compiles every csrc/*.cu to an object file (in parallel) and links them into the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, LIBNAME + ".sha256")
     fp = _fingerprint()
@@ -56,12 +58,28 @@ def build(force=False, verbose=False):
         with open(stamp) as fh:
             if fh.read().strip() == fp:
                 return lib_path()
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib_path()] + _sources()
+    nvcc = find_nvcc()
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout)
+        return obj, proc.stdout
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, _sources()))
+    if verbose:
+        for _, out in results:
+            print(out)
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", lib_path()] + [obj for obj, _ in results]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout)
-    if verbose:
-        print(proc.stdout)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout)
     with open(stamp, "w") as fh:
         fh.write(fp)
     return lib_path()

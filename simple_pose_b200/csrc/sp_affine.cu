@@ -277,7 +277,7 @@ extern "C" int sp_box_affine_f64(const double* boxes, int box_format, float* cen
     SP_CUDA(sp_launch(box_affine_kernel, dim3((P + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
                       boxes, box_format == SP_BOX_XYWH ? 1 : 0, center, scale, area, trans_inv, trans_inv_f64, trans_f64, P,
                       w_h_ratio, (double)out_w, (double)out_h, scale_mult));
-    return sp_launch_status();
+    return 0;
 }
 
 static int center_scale_affine(const float* center, const float* scale, const double* rot_deg, float* trans_inv,
@@ -287,7 +287,7 @@ static int center_scale_affine(const float* center, const float* scale, const do
     SP_RETURN_IF(!center || !scale || (!trans_inv && !trans_inv_f64 && !trans_f64), SP_ERR_BAD_ARGUMENT);
     SP_CUDA(sp_launch(center_scale_affine_kernel, dim3((P + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
                       center, scale, rot_deg, trans_inv, trans_inv_f64, trans_f64, P, (double)out_w, (double)out_h));
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_center_scale_affine_f64(const float* center, const float* scale, float* trans_inv,
@@ -315,7 +315,7 @@ extern "C" int sp_train_geometry_f32(const double* boxes, const int* img_w, cons
                       static_cast<cudaStream_t>(stream), boxes, img_w, joints, scale_ratio, rot_deg, flip, perm, joints_hm,
                       joints_input, trans_inv, trans_inv_f64, img_trans_f64, center, scale, P, K,
                       (double)in_w / (double)in_h, (double)in_w, (double)in_h, (double)out_w, (double)out_h, scale_mult));
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_transform_joints_f32(const float* joints, const double* trans, const unsigned char* flip,
@@ -327,5 +327,5 @@ extern "C" int sp_transform_joints_f32(const float* joints, const double* trans,
     const long long rows = (long long)P * K;
     SP_CUDA(sp_launch(transform_joints_kernel, dim3((unsigned)((rows + 127) / 128)), dim3(128), 0,
                       static_cast<cudaStream_t>(stream), joints, trans, flip, img_w, perm, out, rows, K));
-    return sp_launch_status();
+    return 0;
 }

@@ -26,13 +26,31 @@ static inline int sp_sm_count() {
     return cached[dev];
 }
 
-static inline int sp_env_int(const char* name, int fallback) {
-    const char* v = getenv(name);
-    if (!v || !*v) return fallback;
-    return atoi(v);
-}
+// ---- tuning knobs ------------------------------------------------------------------------------
+// Read from the environment ONCE per process (first library call) into this table; a launch never
+// calls getenv. sp_reload_tuning() re-reads it (tests and scratch/ubench.py sweep a knob by setting
+// the variable and reloading). SP_UNSET = variable absent -> the launch code's own default.
+#define SP_UNSET (-2147483647 - 1)
+struct SpTuning {
+    int no_pdl;
+    int encode_warps, encode_parts;
+    int loss_force_ldg, loss_chunk_quads, loss_ring, loss_warps, loss_bulk_store;
+    int train_force_ldg, train_chunk_quads, train_no_tile, train_tile_cfg, train_depth, train_static_pct,
+        train_warps, train_ring, train_bulk_store;
+    int decode_force_generic, decode_warps, decode_stages, decode_grid_wide, decode_runtime_ksize;
+    int step_warps, step_no_fused;
+    int nms_serial;
+};
+const SpTuning& sp_tuning();                                     // sp_abi.cu
+static inline int sp_knob(int value, int fallback) { return value == SP_UNSET ? fallback : value; }
 
-static inline int sp_launch_status() { return (int)cudaGetLastError(); }
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size high-water mark)
+// instead of a driver call on every launch (sp_abi.cu).
+cudaError_t sp_ensure_dyn_smem(const void* func, size_t bytes);
+
+// Launch status of the triple-chevron launches: peek (do not clear errors that belong to other
+// users of the context, e.g. PyTorch kernels on the same device).
+static inline int sp_launch_status() { return (int)cudaPeekAtLastError(); }
 
 // Every kernel of the library is launched with programmatic dependent launch (PDL) allowed: its
 // CTAs may be scheduled as soon as CTAs of the previous kernel on the stream exit, which hides the
@@ -44,11 +62,6 @@ static inline int sp_launch_status() { return (int)cudaGetLastError(); }
 // DIFFERENT kernels alternate on a stream (encode+loss+decode step: 1535 us with it, 1455 us
 // without; scratch/seq_step.py), and to gain < 1 % for back-to-back launches of one kernel.
 // SP_NO_PDL=1 in the environment restores plain stream-ordered launches.
-static inline bool sp_pdl_enabled() {
-    const char* v = getenv("SP_NO_PDL");
-    return !(v && v[0] == '1');
-}
-
 template <typename... KArgs, typename... Args>
 static inline cudaError_t sp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                     Args... args) {
@@ -61,7 +74,32 @@ static inline cudaError_t sp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = sp_pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = sp_tuning().no_pdl == 1 ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Same, raising the kernel's dynamic shared-memory limit first when it needs more than 48 KB.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sp_launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+    if (smem > 48 * 1024) {
+        const cudaError_t e = sp_ensure_dyn_smem(reinterpret_cast<const void*>(kernel), smem);
+        if (e != cudaSuccess) return e;
+    }
+    return sp_launch(kernel, grid, block, smem, st, args...);
+}
+
+// Plain stream-ordered launch (kernels that do not call griddepcontrol.wait).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sp_launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

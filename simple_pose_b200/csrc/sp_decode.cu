@@ -60,6 +60,8 @@ struct DecodeArgs {
     float* coords;
     float* maxval;
     int* argmax;
+    float* rows;               // optional result table: rows[person * row_stride + 3*joint + {0,1,2}] = x, y, peak value
+    int row_stride;
     int nmaps, K, H, W, ksize, mode;
     unsigned int* work;        // caller's workspace {next map, CTAs finished}; nullptr = equal per-CTA ranges
 };
@@ -465,9 +467,14 @@ __device__ __forceinline__ void finish_map(const DecodeArgs& A, const View& map,
             outx = __fadd_rn(fmaf(y, T.b, __fmul_rn(x, T.a)), T.c);
             outy = __fadd_rn(fmaf(y, T.e, __fmul_rn(x, T.d)), T.f);
         }
-        reinterpret_cast<float2*>(A.coords)[m] = make_float2(outx, outy);
-        A.maxval[m] = pk.value;
+        if (A.coords) reinterpret_cast<float2*>(A.coords)[m] = make_float2(outx, outy);
+        if (A.maxval) A.maxval[m] = pk.value;
         if (A.argmax) A.argmax[m] = pk.index;
+        if (A.rows) {
+            const int person = m / A.K;
+            float* r = A.rows + (size_t)person * A.row_stride + 3 * (m - person * A.K);
+            r[0] = outx; r[1] = outy; r[2] = pk.value;
+        }
     }
 }
 
@@ -654,22 +661,18 @@ decode_generic_kernel(const DecodeArgs A) {
     }
 }
 
-int env_int(const char* name, int fallback) {
-    const char* v = getenv(name);
-    if (!v || !*v) return fallback;
-    return atoi(v);
-}
-
 }  // namespace
 
 extern "C" size_t sp_decode_workspace_bytes(void) { return 16; }
 
 static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
                          const float* trans_inv, const float* blur_w,
-                         float* coords, float* maxval, int* argmax,
+                         float* coords, float* maxval, int* argmax, float* rows, int row_stride,
                          int B, int K, int H, int W, int ksize, int mode, unsigned int* work, void* stream) {
     SP_RETURN_IF(B < 0 || K <= 0 || H <= 0 || W <= 0, SP_ERR_BAD_ARGUMENT);
-    SP_RETURN_IF(B > 0 && (!hm || !coords || !maxval), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B > 0 && !hm, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B > 0 && !rows && (!coords || !maxval), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(rows && row_stride < 3 * K, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(mode < SP_DECODE_GAUSS_TAYLOR || mode > SP_DECODE_DARK_ORIGINAL, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(hm_flip && !perm, SP_ERR_BAD_ARGUMENT);
     if (mode == SP_DECODE_GAUSS_TAYLOR || mode == SP_DECODE_DARK_ORIGINAL) {
@@ -680,22 +683,23 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
     }
     SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
     if (B == 0) return 0;
-    SP_RETURN_IF(!sp_aligned16(coords), SP_ERR_BAD_ALIGNMENT);
+    SP_RETURN_IF(coords && !sp_aligned16(coords), SP_ERR_BAD_ALIGNMENT);
 
     DecodeArgs A;
     A.hm = hm; A.hm_flip = hm_flip; A.perm = perm; A.trans_inv = trans_inv; A.blur_w = blur_w;
-    A.coords = coords; A.maxval = maxval; A.argmax = argmax;
+    A.coords = coords; A.maxval = maxval; A.argmax = argmax; A.rows = rows; A.row_stride = row_stride;
     A.nmaps = B * K; A.K = K; A.H = H; A.W = W; A.ksize = ksize; A.mode = mode;
     A.work = work;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool flip = hm_flip != nullptr;
 
     // fast path needs 16-byte bulk copies and row-aligned quads
+    const SpTuning& tune = sp_tuning();
     const size_t map_bytes = (size_t)H * W * 4;
     const size_t stage_bytes = flip ? 2 * map_bytes : map_bytes;
     const size_t budget = 227 * 1024 - kBarBytes - kWtsBytes;
     bool fast = (W % 4 == 0) && sp_aligned16(hm) && (!flip || sp_aligned16(hm_flip)) &&
-                (stage_bytes + kPatchBytes <= budget) && !env_int("SP_DECODE_FORCE_GENERIC", 0);
+                (stage_bytes + kPatchBytes <= budget) && sp_knob(tune.decode_force_generic, 0) == 0;
     if (fast) {
         // as many warps as fit (<= 16), then as many stages per warp as still fit (<= 4)
         int nwarps = (int)(budget / (stage_bytes + kPatchBytes));
@@ -703,12 +707,12 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
         // large launches of small maps: 14 warps (172 KB in flight per SM) measured 2 % faster than 16
         // (196 KB); small launches keep 16 so that every map is in flight at once
         if (nwarps > 14 && (long long)A.nmaps >= 4LL * 16 * sp_sm_count()) nwarps = 14;
-        nwarps = env_int("SP_DECODE_WARPS", nwarps);
+        nwarps = sp_knob(tune.decode_warps, nwarps);
         if (nwarps < 1) nwarps = 1;
         if (nwarps > 16) nwarps = 16;
         int stages = (int)((budget / nwarps - kPatchBytes) / stage_bytes);
         if (stages > 4) stages = 4;
-        stages = env_int("SP_DECODE_STAGES", stages);
+        stages = sp_knob(tune.decode_stages, stages);
         if (stages < 1) stages = 1;
         while (nwarps * stages > 64 && stages > 1) --stages;       // mbarrier / claim tables hold 64 entries
         while ((size_t)nwarps * (stages * stage_bytes + kPatchBytes) > budget && stages > 1) --stages;
@@ -722,33 +726,32 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
         // for 512 persons) -- and loses below (64x48: 36 -> 61 us), so smaller items keep the equal ranges.
         // SP_DECODE_GRID_WIDE=1/0 forces either.
         {
-            const int force = env_int("SP_DECODE_GRID_WIDE", -1);
+            const int force = sp_knob(tune.decode_grid_wide, -1);
             if (force == 0 || (force < 0 && stage_bytes < 40 * 1024)) A.work = nullptr;
         }
 #define SP_LAUNCH_DECODE(F, KS)                                                                                     \
     do {                                                                                                            \
-        SP_CUDA(cudaFuncSetAttribute(decode_tma_kernel<F, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SP_CUDA(sp_launch(decode_tma_kernel<F, KS>, dim3(grid), dim3(nwarps * 32), smem, st, A, nwarps, stages));        \
+        SP_CUDA(sp_launch_smem(decode_tma_kernel<F, KS>, dim3(grid), dim3(nwarps * 32), smem, st, A, nwarps, stages));   \
     } while (0)
-        const bool ks11 = (ksize == 11) && !env_int("SP_DECODE_RUNTIME_KSIZE", 0);
+        const bool ks11 = (ksize == 11) && sp_knob(tune.decode_runtime_ksize, 0) == 0;
         if (flip) { if (ks11) SP_LAUNCH_DECODE(true, 11); else SP_LAUNCH_DECODE(true, 0); }
         else      { if (ks11) SP_LAUNCH_DECODE(false, 11); else SP_LAUNCH_DECODE(false, 0); }
 #undef SP_LAUNCH_DECODE
-        return sp_launch_status();
+        return 0;
     }
     int grid = sp_sm_count() * 8;
     const int need = (A.nmaps + 7) / 8;
     if (grid > need) grid = need;
     if (flip) SP_CUDA(sp_launch(decode_generic_kernel<true>, dim3(grid), dim3(256), 0, st, A));
     else      SP_CUDA(sp_launch(decode_generic_kernel<false>, dim3(grid), dim3(256), 0, st, A));
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_decode_f32(const float* hm, const float* hm_flip, const int* perm,
                              const float* trans_inv, const float* blur_w,
                              float* coords, float* maxval, int* argmax,
                              int B, int K, int H, int W, int ksize, int mode, void* stream) {
-    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, B, K, H, W, ksize, mode, nullptr, stream);
+    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, nullptr, 0, B, K, H, W, ksize, mode, nullptr, stream);
 }
 
 extern "C" int sp_decode_ws_f32(const float* hm, const float* hm_flip, const int* perm,
@@ -759,6 +762,18 @@ extern "C" int sp_decode_ws_f32(const float* hm, const float* hm_flip, const int
     SP_RETURN_IF(!workspace, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(workspace_bytes < sp_decode_workspace_bytes(), SP_ERR_WORKSPACE);
     SP_RETURN_IF(!sp_aligned16(workspace), SP_ERR_BAD_ALIGNMENT);
-    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, B, K, H, W, ksize, mode,
+    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, argmax, nullptr, 0, B, K, H, W, ksize, mode,
                          static_cast<unsigned int*>(workspace), stream);
+}
+
+extern "C" int sp_decode_rows_f32(const float* hm, const float* hm_flip, const int* perm,
+                                  const float* trans_inv, const float* blur_w,
+                                  float* rows, int row_stride, float* coords, float* maxval,
+                                  int B, int K, int H, int W, int ksize, int mode,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    SP_RETURN_IF(!workspace || (B > 0 && !rows), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(workspace_bytes < sp_decode_workspace_bytes(), SP_ERR_WORKSPACE);
+    SP_RETURN_IF(!sp_aligned16(workspace), SP_ERR_BAD_ALIGNMENT);
+    return decode_launch(hm, hm_flip, perm, trans_inv, blur_w, coords, maxval, nullptr, rows, row_stride, B, K, H, W, ksize,
+                         mode, static_cast<unsigned int*>(workspace), stream);
 }

@@ -146,7 +146,8 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     // the per-SM load even: 2-warp CTAs put 29.4 +- 0.5 CTAs on an SM where 8-warp CTAs put 7 or 8
     // (96x72, 512 persons: 9 % of the launch was the SMs that drew 8). Measured 8 -> 2 warps per CTA:
     // 0.934 -> 0.954 of the HBM peak at 64x48 x 1024, 0.862 -> 0.900 at 96x72 x 512, 10.6 -> 7.9 us at 64x48 x 128.
-    int warps = sp_env_int("SP_ENCODE_WARPS", 2);
+    const SpTuning& tune = sp_tuning();
+    int warps = sp_knob(tune.encode_warps, 2);
     if (warps != 2 && warps != 4 && warps != 8) warps = 2;
     const size_t smem = (size_t)warps * (wpad + ((H + 1) & ~1)) * sizeof(double);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
@@ -160,7 +161,7 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     // re-evaluated per unit: 64x48 x 1024 40.9 us).
     int parts = H / 32;
     if (parts < 1) parts = 1;
-    parts = sp_env_int("SP_ENCODE_PARTS", parts);
+    parts = sp_knob(tune.encode_parts, parts);
     if (parts < 1) parts = 1;
     if (parts > H) parts = H;
     const long long units = (long long)nmaps * parts;
@@ -169,14 +170,12 @@ extern "C" int sp_encode_f32(const float* joints, float* targets, float* weights
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define SP_LAUNCH_ENCODE(V, NW)                                                                                         \
     do {                                                                                                                \
-        if (smem > 48 * 1024)                                                                                           \
-            SP_CUDA(cudaFuncSetAttribute(encode_refine_kernel<V, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SP_CUDA(sp_launch(encode_refine_kernel<V, NW>, dim3(grid), dim3(NW * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom, parts)); \
+        SP_CUDA(sp_launch_smem(encode_refine_kernel<V, NW>, dim3(grid), dim3(NW * SP_WARP), smem, st, joints, targets, weights, nmaps, H, W, reach, denom, parts)); \
     } while (0)
     if (vec4) { if (warps == 2) SP_LAUNCH_ENCODE(true, 2); else if (warps == 4) SP_LAUNCH_ENCODE(true, 4); else SP_LAUNCH_ENCODE(true, 8); }
     else      { if (warps == 2) SP_LAUNCH_ENCODE(false, 2); else if (warps == 4) SP_LAUNCH_ENCODE(false, 4); else SP_LAUNCH_ENCODE(false, 8); }
 #undef SP_LAUNCH_ENCODE
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_encode_basic_f32(const float* joints, const float* table, float* targets, float* weights,
@@ -189,5 +188,5 @@ extern "C" int sp_encode_basic_f32(const float* joints, const float* table, floa
     const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
     SP_CUDA(sp_launch(encode_basic_kernel, dim3(grid), dim3(kWarpsPerCta * SP_WARP), (size_t)side * side * sizeof(float),
                       static_cast<cudaStream_t>(stream), joints, table, targets, weights, nmaps, H, W, sigma * 3.0, (float)stride, side));
-    return sp_launch_status();
+    return 0;
 }

@@ -230,19 +230,20 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
     const int skip = (flags & SP_MSE_SKIP_MASKED) ? 1 : 0;
 
     // ring kernel: needs 16-byte rows and a chunk size (in quads) that divides the map
-    if (vec4 && !skip && !sp_env_int("SP_LOSS_FORCE_LDG", 0)) {
+    const SpTuning& tune = sp_tuning();
+    if (vec4 && !skip && sp_knob(tune.loss_force_ldg, 0) == 0) {
         const int nq = HW >> 2;
-        int want = sp_env_int("SP_LOSS_CHUNK_QUADS", 192);           // 3 KB per stream
+        int want = sp_knob(tune.loss_chunk_quads, 192);           // 3 KB per stream
         if (want < 8) want = 8;
         if (want > 2048) want = 2048;
         int chunk_quads = 0;
         for (int d = want < nq ? want : nq; d >= 8; --d)
             if (nq % d == 0) { chunk_quads = d; break; }
         if (chunk_quads * 2 >= (want < nq ? want : nq)) {            // else: awkward map size, use the fallback
-            int ring = sp_env_int("SP_LOSS_RING", 3);
+            int ring = sp_knob(tune.loss_ring, 3);
             if (ring < 1) ring = 1;
             if (ring > 8) ring = 8;
-            int nwarps = sp_env_int("SP_LOSS_WARPS", 4);   // 4 warps x 3 slots x 6 KB = 72 KB in flight per SM (sweep: profiles/)
+            int nwarps = sp_knob(tune.loss_warps, 4);   // 4 warps x 3 slots x 6 KB = 72 KB in flight per SM (sweep: profiles/)
             if (nwarps < 1) nwarps = 1;
             if (nwarps > 32) nwarps = 32;
             const size_t slot_bytes = (size_t)chunk_quads * 32;      // pred chunk + target chunk
@@ -253,15 +254,13 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
                 int grid = sp_sm_count();
                 if ((long long)grid * nwarps > nchunks) grid = (int)((nchunks + nwarps - 1) / nwarps);
                 if (grad) {
-                    SP_CUDA(cudaFuncSetAttribute(mse_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    SP_CUDA(sp_launch(mse_ring_kernel<true>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
+                    SP_CUDA(sp_launch_smem(mse_ring_kernel<true>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
                                       nchunks, chunk_quads, nq / chunk_quads, nwarps, ring, norm, half_scale, 1.0 / count));
                 } else {
-                    SP_CUDA(cudaFuncSetAttribute(mse_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    SP_CUDA(sp_launch(mse_ring_kernel<false>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
+                    SP_CUDA(sp_launch_smem(mse_ring_kernel<false>, dim3(grid), dim3(nwarps * 32), smem, st, pred, target, mask, grad, loss, ws,
                                       nchunks, chunk_quads, nq / chunk_quads, nwarps, ring, norm, half_scale, 1.0 / count));
                 }
-                return sp_launch_status();
+                return 0;
             }
         }
     }
@@ -274,7 +273,7 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
     if (vec4) { if (grad) SP_LAUNCH_MSE(true, true); else SP_LAUNCH_MSE(true, false); }
     else      { if (grad) SP_LAUNCH_MSE(false, true); else SP_LAUNCH_MSE(false, false); }
 #undef SP_LAUNCH_MSE
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_scale_inplace_f32(float* data, long long n, const float* scale_dev, void* stream) {
@@ -286,5 +285,5 @@ extern "C" int sp_scale_inplace_f32(float* data, long long n, const float* scale
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     SP_CUDA(sp_launch(scale_inplace_kernel, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), data, n, scale_dev));
-    return sp_launch_status();
+    return 0;
 }

@@ -11,6 +11,7 @@
 // keeps the reference's operation order, including NumPy's 8-accumulator pairwise summation,
 // so that the `oks > thresh` decisions agree.
 #include "sp_common.cuh"
+#include <math_constants.h>
 
 namespace {
 
@@ -69,25 +70,28 @@ __device__ __forceinline__ double joint_var(const OksParams& P, int k) {
     return __dmul_rn(t, t);
 }
 
-// oks_iou for one (pick, candidate) pair, naive_data.py:139-149
-__device__ double oks_pair(const OksParams& P, const double* __restrict__ pick, const double* __restrict__ cand,
+// oks_iou for one (pick, candidate) pair, naive_data.py:139-149. T = double (the reference's arrays) or
+// float (decoder output rows; the JSON round trip of eval.py:138-160 widens exactly these floats).
+template <typename T>
+__device__ double oks_pair(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
                            double pick_area, double cand_area) {
     const double denom_area = __dadd_rn(__ddiv_rn(__dadd_rn(pick_area, cand_area), 2.0), 1e-12);
     int nvis = P.K;
     if (P.use_vis) {
         nvis = 0;
-        for (int k = 0; k < P.K; ++k) nvis += (cand[3 * k + 2] > P.vis_thresh) && (pick[3 * k + 2] > P.vis_thresh);
+        for (int k = 0; k < P.K; ++k)
+            nvis += ((double)cand[3 * k + 2] > P.vis_thresh) && ((double)pick[3 * k + 2] > P.vis_thresh);
     }
     NumpySum acc;
     acc.begin(P.K);
     for (int k = 0; k < P.K; ++k) {
-        const double dx = __dsub_rn(cand[3 * k + 0], pick[3 * k + 0]);
-        const double dy = __dsub_rn(cand[3 * k + 1], pick[3 * k + 1]);
+        const double dx = __dsub_rn((double)cand[3 * k + 0], (double)pick[3 * k + 0]);
+        const double dy = __dsub_rn((double)cand[3 * k + 1], (double)pick[3 * k + 1]);
         double e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         e = __ddiv_rn(__ddiv_rn(__ddiv_rn(e, joint_var(P, k)), denom_area), 2.0);
         double v = exp(-e);
         if (P.use_vis) {
-            const bool vis = (cand[3 * k + 2] > P.vis_thresh) && (pick[3 * k + 2] > P.vis_thresh);
+            const bool vis = ((double)cand[3 * k + 2] > P.vis_thresh) && ((double)pick[3 * k + 2] > P.vis_thresh);
             v = __dmul_rn(v, vis ? 1.0 : 0.0);
         }
         acc.push(v);
@@ -95,6 +99,24 @@ __device__ double oks_pair(const OksParams& P, const double* __restrict__ pick, 
     // (vd_vis.sum(-1) + 1e-12) is float32 arithmetic in the reference
     const float cnt = __fadd_rn((float)nvis, 1e-12f);
     return __ddiv_rn(acc.result(), (double)cnt);
+}
+
+// eval.py:168-175 for one person: box_score * mean(conf[conf > thr]) (0 if none)
+template <typename T>
+__device__ double rescore_one(const T* __restrict__ k, int K, double thr, double box_score) {
+    int cnt = 0;
+    for (int j = 0; j < K; ++j) cnt += ((double)k[3 * j + 2] > thr);
+    double mean = 0.0;
+    if (cnt > 0) {
+        NumpySum acc;
+        acc.begin(cnt);
+        for (int j = 0; j < K; ++j) {
+            const double c = (double)k[3 * j + 2];
+            if (c > thr) acc.push(c);
+        }
+        mean = __ddiv_rn(acc.result(), (double)cnt);
+    }
+    return __dmul_rn(box_score, mean);
 }
 
 __global__ void __launch_bounds__(128)
@@ -106,41 +128,40 @@ oks_iou_kernel(const double* __restrict__ pick_kps, const double* __restrict__ c
     out[i] = oks_pair(P, pick_kps, cand_kps + (size_t)i * 3 * P.K, pick_area[0], cand_area[i]);
 }
 
-__global__ void __launch_bounds__(kNmsThreads)
-oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores, const double* __restrict__ areas,
-               const int* __restrict__ seg, unsigned char* __restrict__ keep, int* __restrict__ rank,
-               int max_seg, double thresh, OksParams P, int force_serial) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    int* order = reinterpret_cast<int*>(nms_smem);
-    unsigned char* alive = nms_smem + (size_t)max_seg * sizeof(int);
-    const int lo = seg[blockIdx.x], hi = seg[blockIdx.x + 1];
-    const int n = hi - lo;
-    if (n <= 0) return;
-    const int tid = threadIdx.x;
+// dynamic shared memory of the NMS kernels, per image (max_seg = the largest image of the launch):
+//   score[max_seg] f64 | area[max_seg] f64 | suppression rows[64] u64 | order[max_seg] i32 | alive[max_seg] u8
+__host__ __device__ inline size_t nms_smem_bytes(int max_seg) {
+    return (size_t)max_seg * 16 + 64 * 8 + (size_t)max_seg * 4 + (((size_t)max_seg + 15) & ~(size_t)15);
+}
 
+// Greedy OKS-NMS of one image whose scores and areas are already in shared memory. kps: person i's
+// (x, y, conf) * K starts at kps + i * stride. Calls emit(i, kept) once per person and writes rank.
+template <typename T, typename Emit>
+__device__ __forceinline__ void nms_image(const T* __restrict__ kps, size_t stride, int n, const double* score,
+                                          const double* area, unsigned long long* rows, int* order, unsigned char* alive,
+                                          int* __restrict__ rank, double thresh, const OksParams& P, int force_serial,
+                                          Emit&& emit) {
+    const int tid = threadIdx.x;
     // descending-score visiting order; ties: higher index first
     for (int i = tid; i < n; i += kNmsThreads) {
-        const double si = scores[lo + i];
+        const double si = score[i];
         int r = 0;
         for (int j = 0; j < n; ++j) {
-            const double sj = scores[lo + j];
+            const double sj = score[j];
             r += (sj > si) || (sj == si && j > i);
         }
         order[r] = i;
-        rank[lo + i] = r;
+        if (rank) rank[i] = r;
         alive[i] = 1;
-        keep[lo + i] = 0;
     }
     __syncthreads();
 
-    const size_t stride = (size_t)3 * P.K;
     if (n <= 64 && !force_serial) {
         // Small image (the COCO case: ~20 boxes): score ALL n(n-1)/2 (earlier, later) pairs of the
         // visiting order at once, one thread per pair, into 64-bit suppression rows; the greedy pass
         // is then n bit operations. Same decisions as the loop below (oks_pair is evaluated with the
         // earlier person as the pick, exactly as the loop would), but one exp-chain deep instead of
         // one per surviving pick.
-        unsigned long long* rows = reinterpret_cast<unsigned long long*>(nms_smem + (((size_t)max_seg * 5 + 15) & ~(size_t)15));
         for (int i = tid; i < n; i += kNmsThreads) rows[i] = 0ull;
         __syncthreads();
         const int total = n * (n - 1) / 2;
@@ -153,35 +174,95 @@ oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores
             while (p > 0 && p * n - p * (p + 1) / 2 > idx) --p;
             const int c = p + 1 + (idx - (p * n - p * (p + 1) / 2));
             const int i = order[p], j = order[c];
-            const double oks = oks_pair(P, kps + (size_t)(lo + i) * stride, kps + (size_t)(lo + j) * stride,
-                                        areas[lo + i], areas[lo + j]);
+            const double oks = oks_pair(P, kps + (size_t)i * stride, kps + (size_t)j * stride, area[i], area[j]);
             if (oks > thresh) atomicOr(&rows[p], 1ull << c);
         }
         __syncthreads();
         if (tid == 0) {
             unsigned long long alive_bits = (n == 64) ? ~0ull : ((1ull << n) - 1ull);
             for (int p = 0; p < n; ++p) {
-                if (!((alive_bits >> p) & 1ull)) continue;
-                keep[lo + order[p]] = 1;
+                if (!((alive_bits >> p) & 1ull)) { alive[p] = 0; continue; }
                 alive_bits &= ~rows[p];
             }
         }
-        return;
-    }
-    for (int p = 0; p < n; ++p) {
-        if (!alive[p]) continue;                       // uniform: everyone reads the same byte
-        const int i = order[p];
-        if (tid == 0) keep[lo + i] = 1;
-        const double* pick = kps + (size_t)(lo + i) * stride;
-        const double pick_area = areas[lo + i];
-        for (int c = p + 1 + tid; c < n; c += kNmsThreads) {
-            if (!alive[c]) continue;
-            const int j = order[c];
-            const double oks = oks_pair(P, pick, kps + (size_t)(lo + j) * stride, pick_area, areas[lo + j]);
-            if (oks > thresh) alive[c] = 0;            // survivors satisfy oks <= thresh
-        }
         __syncthreads();
+    } else {
+        for (int p = 0; p < n; ++p) {
+            if (!alive[p]) continue;                   // uniform: everyone reads the same byte
+            const int i = order[p];
+            const T* pick = kps + (size_t)i * stride;
+            const double pick_area = area[i];
+            for (int c = p + 1 + tid; c < n; c += kNmsThreads) {
+                if (!alive[c]) continue;
+                const int j = order[c];
+                const double oks = oks_pair(P, pick, kps + (size_t)j * stride, pick_area, area[j]);
+                if (oks > thresh) alive[c] = 0;        // survivors satisfy oks <= thresh
+            }
+            __syncthreads();
+        }
     }
+    // alive[p] now says whether the p-th person of the visiting order was picked
+    for (int p = tid; p < n; p += kNmsThreads) emit(order[p], alive[p] != 0);
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores, const double* __restrict__ areas,
+               const int* __restrict__ seg, unsigned char* __restrict__ keep, int* __restrict__ rank,
+               int max_seg, double thresh, OksParams P, int force_serial) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    double* sc = reinterpret_cast<double*>(nms_smem);
+    double* ar = sc + max_seg;
+    unsigned long long* rows = reinterpret_cast<unsigned long long*>(ar + max_seg);
+    int* order = reinterpret_cast<int*>(rows + 64);
+    unsigned char* alive = reinterpret_cast<unsigned char*>(order + max_seg);
+    const int lo = seg[blockIdx.x], hi = seg[blockIdx.x + 1];
+    const int n = hi - lo;
+    if (n <= 0) return;
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+        sc[i] = scores[lo + i];
+        ar[i] = areas[lo + i];
+    }
+    __syncthreads();
+    const size_t stride = (size_t)3 * P.K;
+    nms_image(kps + (size_t)lo * stride, stride, n, sc, ar, rows, order, alive, rank + lo, thresh, P, force_serial,
+              [&](int i, bool kept) { keep[lo + i] = kept ? 1 : 0; });
+}
+
+// The eval chain after the decoder in ONE launch (eval.py:153-197): the decoder has written
+// (x, y, conf) * K into float32 result rows; per image this kernel rescores every person
+// (box_score * mean(conf > thr)), runs the greedy OKS-NMS and completes the rows in place:
+//   row[3K] = keep flag (0/1), row[3K+1], row[3K+2] = low / high 32 bits of the float64 score.
+// No float64 keypoint copy (pack_kps), no separate rescoring pass, no pack_rows pass.
+__global__ void __launch_bounds__(kNmsThreads)
+eval_rows_nms_kernel(float* __restrict__ rows_io, int row_stride, const double* __restrict__ box_scores,
+                     const double* __restrict__ areas_f64, const float* __restrict__ areas_f32,
+                     const int* __restrict__ seg, int* __restrict__ rank, int max_seg, double vis_thr, double thresh,
+                     OksParams P, int force_serial) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    double* sc = reinterpret_cast<double*>(nms_smem);
+    double* ar = sc + max_seg;
+    unsigned long long* rows = reinterpret_cast<unsigned long long*>(ar + max_seg);
+    int* order = reinterpret_cast<int*>(rows + 64);
+    unsigned char* alive = reinterpret_cast<unsigned char*>(order + max_seg);
+    sp::grid_dep_wait();                // the rows come from the decode kernel just before on the stream
+    const int lo = seg[blockIdx.x], hi = seg[blockIdx.x + 1];
+    const int n = hi - lo;
+    if (n <= 0) return;
+    float* base = rows_io + (size_t)lo * row_stride;
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+        sc[i] = rescore_one(base + (size_t)i * row_stride, P.K, vis_thr, box_scores[lo + i]);
+        ar[i] = areas_f64 ? areas_f64[lo + i] : (double)areas_f32[lo + i];
+    }
+    __syncthreads();
+    const int K = P.K;
+    nms_image(base, (size_t)row_stride, n, sc, ar, rows, order, alive, rank ? rank + lo : nullptr, thresh, P, force_serial,
+              [&](int i, bool kept) {
+                  float* r = base + (size_t)i * row_stride + 3 * K;
+                  const unsigned long long bits = (unsigned long long)__double_as_longlong(sc[i]);
+                  r[0] = kept ? 1.f : 0.f;
+                  r[1] = __uint_as_float((unsigned)(bits & 0xffffffffull));
+                  r[2] = __uint_as_float((unsigned)(bits >> 32));
+              });
 }
 
 // eval.py:168-175
@@ -190,20 +271,7 @@ rescore_kernel(const double* __restrict__ kps, const double* __restrict__ box_sc
                int N, int K, double thr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const double* k = kps + (size_t)i * 3 * K;
-    int cnt = 0;
-    for (int j = 0; j < K; ++j) cnt += (k[3 * j + 2] > thr);
-    double mean = 0.0;
-    if (cnt > 0) {
-        NumpySum acc;
-        acc.begin(cnt);
-        for (int j = 0; j < K; ++j) {
-            const double c = k[3 * j + 2];
-            if (c > thr) acc.push(c);
-        }
-        mean = __ddiv_rn(acc.result(), (double)cnt);
-    }
-    scores[i] = __dmul_rn(box_scores[i], mean);
+    scores[i] = rescore_one(kps + (size_t)i * 3 * K, K, thr, box_scores[i]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -239,7 +307,57 @@ pack_rows_kernel(const float* __restrict__ coords, const float* __restrict__ max
     }
 }
 
+// kps_to_dict_ (metrics/pose_metrics.py:172-179) as one table: rows [N, 3K+1] f32 = (x, y, conf) * K, then the
+// person score mean(conf) + max(conf). The mean is accumulated in float64 and rounded once (torch's float32
+// reduction order differs between its CPU and CUDA kernels; this is within 1 ulp of either).
+__global__ void __launch_bounds__(128)
+person_rows_kernel(const float* __restrict__ coords, const float* __restrict__ maxval, float* __restrict__ rows, int N, int K) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    float* r = rows + (size_t)p * (3 * K + 1);
+    double sum = 0.0;
+    float mx = -CUDART_INF_F;
+    bool nan = false;
+    for (int k = 0; k < K; ++k) {
+        const float2 c = reinterpret_cast<const float2*>(coords)[(size_t)p * K + k];
+        const float v = maxval[(size_t)p * K + k];
+        r[3 * k + 0] = c.x;
+        r[3 * k + 1] = c.y;
+        r[3 * k + 2] = v;
+        sum += (double)v;
+        nan |= (v != v);
+        mx = fmaxf(mx, v);
+    }
+    const float mean = (float)(sum / (double)K);
+    r[3 * K] = nan ? CUDART_NAN_F : __fadd_rn(mean, mx);
+}
+
 }  // namespace
+
+extern "C" int sp_person_rows_f32(const float* coords, const float* maxval, float* rows, int N, int K, void* stream) {
+    SP_RETURN_IF(N < 0 || K <= 0, SP_ERR_BAD_ARGUMENT);
+    if (N == 0) return 0;
+    SP_RETURN_IF(!coords || !maxval || !rows, SP_ERR_BAD_ARGUMENT);
+    SP_CUDA(sp_launch_plain(person_rows_kernel, dim3((N + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                            coords, maxval, rows, N, K));
+    return 0;
+}
+
+extern "C" int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                                    const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                                    int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, void* stream) {
+    SP_RETURN_IF(N < 0 || I < 0 || K <= 0 || K > kMaxJoints || max_seg < 0 || row_stride < 3 * K + 3, SP_ERR_BAD_ARGUMENT);
+    if (N == 0 || I == 0) return 0;
+    SP_RETURN_IF(!rows || !box_scores || !seg || (!areas_f64 && !areas_f32), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
+    const size_t smem = nms_smem_bytes(max_seg);
+    SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
+    OksParams P{sigmas, K, 0, 0.0};
+    SP_CUDA(sp_launch_smem(eval_rows_nms_kernel, dim3(I), dim3(kNmsThreads), smem, static_cast<cudaStream_t>(stream),
+                           rows, row_stride, box_scores, areas_f64, areas_f32, seg, rank, max_seg, in_vis_thre, oks_thre, P,
+                           sp_knob(sp_tuning().nms_serial, 0)));
+    return 0;
+}
 
 extern "C" int sp_pack_rows_f32(const float* coords, const float* maxval, const unsigned char* keep, const double* scores,
                                 float* rows, int N, int K, void* stream) {
@@ -250,8 +368,9 @@ extern "C" int sp_pack_rows_f32(const float* coords, const float* maxval, const 
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)sp_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    pack_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(coords, maxval, keep, scores, rows, N, K);
-    return sp_launch_status();
+    SP_CUDA(sp_launch_plain(pack_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            coords, maxval, keep, scores, rows, (long long)N, K));
+    return 0;
 }
 
 extern "C" int sp_oks_iou_f64(const double* pick_kps, const double* cand_kps, const double* pick_area,
@@ -262,8 +381,9 @@ extern "C" int sp_oks_iou_f64(const double* pick_kps, const double* cand_kps, co
     SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
     if (n == 0) return 0;
     OksParams P{sigmas, K, use_vis_thresh ? 1 : 0, vis_thresh};
-    oks_iou_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pick_kps, cand_kps, pick_area, cand_area, out, n, P);
-    return sp_launch_status();
+    SP_CUDA(sp_launch_plain(oks_iou_kernel, dim3((n + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                            pick_kps, cand_kps, pick_area, cand_area, out, n, P));
+    return 0;
 }
 
 extern "C" int sp_oks_nms_f64(const double* kps, const double* scores, const double* areas, const int* seg,
@@ -274,15 +394,13 @@ extern "C" int sp_oks_nms_f64(const double* kps, const double* scores, const dou
     SP_RETURN_IF(N < 0 || I < 0 || K <= 0 || K > kMaxJoints || max_seg < 0, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(!sigmas && K != 17, SP_ERR_BAD_ARGUMENT);
     if (N == 0 || I == 0) return 0;
-    // order[max_seg] int + alive[max_seg] bytes, then (16-byte aligned) 64 suppression rows for small images
-    const size_t smem = (((size_t)max_seg * (sizeof(int) + 1) + 15) & ~(size_t)15) + 64 * sizeof(unsigned long long);
+    const size_t smem = nms_smem_bytes(max_seg);
     SP_RETURN_IF(smem > 200 * 1024, SP_ERR_UNSUPPORTED);
-    if (smem > 48 * 1024)
-        SP_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) SP_CUDA(sp_ensure_dyn_smem(reinterpret_cast<const void*>(oks_nms_kernel), smem));
     OksParams P{sigmas, K, use_vis_thresh ? 1 : 0, vis_thresh};
-    oks_nms_kernel<<<I, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(kps, scores, areas, seg, keep, rank, max_seg, thresh, P,
-                                                                                sp_env_int("SP_NMS_SERIAL", 0));
-    return sp_launch_status();
+    SP_CUDA(sp_launch_plain(oks_nms_kernel, dim3(I), dim3(kNmsThreads), smem, static_cast<cudaStream_t>(stream),
+                            kps, scores, areas, seg, keep, rank, max_seg, thresh, P, sp_knob(sp_tuning().nms_serial, 0)));
+    return 0;
 }
 
 extern "C" int sp_rescore_f64(const double* kps, const double* box_scores, double* scores,
@@ -290,8 +408,9 @@ extern "C" int sp_rescore_f64(const double* kps, const double* box_scores, doubl
     SP_RETURN_IF(!kps || !box_scores || !scores, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(N < 0 || K <= 0 || K > 128, SP_ERR_BAD_ARGUMENT);
     if (N == 0) return 0;
-    rescore_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(kps, box_scores, scores, N, K, in_vis_thre);
-    return sp_launch_status();
+    SP_CUDA(sp_launch_plain(rescore_kernel, dim3((N + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                            kps, box_scores, scores, N, K, in_vis_thre));
+    return 0;
 }
 
 extern "C" int sp_pack_kps_f64(const float* coords, const float* maxval, double* out_kps, int N, int K, void* stream) {
@@ -299,6 +418,7 @@ extern "C" int sp_pack_kps_f64(const float* coords, const float* maxval, double*
     SP_RETURN_IF(N < 0 || K <= 0, SP_ERR_BAD_ARGUMENT);
     const long long nk = (long long)N * K;
     if (nk == 0) return 0;
-    pack_kps_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(coords, maxval, out_kps, nk);
-    return sp_launch_status();
+    SP_CUDA(sp_launch_plain(pack_kps_kernel, dim3((unsigned)((nk + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                            coords, maxval, out_kps, nk));
+    return 0;
 }

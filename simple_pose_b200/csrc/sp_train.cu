@@ -904,23 +904,22 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
 
     // Ring variant: needs the map to split into equal chunks of a multiple of 32 quads (<= 4 KB)
     const int nq = (H * W) >> 2;
-    const char* force = getenv("SP_TRAIN_FORCE_LDG");
+    const SpTuning& tune = sp_tuning();
+    const bool force_ldg = sp_knob(tune.train_force_ldg, 0) == 1;
     int chunk_quads = 0;
     if ((H * W) % 4 == 0 && nq % 32 == 0) {
-        int want = 192;                                   // 3 KB
-        const char* ec = getenv("SP_TRAIN_CHUNK_QUADS");
-        if (ec && *ec) want = atoi(ec);
+        int want = sp_knob(tune.train_chunk_quads, 192);  // 3 KB
         if (want < 32) want = 32;
         for (int d = want - want % 32; d >= 32; d -= 32)
             if (nq % d == 0) { chunk_quads = d; break; }
     }
     // Variant C: W = 48 / 72 (12 / 18 quads per row), whole periods per map, grad wanted, targets not
     const int qpr = W >> 2;
-    if ((qpr == 12 || qpr == 18) && grad && !targets && !(force && force[0] == '1') && !sp_env_int("SP_TRAIN_NO_TILE", 0)) {
+    if ((qpr == 12 || qpr == 18) && grad && !targets && !force_ldg && sp_knob(tune.train_no_tile, 0) == 0) {
         const int period = (qpr == 12) ? Tile<12>::PERIOD : Tile<18>::PERIOD;
         const int rows = (qpr == 12) ? Tile<12>::ROWS : Tile<18>::ROWS;
         // tuned layouts (PPC periods per chunk, ring depth); SP_TRAIN_TILE_CFG picks another compiled one
-        const int cfg = sp_env_int("SP_TRAIN_TILE_CFG", 0);
+        const int cfg = sp_knob(tune.train_tile_cfg, 0);
         int ppc = 1, ring = 2;
         if (qpr == 12) {
             if (cfg == 1) { ppc = 1; ring = 2; } else if (cfg == 2) { ppc = 2; ring = 2; } else if (cfg == 3) { ppc = 4; ring = 1; }
@@ -929,7 +928,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
             if (cfg == 1) { ppc = 1; ring = 1; } else if (cfg == 2) { ppc = 1; ring = 3; } else if (cfg == 3) { ppc = 1; ring = 4; } else { ppc = 1; ring = 2; }
         }
         // copies kept in flight per warp in steady state (the whole ring is used once a warp is on its last map)
-        int depth = sp_env_int("SP_TRAIN_DEPTH", ring);
+        int depth = sp_knob(tune.train_depth, ring);
         if (depth < 1) depth = 1;
         if (depth > ring) depth = ring;
         const int periods = nq / (32 * period);
@@ -942,7 +941,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
             // thin tail; 8 warps (74 KB in flight per SM) halve it (512 persons: 88 -> 83 us) once there
             // are enough maps to keep the warps fed. Small launches keep 16 warps (more maps in flight).
             int want_warps = (qpr == 18 && nmaps >= 2 * 16 * sp_sm_count()) ? 8 : 16;
-            want_warps = sp_env_int("SP_TRAIN_WARPS", want_warps);
+            want_warps = sp_knob(tune.train_warps, want_warps);
             if (want_warps < nwarps) nwarps = want_warps;
             if (nwarps >= 1) {
                 const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
@@ -952,16 +951,14 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
                 // maps per warp that are assigned up front (no atomic); the rest are dealt from the grid-wide
                 // counter. All atomics hit one address (~3.5 ns each on B200), so the dynamic share is kept to
                 // what the spread of SM speeds needs: half of a warp's expected maps, at least 2 fixed.
-                int static_maps = (int)((long long)nmaps * sp_env_int("SP_TRAIN_STATIC_PCT", 50) / 100 / ((long long)grid * nwarps));
+                int static_maps = (int)((long long)nmaps * sp_knob(tune.train_static_pct, 50) / 100 / ((long long)grid * nwarps));
                 if (static_maps < 2) static_maps = 2;
 #define SP_LAUNCH_TILE(Q, P, R)                                                                                              \
     do {                                                                                                                     \
         if (pred_xy) {                                                                                                       \
-            SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
+            SP_CUDA(sp_launch_smem(encode_mse_tile_kernel<Q, P, R, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
         } else {                                                                                                             \
-            SP_CUDA(cudaFuncSetAttribute(encode_mse_tile_kernel<Q, P, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SP_CUDA(sp_launch(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
+            SP_CUDA(sp_launch_smem(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
         }                                                                                                                    \
     } while (0)
                 if (qpr == 12) {
@@ -973,21 +970,19 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
                     else if (ring == 4) SP_LAUNCH_TILE(18, 1, 4); else SP_LAUNCH_TILE(18, 1, 2);
                 }
 #undef SP_LAUNCH_TILE
-                return sp_launch_status();
+                return 0;
             }
         }
     }
-    if (chunk_quads > 0 && !(force && force[0] == '1')) {
+    if (chunk_quads > 0 && !force_ldg) {
         const size_t chunk_bytes = (size_t)chunk_quads * 16;
         const size_t budget = 226 * 1024 - kRingHeader;        // 1 KB spare for static shared memory
-        int ring = 2;
-        const char* er = getenv("SP_TRAIN_RING");
-        if (er && *er) ring = atoi(er);
+        int ring = sp_knob(tune.train_ring, 2);
         if (ring < 1) ring = 1;
         if (ring > 8) ring = 8;
         int nwarps = (int)(budget / (fac_bytes + ring * chunk_bytes));
         if (nwarps > 16) nwarps = 16;      // 16 x 2 x 3 KB = 96 KB in flight per SM; more warps = more HBM streams = slower
-        { const int w = sp_env_int("SP_TRAIN_WARPS", 16); if (w < nwarps) nwarps = w; }
+        { const int w = sp_knob(tune.train_warps, 16); if (w < nwarps) nwarps = w; }
         if (nwarps < 1) nwarps = 1;
         SP_RETURN_IF((size_t)nwarps * ring * 8 > 1024, SP_ERR_UNSUPPORTED);
         const size_t smem = kRingHeader + (size_t)nwarps * (fac_bytes + ring * chunk_bytes);
@@ -996,8 +991,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         if (grid > need) grid = need;
 #define SP_LAUNCH_RING(G, T, A)                                                                                              \
     do {                                                                                                                     \
-        SP_CUDA(cudaFuncSetAttribute(encode_mse_ring_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SP_CUDA(sp_launch(encode_mse_ring_kernel<G, T, A>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, ring, chunk_quads)); \
+        SP_CUDA(sp_launch_smem(encode_mse_ring_kernel<G, T, A>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, ring, chunk_quads)); \
     } while (0)
         switch (sel) {
             case 0: SP_LAUNCH_RING(false, false, false); break;
@@ -1010,7 +1004,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
             default: SP_LAUNCH_RING(true, true, true); break;
         }
 #undef SP_LAUNCH_RING
-        return sp_launch_status();
+        return 0;
     }
 
     const size_t smem = (size_t)kWarps * fac_bytes;
@@ -1019,9 +1013,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     if (grid > kMaxPartials) grid = kMaxPartials;
 #define SP_LAUNCH_TRAIN(G, T, A)                                                                                         \
     do {                                                                                                                 \
-        if (smem > 48 * 1024)                                                                                            \
-            SP_CUDA(cudaFuncSetAttribute(encode_mse_kernel<G, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SP_CUDA(sp_launch(encode_mse_kernel<G, T, A>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count));       \
+        SP_CUDA(sp_launch_smem(encode_mse_kernel<G, T, A>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count));       \
     } while (0)
     switch (sel) {
         case 0: SP_LAUNCH_TRAIN(false, false, false); break;
@@ -1034,7 +1026,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
         default: SP_LAUNCH_TRAIN(true, true, true); break;
     }
 #undef SP_LAUNCH_TRAIN
-    return sp_launch_status();
+    return 0;
 }
 
 extern "C" int sp_heatmap_acc_f32(const float* pred_xy, const float* label_xy, float* acc,
@@ -1048,5 +1040,5 @@ extern "C" int sp_heatmap_acc_f32(const float* pred_xy, const float* label_xy, f
     SP_CUDA(sp_launch(heatmap_acc_kernel, dim3(1), dim3(256), (size_t)2 * K * sizeof(int), static_cast<cudaStream_t>(stream),
                       reinterpret_cast<const float2*>(pred_xy), reinterpret_cast<const float2*>(label_xy), acc, B, K, nx, ny,
                       distance_thresh));
-    return sp_launch_status();
+    return 0;
 }

@@ -5,8 +5,13 @@ The reference evaluates on a single device (DDP ``val()`` runs on rank 0 only,
 ``dp_pose_hrnet_solver.py:83-84,160``). Persons are independent for decode and images are
 independent for OKS-NMS, so here every rank owns a contiguous range of *images* (balanced by
 person count), decodes and NMS-filters its own persons with the CUDA kernels, and the only
-exchange is one ``all_gather_into_tensor`` of the packed per-person results
-(K*3 + 2 float32 = 212 B per person at K = 17) over NCCL/NVLink.
+exchange is an ``all_gather_into_tensor`` of the packed per-person result rows
+(K*3 + 3 float32 = 216 B per person at K = 17) over NCCL/NVLink, issued per chunk of the shard so that
+it runs on NCCL's stream while the next chunk is being decoded.
+
+Result row (``ROW_EXTRA`` = 3 trailing floats): ``(x, y, conf) * K, keep, score_lo, score_hi`` -- the last
+two are the two 32-bit halves of the float64 rescored score (``row_scores`` reassembles them), so the
+score reaches the COCO result file with the reference's precision (``eval.py:168-193``).
 
 One process per GPU (``torchrun``); the sharding / padding / ordering logic (``shard_images``,
 ``person_range``, ``gather_rows``) is device-agnostic and runs under ``gloo`` on CPU tensors in the
@@ -80,57 +85,204 @@ def gather_rows(local_rows, counts, group=None):
     return torch.cat(parts, dim=0)
 
 
+ROW_EXTRA = 3
+
+
+def row_width(num_joints):
+    return 3 * int(num_joints) + ROW_EXTRA
+
+
+def row_keep(rows):
+    """[n, 3K+3] result rows -> bool [n]: survived the OKS-NMS."""
+    return rows[:, -3] > 0.5
+
+
+def row_scores(rows):
+    """[n, 3K+3] result rows -> float64 [n]: the rescored person score, bit-exact (two float32 slots hold
+    its low and high 32 bits)."""
+    return rows[:, -2:].contiguous().view(torch.float64).reshape(-1)
+
+
+def row_keypoints(rows):
+    """[n, 3K+3] result rows -> float32 [n, K, 3] (x, y, conf)."""
+    return rows[:, :-ROW_EXTRA].reshape(rows.shape[0], -1, 3)
+
+
+def chunk_cuts(seg_offsets, cuts, chunks):
+    """Per rank, cut its image range into ``chunks`` contiguous image-aligned pieces balanced by person
+    count. Returns int64 [world, chunks+1] image indices (row r starts at cuts[r], ends at cuts[r+1])."""
+    seg = np.asarray(seg_offsets, dtype=np.int64)
+    world = len(cuts) - 1
+    out = np.zeros((world, chunks + 1), dtype=np.int64)
+    for r in range(world):
+        lo, hi = int(cuts[r]), int(cuts[r + 1])
+        sub = seg[lo:hi + 1] - seg[lo]
+        out[r] = shard_images(sub, chunks) + lo
+    return out
+
+
+def gather_chunk(chunk_buffer, rank, group=None, async_op=False):
+    """All-gather one chunk of the transport buffer: ``chunk_buffer`` [world, chunk_len, width], of which
+    this rank has filled ``chunk_buffer[rank]``. On CUDA/NCCL the collective runs IN PLACE (the send slot
+    is the rank's own slice of the receive buffer: no staging copy, no zero fill, no concatenation); gloo
+    does not define aliased buffers, so host tensors send a copy of the slot. Returns the work handle
+    (``async_op``) or None."""
+    world, chunk_len, width = chunk_buffer.shape
+    slot = chunk_buffer[rank]
+    if not chunk_buffer.is_cuda:
+        slot = slot.clone()
+    return dist.all_gather_into_tensor(chunk_buffer.view(world * chunk_len, width), slot, group=group, async_op=async_op)
+
+
+class ShardedTable(object):
+    """The all-gathered result rows in their transport layout: ``buffer`` [chunks, world, chunk_len, width]
+    (rank r's c-th chunk of persons sits in ``buffer[c, r, :counts[r][c]]``; the rest of a slot is zero
+    padding). ``rows()`` returns the dense [N, width] table in global person order -- a view when there is
+    one rank and one chunk, otherwise one ``torch.cat`` of the valid slices."""
+
+    def __init__(self, buffer, counts):
+        self.buffer = buffer
+        self.counts = [[int(c) for c in row] for row in counts]
+
+    @property
+    def persons(self):
+        return sum(sum(row) for row in self.counts)
+
+    def rows(self):
+        parts = [self.buffer[c, r, :n] for r, row in enumerate(self.counts) for c, n in enumerate(row) if n > 0]
+        if not parts:
+            return self.buffer.new_zeros((0, self.buffer.shape[-1]))
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+
 class ShardedPoseEvaluator(object):
-    """decode (+flip) -> rescoring -> OKS-NMS on this rank's persons, then one all-gather.
+    """decode (+flip) -> rescoring + OKS-NMS on this rank's persons, chunk by chunk, each chunk all-gathered
+    (in place, asynchronously) as soon as its rows are complete.
 
-    ``plan(seg_offsets)`` once per dataset; ``run(...)`` with the heatmaps of THIS rank's
-    persons (produced by this rank's backbone replica). Every rank returns the full result
-    table in global person order."""
+    ``plan(seg_offsets)`` once per dataset; ``run(...)`` with the heatmaps of THIS rank's persons (produced
+    by this rank's backbone replica). Every rank returns the full result table in global person order.
+    ``run(..., compact=False)`` returns the transport buffer without any copy (see ``ShardedTable``).
+    Three launches per chunk (``sp_decode_rows_f32``, ``sp_eval_rows_nms_f32``, the NCCL all-gather) plus
+    one ``sp_box_affine_f64`` per run when boxes are given; all buffers are allocated at the first run."""
 
-    def __init__(self, kernel_size=11, num_joints=17, in_vis_thre=0.2, oks_thre=0.9, group=None):
+    def __init__(self, kernel_size=11, num_joints=17, in_vis_thre=0.2, oks_thre=0.9, group=None, chunks=None):
         from .metrics.pose_metrics import GaussTaylorKeyPointDecoder
         self.decoder = GaussTaylorKeyPointDecoder(kernel_size, num_joints)
-        self.in_vis_thre, self.oks_thre = in_vis_thre, oks_thre
+        self.num_joints = int(num_joints)
+        self.in_vis_thre, self.oks_thre = float(in_vis_thre), float(oks_thre)
         self.group = group
-        self.seg = None
-        self.cuts = None
+        self.chunks = chunks
+        self.seg = self.cuts = self.ccuts = None
+        self._dev_state = {}
 
-    def plan(self, seg_offsets):
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+    def _world_rank(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group), dist.get_rank(self.group)
+        return 1, 0
+
+    def plan(self, seg_offsets, chunks=None):
+        world, _ = self._world_rank()
         self.seg = np.asarray(seg_offsets, dtype=np.int64)
         self.cuts = shard_images(self.seg, world)
+        nchunks = chunks if chunks is not None else self.chunks
+        if nchunks is None:
+            nchunks = 1 if world == 1 else 2        # one chunk's NMS + all-gather hides behind the next chunk's decode
+        nchunks = max(1, int(nchunks))
+        self.ccuts = chunk_cuts(self.seg, self.cuts, nchunks)
+        self.counts = [[int(self.seg[self.ccuts[r, c + 1]] - self.seg[self.ccuts[r, c]]) for c in range(nchunks)]
+                       for r in range(world)]
+        self.chunk_len = max(1, max(max(row) for row in self.counts))
+        self._dev_state = {}
         return self.cuts
 
     def my_persons(self):
-        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        _, rank = self._world_rank()
         return person_range(self.seg, self.cuts, rank)
+
+    def _state(self, dev):
+        st = self._dev_state.get(dev)
+        if st is None:
+            world, rank = self._world_rank()
+            nchunks = self.ccuts.shape[1] - 1
+            width = row_width(self.num_joints)
+            st = {"buffer": torch.zeros((nchunks, world, self.chunk_len, width), dtype=torch.float32, device=dev),
+                  "seg": [], "max_seg": [], "images": []}
+            for c in range(nchunks):
+                i0, i1 = int(self.ccuts[rank, c]), int(self.ccuts[rank, c + 1])
+                local = (self.seg[i0:i1 + 1] - self.seg[i0]).astype(np.int32)
+                st["seg"].append(torch.from_numpy(np.ascontiguousarray(local)).to(dev))
+                st["max_seg"].append(int(np.diff(local).max()) if i1 > i0 else 0)
+                st["images"].append(i1 - i0)
+            self._dev_state[dev] = st
+        return st
 
     @torch.no_grad()
     def run(self, heat_map, trans_inv, box_scores, areas, heat_map_flip=None, joint_pairs=None, boxes=None,
-            input_shape=(192, 256)):
+            input_shape=(192, 256), compact=True):
         """``boxes`` [n,4] (x1, y1, x2, y2) may replace ``trans_inv``/``areas``: both are then derived
-        on the device exactly as ``BasicTransform`` does (``naive_data.box_affines``)."""
-        from .datasets.naive_data import pack_keypoints, rescore_and_nms, box_affines
-        if boxes is not None:
-            aff = box_affines(boxes, input_shape, (int(heat_map.shape[-1]), int(heat_map.shape[-2])))
-            trans_inv, areas = aff["trans_inv"], aff["area"].double()
-        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        on the device exactly as ``BasicTransform`` does (``naive_data.box_affines``). Returns the dense
+        [N, 3K+3] float32 table (``compact=True``) or the ``ShardedTable`` it would be built from."""
+        from . import _abi
+        from .datasets.naive_data import box_affines
+        world, rank = self._world_rank()
         lo, hi = person_range(self.seg, self.cuts, rank)
-        assert heat_map.shape[0] == hi - lo, "this rank owns persons [%d, %d)" % (lo, hi)
-        if heat_map_flip is None:
-            coords, conf = self.decoder(heat_map, trans_inv)
+        n = hi - lo
+        if heat_map.dim() != 4 or heat_map.shape[0] != n or heat_map.shape[1] != self.num_joints:
+            raise ValueError("this rank owns persons [%d, %d): heat_map must be [%d, %d, H, W]" % (lo, hi, n, self.num_joints))
+        dev = _abi.require_cuda(heat_map, heat_map_flip, trans_inv)
+        k, h, w = self.num_joints, int(heat_map.shape[2]), int(heat_map.shape[3])
+        hm = _abi.dense(heat_map, torch.float32)
+        hf = perm = None
+        if heat_map_flip is not None:
+            if tuple(heat_map_flip.shape) != tuple(heat_map.shape):
+                raise ValueError("heat_map_flip must have the shape of heat_map")
+            hf = _abi.dense(heat_map_flip, torch.float32)
+            perm = self.decoder._perm_on(dev, k, joint_pairs)
+        area32 = area64 = None
+        if boxes is not None:
+            aff = box_affines(boxes, input_shape, (w, h))
+            ti, area32 = aff["trans_inv"], aff["area"]
         else:
-            coords, conf = self.decoder.flip_call(heat_map, heat_map_flip, trans_inv, joint_pairs)
-        local_seg = (self.seg[self.cuts[rank]:self.cuts[rank + 1] + 1] - lo).astype(np.int32)
-        if hi > lo:
-            kps = pack_keypoints(coords, conf)
-            keep, scores, _ = rescore_and_nms(kps, box_scores, areas, local_seg, self.in_vis_thre, self.oks_thre)
-        else:
-            keep = torch.zeros(0, dtype=torch.uint8, device=coords.device)
-            scores = torch.zeros(0, dtype=torch.float64, device=coords.device)
-        rows = pack_results(coords, conf, keep, scores)
-        if world == 1:
-            return rows
-        counts = [person_range(self.seg, self.cuts, r) for r in range(world)]
-        return gather_rows(rows, [b - a for a, b in counts], self.group)
+            ti = _abi.dense(_abi.to_device(trans_inv, torch.float32, dev), torch.float32)
+            area64 = _abi.to_device(areas, torch.float64, dev).reshape(-1)
+        bs = _abi.to_device(box_scores, torch.float64, dev).reshape(-1)
+        if tuple(ti.shape) != (n, 2, 3) or bs.shape[0] != n or (area64 is not None and area64.shape[0] != n):
+            raise ValueError("trans_inv / box_scores / areas must describe this rank's %d persons" % n)
+        st = self._state(dev)
+        buf = st["buffer"]
+        width = buf.shape[-1]
+        blur = self.decoder._weights_on(dev)
+        lib = _abi.lib()
+        stream = _abi.stream_ptr(dev)
+        ws = _abi.scratch(dev, stream, 16, "decode")
+        map_elems = k * h * w
+        handles = []
+        a = 0
+        with torch.cuda.device(dev):
+            for c, cnt in enumerate(self.counts[rank]):
+                slot = buf[c, rank]
+                if cnt > 0:
+                    b = a + cnt
+                    _abi.check_ws(lib.sp_decode_rows_f32(
+                        hm.data_ptr() + 4 * a * map_elems, None if hf is None else hf.data_ptr() + 4 * a * map_elems,
+                        _abi.ptr(perm), ti.data_ptr() + 24 * a, blur.data_ptr(), slot.data_ptr(), width, None, None,
+                        cnt, k, h, w, int(self.decoder.kernel_size), _abi.SP_DECODE_GAUSS_TAYLOR,
+                        ws.data_ptr(), ws.numel() * 8, stream), dev, stream)
+                    _abi.check(lib.sp_eval_rows_nms_f32(
+                        slot.data_ptr(), width, bs.data_ptr() + 8 * a,
+                        None if area64 is None else area64.data_ptr() + 8 * a,
+                        None if area32 is None else area32.data_ptr() + 4 * a,
+                        st["seg"][c].data_ptr(), None, None, cnt, st["images"][c], k, st["max_seg"][c],
+                        self.in_vis_thre, self.oks_thre, stream))
+                    a = b
+                if world > 1:
+                    # in place: this rank's slot already lies where the collective puts it; NCCL's stream waits for
+                    # the two kernels above and runs while the next chunk is being decoded on this stream
+                    handles.append(gather_chunk(buf[c], rank, self.group, async_op=True))
+        for hnd in handles:
+            hnd.wait()                               # stream-level: later work on this stream sees the gathered rows
+        table = ShardedTable(buf, self.counts)
+        if not compact:
+            return table                             # the transport buffer itself: valid until the next run()
+        rows = table.rows()
+        return rows.clone() if rows.data_ptr() == buf.data_ptr() and rows.numel() else rows

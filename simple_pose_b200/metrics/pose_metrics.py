@@ -13,18 +13,31 @@ from .. import _abi
 from ..commons.joint_utils import swap_permutation
 
 
+# cv.getGaussianKernel(n, 0) returns these fixed tables for n <= 9 (OpenCV's small_gaussian_tab, extended to 9
+# in 4.x), not the closed form
+_OPENCV_FIXED_TAPS = {
+    1: (1.0,),
+    3: (0.25, 0.5, 0.25),
+    5: (0.0625, 0.25, 0.375, 0.25, 0.0625),
+    7: (0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125),
+    9: (4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256, 51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256),
+}
+
+
 def gaussian_kernel_1d(kernel_size):
     """``cv.getGaussianKernel(kernel_size, 0)`` (float64 column). OpenCV itself when importable
-    (as the reference does, pose_metrics.py:57); otherwise its closed form for n > 7
-    (sigma = 0.3*((n-1)*0.5-1)+0.8, normalised exp(-x^2/(2 sigma^2))), which gives bit-identical
-    float32 2-D weights for the reference's kernel_size = 11."""
+    (as the reference does, pose_metrics.py:57); otherwise its fixed tables for n <= 9 and its closed
+    form above that (sigma = 0.3*((n-1)*0.5-1)+0.8, normalised exp(-x^2/(2 sigma^2))), which gives
+    bit-identical float32 2-D weights for the reference's kernel_size = 11."""
     n = int(kernel_size)
     try:
         import cv2
         return cv2.getGaussianKernel(n, 0)
     except ImportError:
-        if n <= 7:
-            raise RuntimeError("kernel_size <= 7 needs OpenCV's fixed tables (cv2 not importable)")
+        if n in _OPENCV_FIXED_TAPS:
+            return np.array(_OPENCV_FIXED_TAPS[n], dtype=np.float64).reshape(-1, 1)
+        if n < 11 or n % 2 == 0:
+            raise RuntimeError("kernel_size %d needs OpenCV (cv2 not importable)" % n)
         sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8
         x = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
         g = np.exp(-(x * x) / (2.0 * sigma * sigma))
@@ -53,10 +66,10 @@ def _decode(heat_map, heat_map_flip, perm, trans_inv, blur_w, ksize, mode, want_
     stream = _abi.stream_ptr(dev)
     ws = _abi.scratch(dev, stream, 16, "decode")
     with torch.cuda.device(dev):
-        _abi.check(_abi.lib().sp_decode_ws_f32(hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), _abi.ptr(ti),
-                                               _abi.ptr(blur_w), coords.data_ptr(), maxval.data_ptr(),
-                                               _abi.ptr(index), b, k, h, w, int(ksize), int(mode),
-                                               ws.data_ptr(), ws.numel() * 8, stream))
+        _abi.check_ws(_abi.lib().sp_decode_ws_f32(hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), _abi.ptr(ti),
+                                                  _abi.ptr(blur_w), coords.data_ptr(), maxval.data_ptr(),
+                                                  _abi.ptr(index), b, k, h, w, int(ksize), int(mode),
+                                                  ws.data_ptr(), ws.numel() * 8, stream), dev, stream)
     if want_index:
         return coords, maxval, index
     return coords, maxval
@@ -176,11 +189,25 @@ class HeatMapAcc(object):
                                      self.distance_thresh, self.norm_frac)
 
 
+def person_rows(predicts, scores):
+    """[B,K,2], [B,K,1] device tensors -> float32 [B, 3K+1] device table: (x, y, conf) * K, then the
+    person score mean(conf) + max(conf) of ``kps_to_dict_``; one launch of ``sp_person_rows_f32``."""
+    dev = _abi.require_cuda(predicts, scores)
+    if predicts.dim() != 3 or predicts.shape[-1] != 2 or scores.numel() != predicts.shape[0] * predicts.shape[1]:
+        raise ValueError("predicts must be [B, K, 2] and scores [B, K, 1]")
+    n, k = int(predicts.shape[0]), int(predicts.shape[1])
+    c = _abi.dense(predicts.detach(), torch.float32)
+    m = _abi.dense(scores.detach(), torch.float32)
+    rows = torch.empty((n, 3 * k + 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(_abi.lib().sp_person_rows_f32(c.data_ptr(), m.data_ptr(), rows.data_ptr(), n, k, _abi.stream_ptr(dev)))
+    return rows
+
+
 def kps_to_dict_(predicts, scores, img_ids, set_in_list):
-    """Reference :172-179 with ONE device->host copy instead of one ``.item()`` + ``.tolist()``
-    per person: score = mean + max of the joint peaks, keypoints = [x, y, score] * K."""
-    sc = scores.reshape(scores.shape[0], -1)
-    person = (sc.mean(dim=1) + sc.max(dim=1)[0]).cpu().tolist()
-    flat = torch.cat([predicts, scores], dim=-1).reshape(predicts.shape[0], -1).cpu().tolist()
-    for kp, s, img_id in zip(flat, person, img_ids):
-        set_in_list.append({"image_id": img_id, "score": float(s), "category_id": 1, "keypoints": kp})
+    """Reference :172-179 with ONE kernel and ONE device->host copy instead of a ``mean``/``max``/``cat``
+    chain plus one ``.item()`` and one ``.tolist()`` (two device syncs) per person:
+    score = mean + max of the joint peaks, keypoints = [x, y, score] * K."""
+    rows = person_rows(predicts, scores).cpu().tolist()
+    for row, img_id in zip(rows, img_ids):
+        set_in_list.append({"image_id": img_id, "score": float(row[-1]), "category_id": 1, "keypoints": row[:-1]})

@@ -44,40 +44,68 @@ class HeatmapHotPath(object):
         self.pred_xy = self.label_xy = None
         self._lib = _abi.lib()
 
+    def _checked(self, t, shape, name, dtype=torch.float32):
+        """The raw-pointer calls below read ``t`` as a dense tensor of exactly this shape and dtype on
+        this object's device: anything else would be an out-of-bounds read, so it raises instead."""
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise RuntimeError("%s must be a tensor on %s (there is no CPU path)" % (name, self.device))
+        if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous %s tensor of shape %s, got %s %s%s" % (
+                name, dtype, tuple(shape), t.dtype, tuple(t.shape), "" if t.is_contiguous() else " (non-contiguous)"))
+        return t
+
+    def _maps(self, t, name):
+        return self._checked(t, (self.batch, self.k, self.h, self.w), name)
+
     # each method enqueues exactly one kernel on the current stream of self.device
     def encode(self, joints):
-        _abi.check(self._lib.sp_encode_f32(joints.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
-                                           self.batch, self.k, self.h, self.w, self.sigma,
-                                           _abi.stream_ptr(self.device)))
+        self._checked(joints, (self.batch, self.k, 3), "joints")
+        with torch.cuda.device(self.device):
+            _abi.check(self._lib.sp_encode_f32(joints.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
+                                               self.batch, self.k, self.h, self.w, self.sigma,
+                                               _abi.stream_ptr(self.device)))
 
     def loss_fwd_bwd(self, pred):
-        stream = _abi.stream_ptr(self.device)
-        ws = _workspace(self.device, stream)
-        _abi.check(self._lib.sp_mse_fwd_bwd_f32(pred.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
-                                                self.grad.data_ptr(), self.loss.data_ptr(), ws.data_ptr(),
-                                                ws.numel() * 8, self.batch, self.k, self.h * self.w, 1.0, 0, stream))
+        self._maps(pred, "pred")
+        with torch.cuda.device(self.device):
+            stream = _abi.stream_ptr(self.device)
+            ws = _workspace(self.device, stream)
+            _abi.check_ws(self._lib.sp_mse_fwd_bwd_f32(pred.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
+                                                       self.grad.data_ptr(), self.loss.data_ptr(), ws.data_ptr(),
+                                                       ws.numel() * 8, self.batch, self.k, self.h * self.w, 1.0, 0, stream),
+                          self.device, stream)
 
     def train_fused(self, joints, pred, with_acc=True):
         """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) in one launch; targets never materialised."""
         if with_acc and self.pred_xy is None:
             self.pred_xy = torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=self.device)
             self.label_xy = torch.empty_like(self.pred_xy)
-        stream = _abi.stream_ptr(self.device)
-        ws = _workspace(self.device, stream)
-        _abi.check(self._lib.sp_encode_mse_fwd_bwd_f32(
-            joints.data_ptr(), pred.data_ptr(), self.grad.data_ptr(), None, self.weights.data_ptr(),
-            self.loss.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
-            _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
-            self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream))
+        self._checked(joints, (self.batch, self.k, 3), "joints")
+        self._maps(pred, "pred")
+        with torch.cuda.device(self.device):
+            stream = _abi.stream_ptr(self.device)
+            ws = _workspace(self.device, stream)
+            _abi.check_ws(self._lib.sp_encode_mse_fwd_bwd_f32(
+                joints.data_ptr(), pred.data_ptr(), self.grad.data_ptr(), None, self.weights.data_ptr(),
+                self.loss.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
+                _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
+                self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream), self.device, stream)
 
     def decode(self, pred, trans_inv, pred_flip=None, perm=None):
-        stream = _abi.stream_ptr(self.device)
-        ws = _abi.scratch(self.device, stream, 16, "decode")
-        _abi.check(self._lib.sp_decode_ws_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
-                                              _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
-                                              self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
-                                              self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
-                                              stream))
+        self._maps(pred, "pred")
+        if trans_inv is not None:
+            self._checked(trans_inv, (self.batch, 2, 3), "trans_inv")
+        if pred_flip is not None:
+            self._maps(pred_flip, "pred_flip")
+            self._checked(perm, (self.k,), "perm", torch.int32)
+        with torch.cuda.device(self.device):
+            stream = _abi.stream_ptr(self.device)
+            ws = _abi.scratch(self.device, stream, 16, "decode")
+            _abi.check_ws(self._lib.sp_decode_ws_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
+                                                     _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
+                                                     self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
+                                                     self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
+                                                     stream), self.device, stream)
 
     def step(self, joints, pred, trans_inv):
         """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches, two orders.

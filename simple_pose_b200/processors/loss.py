@@ -14,18 +14,9 @@ import torch
 
 from .. import _abi
 
-_workspaces = {}
-
-
 def _workspace(device, stream_id):
-    """Zero-initialised scratch per (device, stream); the kernel restores the zero state."""
-    key = (device.index, stream_id)
-    ws = _workspaces.get(key)
-    if ws is None:
-        nbytes = int(_abi.lib().sp_mse_workspace_bytes())
-        ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
-        _workspaces[key] = ws
-    return ws
+    """Zero-initialised reduction workspace per (device, stream); the kernel restores the zero state."""
+    return _abi.scratch(device, stream_id, int(_abi.lib().sp_mse_workspace_bytes()), "mse")
 
 
 def mse_forward_backward(pred, target, mask, need_grad=True, grad_scale=1.0, skip_masked=False):
@@ -48,9 +39,9 @@ def mse_forward_backward(pred, target, mask, need_grad=True, grad_scale=1.0, ski
     ws = _workspace(dev, stream)
     flags = _abi.SP_MSE_SKIP_MASKED if skip_masked else 0
     with torch.cuda.device(dev):
-        _abi.check(_abi.lib().sp_mse_fwd_bwd_f32(p.data_ptr(), t.data_ptr(), m.data_ptr(), _abi.ptr(grad),
-                                                 loss.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                                 b, k, hw, float(grad_scale), flags, stream))
+        _abi.check_ws(_abi.lib().sp_mse_fwd_bwd_f32(p.data_ptr(), t.data_ptr(), m.data_ptr(), _abi.ptr(grad),
+                                                    loss.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                                    b, k, hw, float(grad_scale), flags, stream), dev, stream)
     return loss, grad
 
 
@@ -127,10 +118,10 @@ def encode_mse_forward_backward(joints, pred, sigma=2.0, need_grad=True, want_ta
             out["label_xy"] = BasicKeyPointDecoder.heat_map_to_axis(tg * m)[0]
         return out
     with torch.cuda.device(dev):
-        _abi.check(_abi.lib().sp_encode_mse_fwd_bwd_f32(
+        _abi.check_ws(_abi.lib().sp_encode_mse_fwd_bwd_f32(
             j.data_ptr(), p.data_ptr(), _abi.ptr(out["grad"]), _abi.ptr(out["targets"]), out["weights"].data_ptr(),
             out["loss"].data_ptr(), _abi.ptr(out["pred_xy"]), _abi.ptr(out["label_xy"]), ws.data_ptr(), ws.numel() * 8,
-            b, k, h, w, float(sigma), float(grad_scale), stream))
+            b, k, h, w, float(sigma), float(grad_scale), stream), dev, stream)
     return out
 
 

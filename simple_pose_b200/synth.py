@@ -220,3 +220,73 @@ def train_samples(persons, num_joints=17, seed=0, img_w=(200, 640), img_h=(200, 
     flip = torch.rand(persons, generator=g, dtype=torch.float64) < flip_p
     return {"img_w": w_img.to(torch.int32), "boxes": boxes, "joints": joints_img,
             "scale_ratio": scale_ratio, "rot": rot_deg, "flip": flip}
+
+
+class EvalSet(object):
+    """A COCO-val-sized synthetic eval job (BASELINE config 5) whose content depends on the PERSON index
+    only -- never on how the persons are sharded -- so that the result table of a 1-, 2-, 4- or 8-GPU run
+    must be bit-identical. Images hold 1 + Poisson(mean_group) detections; inside an image a fraction
+    ``dup_frac`` of the detections are near-duplicates of another detection of the same image (the same
+    box jittered by N(0, box_jitter^2) px, the same peak centres jittered by N(0, jitter^2) heatmap px)
+    so that the OKS-NMS has something to suppress. Box scores are distinct.
+
+    Host metadata (``seg``, ``boxes``, ``box_scores``, ``leader``, ``mu``) is generated at once on the CPU;
+    heatmaps are rendered on the device in fixed global blocks of ``block`` persons (``heatmaps(lo, hi)``
+    renders any person range on any rank)."""
+
+    def __init__(self, persons=104000, mean_group=20.0, joints=17, height=64, width=48, seed=12345,
+                 dup_frac=0.3, jitter=0.3, box_jitter=0.5, noise=0.01, block=2048):
+        g = _gen(seed, "cpu")
+        images = max(1, int(persons / (1.0 + mean_group)))
+        sizes = 1 + torch.poisson(torch.full((images,), float(mean_group)), generator=g).long()
+        seg = torch.zeros(images + 1, dtype=torch.int64)
+        seg[1:] = torch.cumsum(sizes, 0)
+        n = int(seg[-1])
+        self.seg = seg.numpy()
+        self.persons, self.images = n, images
+        self.joints, self.height, self.width = joints, height, width
+        self.seed, self.noise, self.block = int(seed), noise, int(block)
+        image_of = torch.repeat_interleave(torch.arange(images), sizes)
+        first = seg[:-1][image_of]                                   # first person of each person's image
+        pos = torch.arange(n) - first
+        # a follower copies an EARLIER detection of its image (position 0 is always an original)
+        is_dup = (torch.rand(n, generator=g) < dup_frac) & (pos > 0)
+        pick = (torch.rand(n, generator=g) * pos.clamp(min=1).double()).long().clamp(max=(pos - 1).clamp(min=0))
+        leader = torch.where(is_dup, first + pick, torch.arange(n))
+        for _ in range(8):                                            # followers of followers -> the original
+            leader = leader[leader]
+        self.leader = leader
+        boxes = detection_boxes(n, seed=seed + 1)
+        boxes = boxes[leader] + torch.where(is_dup[:, None], box_jitter * torch.randn(n, 4, generator=g, dtype=torch.float64),
+                                            torch.zeros(n, 4, dtype=torch.float64))
+        self.boxes = boxes
+        mu = peak_centres(n, joints, height, width, seed + 2, "cpu")
+        mu = mu[leader] + torch.where(is_dup[:, None, None], jitter * torch.randn(n, joints, 2, generator=g), torch.zeros(n, joints, 2))
+        mu[..., 0].clamp_(0, width - 1)
+        mu[..., 1].clamp_(0, height - 1)
+        self.mu = mu
+        self.box_scores = (torch.randperm(n, generator=g).double() + 0.5) / n
+        self.duplicates = int(is_dup.sum())
+
+    def heatmaps(self, lo, hi, device):
+        """float32 [hi-lo, K, H, W] on ``device`` for global persons [lo, hi)."""
+        out = torch.empty((hi - lo, self.joints, self.height, self.width), dtype=torch.float32, device=device)
+        b0 = lo // self.block
+        while b0 * self.block < hi:
+            s, e = b0 * self.block, min((b0 + 1) * self.block, self.persons)
+            a, b = max(s, lo), min(e, hi)
+            if b > a:
+                maps = heatmaps_from_centres(self.mu[s:e].to(device), self.height, self.width, self.seed + 100 + b0, self.noise)
+                out[a - lo:b - lo] = maps[a - s:b - s]
+            b0 += 1
+        return out
+
+
+def table_checksum(rows):
+    """Order-sensitive 64-bit digest of a float32 table (wrapping int64 arithmetic on the raw bits): equal
+    digests across runs <=> bit-identical tables in the same row order (up to 2^-64 collisions)."""
+    bits = rows.contiguous().view(torch.int32).to(torch.int64)
+    n, w = bits.shape
+    weight = (torch.arange(n, device=rows.device, dtype=torch.int64)[:, None] * 1000003 +
+              torch.arange(w, device=rows.device, dtype=torch.int64)[None, :] * 7919 + 1)
+    return int((bits * weight).sum().item())

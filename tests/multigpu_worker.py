@@ -24,27 +24,38 @@ def main():
     n = int(seg[-1])
     hm, hf = synth.flip_pair(n, seed=6)
     tinv, area = synth.inverse_affines(n, seed=6)
-    ev = ShardedPoseEvaluator(group=None)
-    ev.plan(seg.numpy())
-    lo, hi = ev.my_persons()
-    table = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev))
-    assert table.shape == (n, 53), table.shape
-    # single-device result computed on this rank's GPU without any collective
+    # single-device result computed on this rank's GPU without any collective, through the separate kernels
     solo = ShardedPoseEvaluator()
-    solo.seg, solo.cuts = seg.numpy().astype(np.int64), np.array([0, len(seg) - 1], dtype=np.int64)
     from simple_pose_b200.datasets.naive_data import pack_keypoints, rescore_and_nms
-    from simple_pose_b200.eval_shard import pack_results
+    from simple_pose_b200.eval_shard import pack_results, row_keep, row_scores, row_keypoints
     c, m = solo.decoder.flip_call(hm.to(dev), hf.to(dev), tinv.to(dev))
     keep, scores, _ = rescore_and_nms(pack_keypoints(c, m), box, area, seg.numpy())
     want = pack_results(c, m, keep, scores)
-    assert torch.equal(table, want), (table - want).abs().max().item()
+    tables = []
+    for chunks in (1, 2, 5):                     # 5 > images of some ranks: empty chunks take part in the collectives
+        ev = ShardedPoseEvaluator(group=None, chunks=chunks)
+        ev.plan(seg.numpy())
+        lo, hi = ev.my_persons()
+        for _ in range(2):                       # the transport buffer is reused by the second run
+            table = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev))
+        assert table.shape == (n, 54), table.shape
+        assert torch.equal(row_keypoints(table).reshape(n, 51), want[:, :51])
+        assert torch.equal(row_keep(table), keep.bool())
+        assert torch.equal(row_scores(table), scores)               # float64, not narrowed
+        tables.append(table)
+        # transport layout without the final concatenation
+        raw = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev),
+                     compact=False)
+        assert raw.persons == n and torch.equal(raw.rows(), table)
+    assert all(torch.equal(t, tables[0]) for t in tables)
+    table = tables[0]
     # every rank holds the same table
     ref = table.clone()
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, table)
     dist.barrier()
     if rank == 0:
-        print("sharded eval ok: %d persons, %d images, world %d, kept %d" % (n, len(seg) - 1, world, int(table[:, 51].sum())))
+        print("sharded eval ok: %d persons, %d images, world %d, kept %d" % (n, len(seg) - 1, world, int(row_keep(table).sum())))
     dist.destroy_process_group()
 
 

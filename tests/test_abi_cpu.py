@@ -59,7 +59,8 @@ def test_tma_bulk_copy_in_sass(lib):
 
 
 def test_argument_errors_without_gpu(lib):
-    assert lib.sp_abi_version() == 1
+    from simple_pose_b200 import _abi
+    assert lib.sp_abi_version() == _abi.ABI_VERSION == 2
     assert lib.sp_mse_workspace_bytes() >= 16
     assert b"aligned" in lib.sp_error_string(-2)
     assert lib.sp_error_string(0) == b"ok"
@@ -89,6 +90,15 @@ def test_argument_errors_without_gpu(lib):
     assert lib.sp_transform_joints_f32(16, None, None, None, None, 16, 1, 17, None) == -1                              # in place
     assert lib.sp_transform_joints_f32(16, None, 16, None, None, 32, 1, 17, None) == -1                                # flip w/o img_w / perm
     assert lib.sp_center_scale_rot_affine_f64(16, 16, None, None, None, None, 1, 48, 64, None) == -1                   # no output
+    # round 2: decoder -> result rows, fused rescoring + NMS on the rows, kps_to_dict_ table, tuning reload
+    assert lib.sp_decode_rows_f32(16, None, None, None, 16, None, 54, None, None, 1, 17, 64, 48, 11, 0, 16, 16, None) == -1   # no rows
+    assert lib.sp_decode_rows_f32(16, None, None, None, 16, 16, 50, None, None, 1, 17, 64, 48, 11, 0, 16, 16, None) == -1    # stride < 3K
+    assert lib.sp_eval_rows_nms_f32(16, 53, 16, 16, None, 16, None, None, 4, 1, 17, 4, 0.2, 0.9, None) == -1                 # stride < 3K+3
+    assert lib.sp_eval_rows_nms_f32(16, 54, 16, None, None, 16, None, None, 4, 1, 17, 4, 0.2, 0.9, None) == -1               # no areas
+    assert lib.sp_eval_rows_nms_f32(None, 54, None, None, None, None, None, None, 0, 0, 17, 0, 0.2, 0.9, None) == 0
+    assert lib.sp_person_rows_f32(None, 16, 16, 1, 17, None) == -1
+    assert lib.sp_person_rows_f32(None, None, None, 0, 17, None) == 0
+    assert lib.sp_reload_tuning() == 0
     # empty batches are a no-op success
     assert lib.sp_encode_f32(None, None, None, 0, 17, 64, 48, 2.0, None) == 0
     assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 0, 17, 64, 48, 11, 0, None) == 0

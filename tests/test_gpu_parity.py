@@ -82,11 +82,13 @@ def test_encode_cta_sizes_agree(api, warps):
     joints = synth.joints(37, seed=321).to(DEV)
     base_t, base_w = api.transforms.encode_heat_maps(joints)
     os.environ["SP_ENCODE_WARPS"] = warps
+    api.abi.reload_tuning()
     try:
         t, w = api.transforms.encode_heat_maps(joints)
         t2, w2 = api.transforms.encode_heat_maps(joints[:, :, :], 2.0, (48, 64))
     finally:
         del os.environ["SP_ENCODE_WARPS"]
+        api.abi.reload_tuning()
     assert torch.equal(t, base_t) and torch.equal(w, base_w) and torch.equal(t2, base_t) and torch.equal(w2, base_w)
 
 
@@ -98,12 +100,15 @@ def test_encode_row_parts_agree(api, parts, shape):
     w, h = shape
     joints = synth.joints(21, height=h, width=w, seed=654).to(DEV)
     os.environ["SP_ENCODE_PARTS"] = "1"
+    api.abi.reload_tuning()
     try:
         base_t, base_w = api.transforms.encode_heat_maps(joints, 2.0, shape)
         os.environ["SP_ENCODE_PARTS"] = parts
+        api.abi.reload_tuning()
         t, wt = api.transforms.encode_heat_maps(joints, 2.0, shape)
     finally:
         del os.environ["SP_ENCODE_PARTS"]
+        api.abi.reload_tuning()
     auto_t, auto_w = api.transforms.encode_heat_maps(joints, 2.0, shape)
     assert torch.equal(t, base_t) and torch.equal(wt, base_w) and torch.equal(auto_t, base_t) and torch.equal(auto_w, base_w)
 
@@ -256,10 +261,12 @@ def test_decode_generic_path_matches_fast_path(api):
     dec = api.metrics.GaussTaylorKeyPointDecoder()
     a = dec.decode_with_index(hm)
     os.environ["SP_DECODE_FORCE_GENERIC"] = "1"
+    api.abi.reload_tuning()
     try:
         b = dec.decode_with_index(hm)
     finally:
         del os.environ["SP_DECODE_FORCE_GENERIC"]
+        api.abi.reload_tuning()
     assert torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
     assert (a[0] - b[0]).abs().max().item() <= 1e-5
 
@@ -270,10 +277,12 @@ def test_decode_ring_configurations(api, warps, stages):
     hm = synth.heatmaps(40, seed=6)
     ref_hsp, ref_max = O.gauss_taylor_decode(hm, None, return_heatmap_space=True)
     os.environ["SP_DECODE_WARPS"], os.environ["SP_DECODE_STAGES"] = str(warps), str(stages)
+    api.abi.reload_tuning()
     try:
         check_decode(api, hm, None, None, ref_hsp.numpy(), ref_max.numpy(), O.argmax_index(hm).numpy())
     finally:
         del os.environ["SP_DECODE_WARPS"], os.environ["SP_DECODE_STAGES"]
+        api.abi.reload_tuning()
 
 
 def test_argmax_special_values(api):
@@ -480,10 +489,12 @@ def test_oks_nms_pair_matrix_path_equals_greedy_loop(api, mean_group):
     seg2 = np.array(cuts, dtype=np.int32)
     keep, rank = api.naive.oks_nms_batched(kps, box, area, seg2, 0.9)
     os.environ["SP_NMS_SERIAL"] = "1"
+    api.abi.reload_tuning()
     try:
         keep_s, rank_s = api.naive.oks_nms_batched(kps, box, area, seg2, 0.9)
     finally:
         del os.environ["SP_NMS_SERIAL"]
+        api.abi.reload_tuning()
     assert torch.equal(keep, keep_s) and torch.equal(rank, rank_s)
     sizes = np.diff(seg2)
     assert sizes.min() <= 2 and (sizes == 63).any() and (sizes == 64).any() and (sizes == 65).any()
@@ -541,6 +552,95 @@ def test_pack_rows_equals_torch_composition(api):
         assert rows.shape == (n, 3 * k + 2) and torch.equal(rows, want)
     with pytest.raises(RuntimeError, match="no CPU path"):
         pack_results(coords.cpu(), conf.cpu(), keep.cpu(), scores.cpu())
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+@pytest.mark.parametrize("use_boxes,flip", [(True, False), (False, True)])
+def test_sharded_evaluator_single_rank_fused_rows(api, chunks, use_boxes, flip):
+    """ShardedPoseEvaluator (decoder writing the result rows, rescoring + NMS fused on the rows) against the
+    stand-alone kernels and the oracle: keypoints and keep flags identical, the float64 score bit-exact."""
+    from simple_pose_b200 import eval_shard
+    es = synth.EvalSet(persons=900, mean_group=7.0, seed=31)
+    n = es.persons
+    hm = es.heatmaps(0, n, "cpu")
+    hf = synth.heatmaps(n, seed=32) if flip else None
+    ev = eval_shard.ShardedPoseEvaluator(chunks=chunks)
+    ev.plan(es.seg)
+    assert ev.my_persons() == (0, n)
+    c_, s_, area_np, tinv_np = O.box_affines(es.boxes.tolist())
+    if use_boxes:
+        rows = ev.run(hm.to(DEV), None, es.box_scores, None, boxes=es.boxes.to(DEV), heat_map_flip=None if hf is None else hf.to(DEV))
+    else:
+        rows = ev.run(hm.to(DEV), torch.from_numpy(tinv_np).to(DEV), es.box_scores, torch.from_numpy(area_np).double(),
+                      heat_map_flip=None if hf is None else hf.to(DEV))
+    assert rows.shape == (n, 54) and rows.dtype == torch.float32
+    dec = api.metrics.GaussTaylorKeyPointDecoder()
+    tinv = torch.from_numpy(tinv_np).to(DEV)
+    xy, conf = dec.flip_call(hm.to(DEV), hf.to(DEV), tinv) if flip else dec(hm.to(DEV), tinv)
+    kps = api.naive.pack_keypoints(xy, conf)
+    keep, scores, _ = api.naive.rescore_and_nms(kps, es.box_scores, torch.from_numpy(area_np).double(), es.seg.astype(np.int32))
+    assert torch.equal(eval_shard.row_keypoints(rows), torch.cat([xy, conf], -1))
+    assert torch.equal(eval_shard.row_keep(rows), keep.bool())
+    assert torch.equal(eval_shard.row_scores(rows), scores)
+    o_keep, o_scores, _ = O.rescore_and_nms(kps.cpu().numpy(), es.box_scores.numpy(), area_np.astype(np.float64), es.seg.astype(np.int32))
+    assert np.array_equal(eval_shard.row_keep(rows).cpu().numpy(), o_keep)
+    assert np.allclose(eval_shard.row_scores(rows).cpu().numpy(), o_scores, rtol=1e-15, atol=0)
+    assert 0 < int(o_keep.sum()) < n - 50                       # the duplicate detections are really suppressed
+    raw = ev.run(hm.to(DEV), tinv, es.box_scores, torch.from_numpy(area_np).double(),
+                 heat_map_flip=None if hf is None else hf.to(DEV), compact=False)
+    assert raw.buffer.shape[:2] == (chunks, 1) and raw.persons == n and torch.equal(raw.rows(), rows)
+    with pytest.raises(ValueError):
+        ev.run(hm[:-1].to(DEV), tinv[:-1], es.box_scores[:-1], torch.from_numpy(area_np[:-1]).double())
+
+
+def test_kps_to_dict_on_device(api):
+    """A10 (metrics/pose_metrics.py:172-179) with CUDA tensors: one kernel + one D2H; keypoints are the
+    decoder's floats exactly, the score mean(conf) + max(conf) agrees with the reference's float32 torch
+    reductions to 1 ulp (its summation order is not defined across torch's CPU and CUDA kernels)."""
+    hm = synth.heatmaps(33, seed=77)
+    tinv, _ = synth.inverse_affines(33, seed=77)
+    xy, conf = api.metrics.GaussTaylorKeyPointDecoder()(hm.to(DEV), tinv.to(DEV))
+    got, want = [], []
+    ids = list(range(500, 533))
+    api.metrics.kps_to_dict_(xy, conf, ids, got)
+    O.kps_to_dict(xy.cpu(), conf.cpu(), ids, want)
+    assert len(got) == len(want) == 33
+    for g, w in zip(got, want):
+        assert g["image_id"] == w["image_id"] and g["category_id"] == 1
+        assert g["keypoints"] == w["keypoints"]
+        assert abs(g["score"] - w["score"]) <= 2.4e-7 * abs(w["score"])
+    rows = api.metrics.person_rows(xy, conf)
+    assert rows.shape == (33, 52) and torch.equal(rows[:, :51].reshape(33, 17, 3), torch.cat([xy, conf], -1))
+    nan_conf = conf.clone()
+    nan_conf[3, 5] = float("nan")
+    assert torch.isnan(api.metrics.person_rows(xy, nan_conf)[3, -1]) and not torch.isnan(api.metrics.person_rows(xy, nan_conf)[4, -1])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.metrics.kps_to_dict_(xy.cpu(), conf.cpu(), ids, [])
+    empty = []
+    api.metrics.kps_to_dict_(xy[:0], conf[:0], [], empty)
+    assert empty == []
+
+
+def test_pipeline_rejects_what_it_cannot_read(api):
+    """HeatmapHotPath hands raw pointers to the C ABI: wrong dtype / shape / layout / device must raise."""
+    from simple_pose_b200.pipeline import HeatmapHotPath
+    hp = HeatmapHotPath(4, 17, 64, 48, device=DEV)
+    joints = synth.joints(4, seed=1).to(DEV)
+    pred = synth.heatmaps(4, seed=1).to(DEV)
+    tinv = synth.identity_affines(4, device=DEV)
+    hp.step(joints, pred, tinv)
+    for bad in (pred.half(), pred[:3], pred.permute(0, 1, 3, 2), pred.double()):
+        with pytest.raises(ValueError):
+            hp.loss_fwd_bwd(bad)
+        with pytest.raises(ValueError):
+            hp.decode(bad, tinv)
+        with pytest.raises(ValueError):
+            hp.train_fused(joints, bad)
+    with pytest.raises(ValueError):
+        hp.encode(joints.double())
+    with pytest.raises(RuntimeError):
+        hp.encode(joints.cpu())
+    torch.cuda.synchronize()
 
 
 def test_errors_are_loud(api):
@@ -788,6 +888,7 @@ def test_fused_kernel_variants_agree(api, env, hw):
     slim = api.loss.encode_mse_forward_backward(joints, pred, want_axes=True)
     bare = api.loss.encode_mse_forward_backward(joints, pred)
     os.environ.update(env)
+    api.abi.reload_tuning()
     try:
         other = api.loss.encode_mse_forward_backward(joints, pred, want_targets=True, want_axes=True)
         other_slim = api.loss.encode_mse_forward_backward(joints, pred, want_axes=True)
@@ -795,6 +896,7 @@ def test_fused_kernel_variants_agree(api, env, hw):
     finally:
         for k in env:
             del os.environ[k]
+            api.abi.reload_tuning()
     for key in ("grad", "targets", "weights", "pred_xy", "label_xy"):
         assert torch.equal(base[key].nan_to_num(nan=7.0), other[key].nan_to_num(nan=7.0)), key
         for alt in (slim, other_slim):      # period-tiled kernel (no targets requested)
@@ -831,10 +933,12 @@ def test_fused_label_argmax_ties_and_outside_centres(api):
     out = api.loss.encode_mse_forward_backward(j.to(DEV), pred, need_grad=False, want_axes=True)
     assert torch.equal(out["label_xy"].cpu(), want)
     os.environ["SP_TRAIN_FORCE_LDG"] = "1"
+    api.abi.reload_tuning()
     try:
         out2 = api.loss.encode_mse_forward_backward(j.to(DEV), pred, need_grad=False, want_axes=True)
     finally:
         del os.environ["SP_TRAIN_FORCE_LDG"]
+        api.abi.reload_tuning()
     assert torch.equal(out2["label_xy"].cpu(), want)
     # sigma outside the analytic range falls back to the tracked argmax
     t3 = np.stack([O.encode_person(x, 0.2, (48, 64))[0] for x in j.numpy()[:8]])
@@ -863,12 +967,14 @@ def test_loss_kernel_variants_agree(api, env, b, hw):
     fwd_only, none = api.loss.mse_forward_backward(pred, tgt, msk, need_grad=False)
     assert none is None and fwd_only.item() == base_loss.item()
     os.environ.update(env)
+    api.abi.reload_tuning()
     try:
         loss, grad = api.loss.mse_forward_backward(pred, tgt, msk)
         loss_f, _ = api.loss.mse_forward_backward(pred, tgt, msk, need_grad=False)
     finally:
         for k in env:
             del os.environ[k]
+            api.abi.reload_tuning()
     assert torch.equal(grad, base_grad)
     assert abs(loss.item() - base_loss.item()) <= 1e-6 * abs(base_loss.item())
     assert loss_f.item() == loss.item()
@@ -907,10 +1013,12 @@ def test_back_to_back_dependent_launches(api):
         return losses.clone(), coords.clone()
 
     os.environ["SP_NO_PDL"] = "1"
+    api.abi.reload_tuning()
     try:
         want_l, want_c = chain(sync=True)
     finally:
         del os.environ["SP_NO_PDL"]
+        api.abi.reload_tuning()
     for _ in range(3):
         got_l, got_c = chain(sync=False)
         assert torch.equal(got_l, want_l) and torch.equal(got_c, want_c)
@@ -925,10 +1033,12 @@ def test_decode_work_distribution_covers_every_map(api, b, k):
     dec = api.metrics.GaussTaylorKeyPointDecoder(num_joints=k)
     got = dec.decode_with_index(hm)
     os.environ["SP_DECODE_FORCE_GENERIC"] = "1"
+    api.abi.reload_tuning()
     try:
         want = dec.decode_with_index(hm)
     finally:
         del os.environ["SP_DECODE_FORCE_GENERIC"]
+        api.abi.reload_tuning()
     assert torch.equal(got[2], want[2]) and torch.equal(got[1], want[1])
     assert (got[0] - want[0]).abs().max().item() <= 1e-5
     assert torch.equal(got[2].long().cpu(), O.argmax_index(hm.cpu()))
@@ -946,12 +1056,15 @@ def test_decode_grid_wide_dealing_equals_equal_ranges(api, b, hw, flip):
     dec = api.metrics.GaussTaylorKeyPointDecoder()
     run = (lambda: dec.flip_call(hm, hf, tinv)) if flip else (lambda: dec(hm, tinv))
     os.environ["SP_DECODE_GRID_WIDE"] = "1"              # by default only items >= 40 KB are dealt grid-wide
+    api.abi.reload_tuning()
     try:
         got = [run() for _ in range(6)]
         os.environ["SP_DECODE_GRID_WIDE"] = "0"
+        api.abi.reload_tuning()
         want = run()
     finally:
         del os.environ["SP_DECODE_GRID_WIDE"]
+        api.abi.reload_tuning()
     got.append(run())                                    # the default policy
     for c, m in got:
         assert torch.equal(c, want[0]) and torch.equal(m, want[1])

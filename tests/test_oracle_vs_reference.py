@@ -176,9 +176,9 @@ def test_eval_rescoring_and_nms_through_the_reference_function(ref, vis, thr):
 
 
 def test_kps_to_dict_host_formatting(ref):
-    """A10: the drop-in's batched formatting (one device->host copy) against the reference's per-person
-    loop (metrics/pose_metrics.py:172-179) on host tensors: identical lists of dicts."""
-    from simple_pose_b200.metrics.pose_metrics import kps_to_dict_
+    """A10: the restatement of the reference's per-person loop (metrics/pose_metrics.py:172-179) on host
+    tensors: identical lists of dicts. (The product's kernel is compared with it under -m gpu.)"""
+    from oracle import heatmap_oracle as O
     g = torch.Generator().manual_seed(0)
     for _ in range(50):
         n = 9
@@ -186,5 +186,5 @@ def test_kps_to_dict_host_formatting(ref):
         sc = torch.rand(n, 17, 1, generator=g)
         a, b = [], []
         ref.kps_to_dict_(pred, sc, list(range(100, 100 + n)), a)
-        kps_to_dict_(pred, sc, list(range(100, 100 + n)), b)
+        O.kps_to_dict(pred, sc, list(range(100, 100 + n)), b)
         assert a == b
