@@ -99,6 +99,23 @@ int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const float* mask
                        float* grad, float* loss, void* workspace, size_t workspace_bytes,
                        int B, int K, int HW, float grad_scale, int flags, void* stream);
 
+/* A2 under torch.cuda.amp (processors/dp_pose_hrnet_solver.py:111-120): `pred` in the autocast dtype, gradient in
+ * the same dtype, arithmetic in float32 exactly as autocast runs the expression (the fp16 * fp32 product promotes
+ * to float32, mse_loss is on autocast's float32 list, d loss / d pred is cast to pred's dtype once, after the
+ * upstream gradient has been applied in float32).
+ *   pred_dtype       SP_DTYPE_F32 / SP_DTYPE_F16 / SP_DTYPE_BF16; grad (nullable) has the same dtype
+ *   loss             nullable: NULL = backward only (no reduction, workspace unused)
+ *   grad_scale_dev   nullable device scalar (f32): the upstream gradient d L / d loss, e.g. GradScaler's scale,
+ *                    multiplied with grad_scale on the device -- autograd's backward never has to read it
+ *                    on the host. At least one of loss / grad must be given.
+ * SP_DTYPE_F32 with loss != NULL and grad_scale_dev == NULL is sp_mse_fwd_bwd_f32 itself. */
+#define SP_DTYPE_F32  0
+#define SP_DTYPE_F16  1
+#define SP_DTYPE_BF16 2
+int sp_mse_fwd_bwd(const void* pred, int pred_dtype, const float* target, const float* mask,
+                   void* grad, float* loss, void* workspace, size_t workspace_bytes,
+                   int B, int K, int HW, float grad_scale, const float* grad_scale_dev, int flags, void* stream);
+
 /* A1+A2(+HeatMapAcc) fused -- SURVEY section 8f ranks 1 and 2: targets are encoded on the fly and never
  * written (unless `targets` is given), so one pass reads pred and writes grad.
  *   targets, mask = get_heat_map(joints)                        commons/transforms.py:167-191
@@ -113,6 +130,33 @@ int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred, float* gra
                               float* weights, float* loss, float* pred_xy, float* label_xy,
                               void* workspace, size_t workspace_bytes,
                               int B, int K, int H, int W, double sigma, float grad_scale, void* stream);
+
+/* The same with `pred` / `grad` in the autocast dtype and the upstream gradient read on the device
+ * (see sp_mse_fwd_bwd for pred_dtype, loss == NULL and grad_scale_dev). float16 / bfloat16 inputs, backward-only
+ * calls and device-side scales run the plain-load kernel; SP_DTYPE_F32 with loss and without grad_scale_dev is
+ * sp_encode_mse_fwd_bwd_f32 itself. */
+int sp_encode_mse_fwd_bwd(const float* joints, const void* pred, int pred_dtype, void* grad, float* targets,
+                          float* weights, float* loss, float* pred_xy, float* label_xy,
+                          void* workspace, size_t workspace_bytes,
+                          int B, int K, int H, int W, double sigma, float grad_scale, const float* grad_scale_dev,
+                          void* stream);
+
+/* The whole per-batch path over a predicted map in ONE launch: A1 + A2 (+ HeatMapAcc argmaxes) + A3/A4/A5, i.e.
+ * sp_encode_f32 + sp_mse_fwd_bwd_f32 + sp_decode_f32(SP_DECODE_GAUSS_TAYLOR) (+ the two heat_map_to_axis passes of
+ * HeatMapAcc) on the same `pred` -- the body of the solvers' val() loop (processors/dp_pose_hrnet_solver.py:150-161:
+ * loss, acc, decoder on one `predicts`) and, with grad, BASELINE configs 1 + 2 together. Every map is staged in
+ * shared memory once and read from HBM once.
+ *   joints [B,K,3] f32 heatmap px; pred [B,K,H,W] f32; trans_inv [B,2,3] f32 (NULL = heatmap-space coords);
+ *   blur_w [121] f32 (ksize must be 11); outputs: targets [B,K,H,W] (NULL = not materialised), weights [B,K]
+ *   (NULL ok), grad [B,K,H,W] (NULL = no backward), loss (1 f32), coords [B,K,2], maxval [B,K],
+ *   pred_xy / label_xy [B,K,2] (both NULL = skip). Workspace as sp_mse_fwd_bwd_f32.
+ * coords / maxval / targets / weights / grad / pred_xy / label_xy are bit-identical to the stand-alone entry points,
+ * the loss up to the float64 summation order. W % 4 != 0, ksize != 11 or maps too large for shared memory:
+ * SP_ERR_UNSUPPORTED (compose the stand-alone calls). */
+int sp_step_f32(const float* joints, const float* pred, const float* trans_inv, const float* blur_w,
+                float* targets, float* weights, float* grad, float* loss, float* coords, float* maxval,
+                float* pred_xy, float* label_xy, void* workspace, size_t workspace_bytes,
+                int B, int K, int H, int W, double sigma, int ksize, float grad_scale, void* stream);
 
 /* HeatMapAcc.__call__ epilogue, metrics/pose_metrics.py:225-245: per-joint fraction of persons whose
  * predicted argmax lies within distance_thresh (in units of (W,H)/norm_frac) of the target argmax, over

@@ -594,3 +594,17 @@ def kps_to_dict(predicts, scores, img_ids, out_list):
         out_list.append({"image_id": img_id, "score": float((sc.mean() + sc.max()).item()), "category_id": 1,
                          "keypoints": torch.cat([pd, sc], dim=-1).reshape(-1).cpu().tolist()})
 
+
+
+def detie_scores(scores):
+    """Distinct scores with the same ordering as ``scores`` where, among EQUAL values, the higher index ranks
+    higher -- the visiting order ``argsort()[::-1]`` yields when the sort underneath is stable. Not part of the
+    reference: ``oks_nms`` (datasets/naive_data.py:163) leaves the order of equal scores to ``numpy.argsort``'s
+    default (unstable) sort, whose tie order depends on NumPy's SIMD dispatch for the host CPU (on AVX-512 /
+    AVX2 builds even two equal scores among eight may swap). Feeding these scores to the reference removes
+    that freedom; the CUDA kernel's documented rule is exactly this order."""
+    scores = np.asarray(scores, dtype=np.float64)
+    order = np.lexsort((np.arange(scores.shape[0]), scores))        # ascending score, then ascending index
+    out = np.empty_like(scores)
+    out[order] = (np.arange(scores.shape[0], dtype=np.float64) + 1.0) / (scores.shape[0] + 1.0)
+    return out

@@ -23,6 +23,7 @@ c_ll = ctypes.c_longlong
 ABI_VERSION = 2
 SP_DECODE_GAUSS_TAYLOR, SP_DECODE_ARGMAX, SP_DECODE_BASIC, SP_DECODE_DARK_ORIGINAL = 0, 1, 2, 3
 SP_MSE_SKIP_MASKED = 1
+SP_DTYPE_F32, SP_DTYPE_F16, SP_DTYPE_BF16 = 0, 1, 2
 SP_BOX_XYXY, SP_BOX_XYWH = 0, 1
 
 # name -> (restype, argtypes); mirrors include/simple_pose_b200.h one to one
@@ -36,7 +37,11 @@ SIGNATURES = {
     "sp_mse_workspace_bytes": (c_size, []),
     "sp_mse_fwd_bwd_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_size,
                                    c_int, c_int, c_int, c_flt, c_int, c_void]),
+    "sp_mse_fwd_bwd": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_size,
+                               c_int, c_int, c_int, c_flt, c_void, c_int, c_void]),
     "sp_encode_mse_fwd_bwd_f32": (c_int, [c_void] * 9 + [c_size, c_int, c_int, c_int, c_int, c_dbl, c_flt, c_void]),
+    "sp_encode_mse_fwd_bwd": (c_int, [c_void, c_void, c_int] + [c_void] * 7 + [c_size, c_int, c_int, c_int, c_int, c_dbl, c_flt, c_void, c_void]),
+    "sp_step_f32": (c_int, [c_void] * 13 + [c_size, c_int, c_int, c_int, c_int, c_dbl, c_int, c_flt, c_void]),
     "sp_heatmap_acc_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_flt, c_flt, c_void]),
     "sp_scale_inplace_f32": (c_int, [c_void, c_ll, c_void, c_void]),
     "sp_decode_f32": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void,
@@ -134,6 +139,24 @@ def dense(t, dtype):
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def refuse_loader_worker(what):
+    """The per-sample drop-ins (``RefineSimpleTransform.get_heat_map`` ...) keep the reference's NumPy signature
+    but run on the GPU. The reference calls them from ``MSCOCO.__getitem__`` inside forked DataLoader workers
+    (``datasets/coco.py:58-60``), where CUDA cannot be initialised; say so instead of dying in a CUDA re-init."""
+    in_worker = False
+    try:
+        from torch.utils.data import get_worker_info
+        in_worker = get_worker_info() is not None
+    except Exception:
+        pass
+    if in_worker or torch.cuda._is_in_bad_fork():
+        raise RuntimeError(
+            "simple_pose_b200: %s was called inside a DataLoader worker / forked process. The kernels need a CUDA "
+            "context, which a forked worker cannot create. Ship the joints from the loader (204 B per person) and "
+            "encode the whole batch on the training device with commons.transforms.encode_heat_maps(joints) or "
+            "processors.loss.EncodeJointsMSELoss -- see INTEGRATION.md section 3." % what)
 
 
 def default_device():

@@ -122,7 +122,11 @@ class RefineSimpleTransform(object):
 
     @staticmethod
     def get_heat_map(joints, sigma=2.0, shape=(48, 64)):
-        """joints [K,3] ndarray -> (targets [K,H,W] float32 ndarray, weights [K] float32 ndarray)."""
+        """joints [K,3] ndarray -> (targets [K,H,W] float32 ndarray, weights [K] float32 ndarray).
+        One person per call costs an H2D copy, a launch, a D2H copy and a sync; it exists for signature parity
+        and small scripts. It cannot run in DataLoader worker processes (it raises there): the training path is
+        the batched ``encode_heat_maps`` / ``EncodeJointsMSELoss`` on the device."""
+        _abi.refuse_loader_worker("RefineSimpleTransform.get_heat_map")
         arr = np.ascontiguousarray(np.asarray(joints, dtype=np.float32))
         if arr.ndim != 2 or arr.shape[1] != 3:
             raise ValueError("joints must be [K, 3]")
@@ -208,6 +212,7 @@ class BasicSimpleTransform(object):
 
     @staticmethod
     def get_heat_map(joints, sigma=2.0, shape=(48, 64), stride=4):
+        _abi.refuse_loader_worker("BasicSimpleTransform.get_heat_map")
         arr = np.ascontiguousarray(np.asarray(joints, dtype=np.float32))
         if arr.ndim != 2 or arr.shape[1] != 3:
             raise ValueError("joints must be [K, 3]")

@@ -96,6 +96,7 @@ encode_refine_kernel(const float* __restrict__ joints, float* __restrict__ targe
 // to int(x/stride + 0.5) and only a (6 sigma + 1)^2 patch of a fixed Gaussian table is pasted.
 // The table is computed on the host exactly as the reference does (NumPy float32) and handed in,
 // so the pasted values are bit-identical by construction. One warp per map, float4 stores.
+template <bool VEC4>
 __global__ void __launch_bounds__(kWarpsPerCta* SP_WARP)
 encode_basic_kernel(const float* __restrict__ joints, const float* __restrict__ table, float* __restrict__ targets,
                     float* __restrict__ weights, int nmaps, int H, int W, double reach, float stride, int side) {
@@ -116,16 +117,39 @@ encode_basic_kernel(const float* __restrict__ joints, const float* __restrict__ 
     const bool culled = lo_x >= W || lo_y >= H || hi_x < 0 || hi_y < 0;
     if (lane == 0) weights[m] = culled ? 0.f : vis;
     const bool draw = !culled && vis > 0.5f;
-    const int x0 = max(0, lo_x), x1 = min(hi_x, W), y0 = max(0, lo_y), y1 = min(hi_y, H);
+    // pasted window, clipped to the map and to the table
+    const int x0 = max(0, lo_x), x1 = min(min(hi_x, W), lo_x + side);
+    const int y0 = max(0, lo_y), y1 = min(min(hi_y, H), lo_y + side);
     float* out = targets + (size_t)m * H * W;
-    for (int i = lane; i < H * W; i += 32) {
-        const int y = i / W, x = i - y * W;
-        float v = 0.f;
-        if (draw && x >= x0 && x < x1 && y >= y0 && y < y1) {
-            const int gy = y - lo_y, gx = x - lo_x;
-            if (gy < side && gx < side) v = tab[gy * side + gx];
+    if (VEC4) {
+        // W % 4 == 0: whole rows of 16-byte stores; (row, quad-in-row) advance incrementally, no division
+        const int qpr = W >> 2, nq = H * qpr;
+        const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
+        int y = lane / qpr;
+        int xq = lane - y * qpr;
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int q = lane; q < nq; q += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int x = 4 * xq;
+            if (draw && y >= y0 && y < y1 && x + 3 >= x0 && x < x1) {
+                const float* row = tab + (y - lo_y) * side - lo_x;
+                if (x >= x0 && x < x1) v.x = row[x];
+                if (x + 1 >= x0 && x + 1 < x1) v.y = row[x + 1];
+                if (x + 2 >= x0 && x + 2 < x1) v.z = row[x + 2];
+                if (x + 3 >= x0 && x + 3 < x1) v.w = row[x + 3];
+            }
+            o4[q] = v;
+            xq += step_x;
+            y += step_y;
+            if (xq >= qpr) { xq -= qpr; ++y; }
         }
-        out[i] = v;
+    } else {
+        for (int i = lane; i < H * W; i += 32) {
+            const int y = i / W, x = i - y * W;
+            float v = 0.f;
+            if (draw && x >= x0 && x < x1 && y >= y0 && y < y1) v = tab[(y - lo_y) * side + (x - lo_x)];
+            out[i] = v;
+        }
     }
 }
 
@@ -186,7 +210,13 @@ extern "C" int sp_encode_basic_f32(const float* joints, const float* table, floa
     if (B == 0) return 0;
     const int nmaps = B * K;
     const int grid = (nmaps + kWarpsPerCta - 1) / kWarpsPerCta;
-    SP_CUDA(sp_launch(encode_basic_kernel, dim3(grid), dim3(kWarpsPerCta * SP_WARP), (size_t)side * side * sizeof(float),
-                      static_cast<cudaStream_t>(stream), joints, table, targets, weights, nmaps, H, W, sigma * 3.0, (float)stride, side));
+    const size_t smem = (size_t)side * side * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (W % 4 == 0 && sp_aligned16(targets))
+        SP_CUDA(sp_launch(encode_basic_kernel<true>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, table, targets, weights,
+                          nmaps, H, W, sigma * 3.0, (float)stride, side));
+    else
+        SP_CUDA(sp_launch(encode_basic_kernel<false>, dim3(grid), dim3(kWarpsPerCta * SP_WARP), smem, st, joints, table, targets, weights,
+                          nmaps, H, W, sigma * 3.0, (float)stride, side));
     return 0;
 }

@@ -24,6 +24,7 @@
 //   d = fl(m*p) - fl(m*t); grad = ((fl(2/N) * d) * 0.5) * m   (mse_loss_backward, then mul backward)
 #include "sp_common.cuh"
 #include "sp_reduce.cuh"
+#include "sp_lowp.cuh"
 
 #ifdef SP_TRAIN_TRACE
 __device__ long long* g_loss_trace_ptr = nullptr;     // scratch instrumentation, trace build only
@@ -107,6 +108,62 @@ mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tar
     }
 
     finish_loss<kThreads>(block_sum, ws, loss, inv_count);
+}
+
+// Mixed-precision variant (torch.cuda.amp, processors/dp_pose_hrnet_solver.py:111-120): `pred` arrives in the
+// autocast dtype PT (float16 / bfloat16; float32 also instantiated) and the gradient leaves in PT. The
+// arithmetic is what autocast runs: `pred.mul(mask)` promotes to float32, mse_loss is on autocast's float32
+// list, the backward of the promoted product casts d loss / d pred to PT once, AFTER the upstream gradient
+// (GradScaler's scale, read here from device memory so that no host sync is needed) has been applied in
+// float32 -- which is the whole point of loss scaling for float16. Eight elements per thread per step:
+// one 16-byte load of pred (8 x PT; 2 x float4 for float32), two of target, one 16-byte grad store.
+// loss == nullptr: backward only (no reduction); grad == nullptr: forward only.
+template <typename PT, bool VEC8>
+__global__ void __launch_bounds__(kThreads)
+mse_mixed_kernel(const PT* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ mask,
+                 PT* __restrict__ grad, float* __restrict__ loss, MseWorkspace* __restrict__ ws, int nmaps, int hw,
+                 float norm, float half_scale_host, const float* __restrict__ scale_dev, double inv_count, int skip_masked) {
+    double block_sum = 0.0;
+    sp::grid_dep_wait();
+    const float half_scale = scale_dev ? __fmul_rn(half_scale_host, __ldg(scale_dev)) : half_scale_host;
+    const bool write_grad = grad != nullptr;
+
+    for (int m = blockIdx.x; m < nmaps; m += gridDim.x) {
+        const float mk = __ldg(mask + m);
+        const size_t base = (size_t)m * hw;
+        float acc = 0.f;
+        if (skip_masked && mk == 0.f) {
+            if (write_grad)
+                for (int i = threadIdx.x; i < hw; i += kThreads) grad[base + i] = sp_lowp::from_float<PT>(0.f);
+            continue;
+        }
+        if (VEC8) {
+            const int n8 = hw >> 3;
+#pragma unroll 2
+            for (int o = threadIdx.x; o < n8; o += kThreads) {
+                float p[8], g[8];
+                sp_lowp::load8(pred + base + 8 * (size_t)o, p);
+                const float4 t0 = ldg_stream(reinterpret_cast<const float4*>(target + base) + 2 * o);
+                const float4 t1 = ldg_stream(reinterpret_cast<const float4*>(target + base) + 2 * o + 1);
+                const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float d = sq_err_and_grad(p[e], t[e], mk, norm, half_scale, g[e]);
+                    acc = fmaf(d, d, acc);
+                }
+                if (write_grad) sp_lowp::store8(grad + base + 8 * (size_t)o, g);
+            }
+        } else {
+            for (int i = threadIdx.x; i < hw; i += kThreads) {
+                float g;
+                const float d = sq_err_and_grad(sp_lowp::to_float(pred[base + i]), target[base + i], mk, norm, half_scale, g);
+                acc = fmaf(d, d, acc);
+                if (write_grad) grad[base + i] = sp_lowp::from_float<PT>(g);
+            }
+        }
+        block_sum += (double)acc;
+    }
+    if (loss != nullptr) finish_loss<kThreads>(block_sum, ws, loss, inv_count);
 }
 
 // dynamic smem: [mbarriers 1024 B][per warp: ring x (pred chunk | target chunk)]
@@ -274,6 +331,50 @@ extern "C" int sp_mse_fwd_bwd_f32(const float* pred, const float* target, const 
     else      { if (grad) SP_LAUNCH_MSE(false, true); else SP_LAUNCH_MSE(false, false); }
 #undef SP_LAUNCH_MSE
     return 0;
+}
+
+template <typename PT>
+static int launch_mixed(const void* pred, const float* target, const float* mask, void* grad, float* loss, MseWorkspace* ws,
+                        int nmaps, int HW, float norm, float half_scale, const float* scale_dev, double inv_count, int skip,
+                        cudaStream_t st) {
+    const bool vec8 = (HW % 8 == 0) && sp_aligned16(pred) && sp_aligned16(target) && (!grad || sp_aligned16(grad));
+    int grid = sp_sm_count() * 8;
+    if (grid > nmaps) grid = nmaps;
+    if (grid > kMaxPartials) grid = kMaxPartials;
+    const PT* p = static_cast<const PT*>(pred);
+    PT* g = static_cast<PT*>(grad);
+    if (vec8) SP_CUDA(sp_launch(mse_mixed_kernel<PT, true>, dim3(grid), dim3(kThreads), 0, st, p, target, mask, g, loss, ws, nmaps, HW, norm, half_scale, scale_dev, inv_count, skip));
+    else      SP_CUDA(sp_launch(mse_mixed_kernel<PT, false>, dim3(grid), dim3(kThreads), 0, st, p, target, mask, g, loss, ws, nmaps, HW, norm, half_scale, scale_dev, inv_count, skip));
+    return 0;
+}
+
+extern "C" int sp_mse_fwd_bwd(const void* pred, int pred_dtype, const float* target, const float* mask,
+                              void* grad, float* loss, void* workspace, size_t workspace_bytes,
+                              int B, int K, int HW, float grad_scale, const float* grad_scale_dev, int flags, void* stream) {
+    SP_RETURN_IF(pred_dtype != SP_DTYPE_F32 && pred_dtype != SP_DTYPE_F16 && pred_dtype != SP_DTYPE_BF16, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!loss && !grad, SP_ERR_BAD_ARGUMENT);
+    if (pred_dtype == SP_DTYPE_F32 && loss && !grad_scale_dev)        // the float32 fast path (TMA ring kernel)
+        return sp_mse_fwd_bwd_f32(static_cast<const float*>(pred), target, mask, static_cast<float*>(grad), loss, workspace,
+                                  workspace_bytes, B, K, HW, grad_scale, flags, stream);
+    SP_RETURN_IF(!pred || !target || !mask, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B <= 0 || K <= 0 || HW <= 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((long long)B * K > 0x7fffffffLL, SP_ERR_UNSUPPORTED);
+    if (loss) {
+        SP_RETURN_IF(!workspace, SP_ERR_BAD_ARGUMENT);
+        SP_RETURN_IF(workspace_bytes < sizeof(MseWorkspace), SP_ERR_WORKSPACE);
+        SP_RETURN_IF(!sp_aligned16(workspace), SP_ERR_BAD_ALIGNMENT);
+    }
+    const double count = (double)B * (double)K * (double)HW;
+    const float norm = (float)(2.0 / count);
+    const float half_scale = 0.5f * grad_scale;
+    const int skip = (flags & SP_MSE_SKIP_MASKED) ? 1 : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
+    if (pred_dtype == SP_DTYPE_F16)
+        return launch_mixed<__half>(pred, target, mask, grad, loss, ws, B * K, HW, norm, half_scale, grad_scale_dev, 1.0 / count, skip, st);
+    if (pred_dtype == SP_DTYPE_BF16)
+        return launch_mixed<__nv_bfloat16>(pred, target, mask, grad, loss, ws, B * K, HW, norm, half_scale, grad_scale_dev, 1.0 / count, skip, st);
+    return launch_mixed<float>(pred, target, mask, grad, loss, ws, B * K, HW, norm, half_scale, grad_scale_dev, 1.0 / count, skip, st);
 }
 
 extern "C" int sp_scale_inplace_f32(float* data, long long n, const float* scale_dev, void* stream) {

@@ -73,8 +73,8 @@ __device__ __forceinline__ double joint_var(const OksParams& P, int k) {
 // oks_iou for one (pick, candidate) pair, naive_data.py:139-149. T = double (the reference's arrays) or
 // float (decoder output rows; the JSON round trip of eval.py:138-160 widens exactly these floats).
 template <typename T>
-__device__ double oks_pair(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
-                           double pick_area, double cand_area) {
+__device__ double oks_pair_generic(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
+                                   double pick_area, double cand_area) {
     const double denom_area = __dadd_rn(__ddiv_rn(__dadd_rn(pick_area, cand_area), 2.0), 1e-12);
     int nvis = P.K;
     if (P.use_vis) {
@@ -99,6 +99,44 @@ __device__ double oks_pair(const OksParams& P, const T* __restrict__ pick, const
     // (vd_vis.sum(-1) + 1e-12) is float32 arithmetic in the reference
     const float cnt = __fadd_rn((float)nvis, 1e-12f);
     return __ddiv_rn(acc.result(), (double)cnt);
+}
+
+// The COCO case (K = 17, in_vis_thresh=None, default sigmas), fully unrolled: the 17 per-joint chains
+// (two float64 divisions and an exp each) are independent, so unrolled they overlap instead of running one
+// after the other -- the NMS kernel is latency-bound (one image per CTA), and this chain is its critical
+// path. Same operations in the same order per joint, and NumPy's pairwise sum written out for n = 17:
+// r[j] = v[j] + v[j+8], ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), + v[16], 0 + that. Division by 2 is exact, so
+// x * 0.5 == x / 2 bit for bit.
+template <typename T>
+__device__ __forceinline__ double oks_pair_coco17(const T* __restrict__ pick, const T* __restrict__ cand,
+                                                  double pick_area, double cand_area) {
+    const double denom_area = __dadd_rn(__dmul_rn(__dadd_rn(pick_area, cand_area), 0.5), 1e-12);
+    double v[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+        const double dx = __dsub_rn((double)cand[3 * k + 0], (double)pick[3 * k + 0]);
+        const double dy = __dsub_rn((double)cand[3 * k + 1], (double)pick[3 * k + 1]);
+        const double s = __ddiv_rn(kCocoSigmas[k], 10.0);
+        const double t = __dmul_rn(s, 2.0);
+        double e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        e = __dmul_rn(__ddiv_rn(__ddiv_rn(e, __dmul_rn(t, t)), denom_area), 0.5);
+        v[k] = exp(-e);
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(v[j], v[j + 8]);
+    double tail = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    tail = __dadd_rn(tail, v[16]);
+    const float cnt = __fadd_rn(17.0f, 1e-12f);
+    return __ddiv_rn(__dadd_rn(0.0, tail), (double)cnt);
+}
+
+template <typename T>
+__device__ __forceinline__ double oks_pair(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
+                                           double pick_area, double cand_area) {
+    if (P.K == 17 && !P.use_vis && P.sigmas == nullptr) return oks_pair_coco17(pick, cand, pick_area, cand_area);
+    return oks_pair_generic(P, pick, cand, pick_area, cand_area);
 }
 
 // eval.py:168-175 for one person: box_score * mean(conf[conf > thr]) (0 if none)

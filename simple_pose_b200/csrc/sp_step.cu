@@ -1,0 +1,179 @@
+// One launch per batch for the whole hot path over a predicted map (BASELINE configs 1 + 2 at their literal
+// batch sizes, and the body of the solvers' val() loop, processors/dp_pose_hrnet_solver.py:150-161):
+//
+//   targets, mask = get_heat_map(joints)                          commons/transforms.py:167-191
+//   loss = 0.5 * MSELoss(pred * mask, target * mask) (+ backward)    processors/dp_pose_hrnet_solver.py:106-107
+//   acc inputs: argmax of pred * mask and target * mask             metrics/pose_metrics.py:223-224
+//   pred_kps, scores = GaussTaylorKeyPointDecoder()(pred, trans_inv) metrics/pose_metrics.py:62-107
+//
+// Why: at batch 128 each of the three stand-alone kernels moves 27-80 MB (4-12 us of HBM time) and the step is
+// bound by launch gaps and per-kernel ramp/tail, not bandwidth (30.6 us per step replayed from a CUDA graph,
+// 47 us launched from Python, against 20 us of HBM time). Here every (person, joint) map is brought into shared
+// memory ONCE by a 1-D TMA bulk copy and the owning warp does everything to it while it is there: argmax +
+// 13-point blur + Taylor step + affine (the decode kernel's device code), then the float64 separable target, the
+// masked difference, loss partial, gradient and -- on request -- the target map itself and the HeatMapAcc
+// argmaxes (the fused training kernel's device code). pred is read once instead of twice and the targets are
+// written but never read back: 3 map-sized HBM streams per person (read pred, write targets, write grad)
+// instead of 5, in one launch instead of three. Results: coords / maxval / targets / weights / grad / acc axes
+// are bit-identical to the stand-alone kernels; the loss differs only in the float64 summation order.
+#include "sp_common.cuh"
+#include "sp_decode_dev.cuh"
+#include "sp_train_dev.cuh"
+
+namespace {
+
+using sp_reduce::MseWorkspace;
+
+constexpr int kHeadBytes = 1024;     // mbarriers (one per warp), claimed-map slots, CTA work counter
+constexpr int kWtsBytes = 1024;      // 11 x 11 blur weights
+constexpr int kPatchBytes = 1536;    // zero-padded 15 x 15 patch for peaks near the border
+
+// dynamic shared memory: [head][blur weights] then per warp [patch][float64 factors][the map]
+template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
+__global__ void __launch_bounds__(512, 1)
+step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
+            double inv_count, int nwarps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int KS = 11;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = A.H * A.W;
+    const uint32_t map_bytes = (uint32_t)hw * 4u;
+    const int wpad = (A.W + 1) & ~1;
+    const size_t fac_bytes = (size_t)(wpad + ((A.H + 1) & ~1)) * sizeof(double);
+    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
+    int& next_map = *reinterpret_cast<int*>(smem + kHeadBytes - 8);
+    float* wts = reinterpret_cast<float*>(smem + kHeadBytes);
+    unsigned char* mine = smem + kHeadBytes + kWtsBytes + (size_t)warp * per_warp;
+    float* patch = reinterpret_cast<float*>(mine);
+    double* ex = reinterpret_cast<double*>(mine + kPatchBytes);
+    double* ey = ex + wpad;
+    float* a = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
+
+    const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
+    const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
+    if (threadIdx.x == 0) next_map = range_lo + nwarps;      // the first nwarps maps of the range are assigned statically
+    if (lane == 0) {
+        sp::mbar_init(bar, 1);
+        sp::mbar_fence_init();
+    }
+    __syncthreads();
+    sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
+
+    auto issue = [&](int m) {       // lane 0: start the copy of map m
+        sp::mbar_expect_tx(bar, map_bytes);
+        sp::bulk_g2s(a, A.hm + (size_t)m * hw, map_bytes, bar);
+    };
+    int m = range_lo + warp;
+    if (m >= range_hi) m = -1;
+    if (lane == 0 && m >= 0) issue(m);
+    for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    __syncthreads();
+    sp_dec::LaneTaps<KS> taps;
+    taps.load(wts, lane);
+
+    double sum_sq = 0.0;
+    uint32_t parity = 0;
+    while (m >= 0) {
+        const sp_dec::Affine T = sp_dec::load_affine(A, m);
+        const sp_trn::Joint3 jc = sp_trn::load_joint(io, m);
+        // float64 Gaussian factors of this map's target while its copy is in flight
+        const sp_gauss::JointVerdict jv = sp_trn::prepare_map<0>(io, m, jc, ex, ey, lane);
+        sp::mbar_wait(bar, parity);
+        parity ^= 1u;
+        // ---- decode (argmax on the raw map, blur at the 13 stencil points, Taylor step, affine)
+        const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
+        sp_dec::DirectView view{a};
+        sp_dec::finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
+            return sp_dec::taylor_refine_smem<KS>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
+        });
+        // ---- target, masked difference, loss partial, gradient (+ target map, + HeatMapAcc argmaxes)
+        sp_trn::MapState st;
+        sp_trn::begin_map(io, jv, st, lane, ACC);
+        sp_trn::run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, reinterpret_cast<const float4*>(a), 0, hw >> 2, jv, ex, ey,
+                                                                st, lane, io.half_scale);
+        if (ACC) sp_trn::end_map_acc(io, m, jv, ex, ey, st, lane);
+        sum_sq += (double)st.acc;
+        __syncwarp();               // every lane is done with the staged map and the factors
+        int nm = -1;
+        if (lane == 0) {
+            nm = atomicAdd(&next_map, 1);
+            if (nm >= range_hi) nm = -1;
+            if (nm >= 0) {
+                sp::fence_proxy_async_smem();
+                issue(nm);
+            }
+        }
+        m = __shfl_sync(SP_FULL, nm, 0);
+    }
+    sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
+}
+
+}  // namespace
+
+extern "C" int sp_step_f32(const float* joints, const float* pred, const float* trans_inv, const float* blur_w,
+                           float* targets, float* weights, float* grad, float* loss, float* coords, float* maxval,
+                           float* pred_xy, float* label_xy, void* workspace, size_t workspace_bytes,
+                           int B, int K, int H, int W, double sigma, int ksize, float grad_scale, void* stream) {
+    SP_RETURN_IF(!joints || !pred || !blur_w || !loss || !coords || !maxval || !workspace, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(B <= 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((pred_xy == nullptr) != (label_xy == nullptr), SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
+    SP_RETURN_IF(W % 4 != 0 || ksize != 11, SP_ERR_UNSUPPORTED);      // callers compose the stand-alone kernels instead
+    SP_RETURN_IF(workspace_bytes < sizeof(MseWorkspace), SP_ERR_WORKSPACE);
+    SP_RETURN_IF(!sp_aligned16(workspace) || !sp_aligned16(pred) || (grad && !sp_aligned16(grad)) || (targets && !sp_aligned16(targets)) ||
+                 !sp_aligned16(coords) || (pred_xy && (!sp_aligned16(pred_xy) || !sp_aligned16(label_xy))), SP_ERR_BAD_ALIGNMENT);
+    const int nmaps = B * K;
+    const size_t map_bytes = (size_t)H * W * 4;
+    const int wpad = (W + 1) & ~1;
+    const size_t fac_bytes = (size_t)(wpad + ((H + 1) & ~1)) * sizeof(double);
+    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
+    const size_t budget = 227 * 1024 - kHeadBytes - kWtsBytes;
+    int fit = (int)(budget / per_warp);
+    SP_RETURN_IF(fit < 1, SP_ERR_UNSUPPORTED);
+    if (fit > 16) fit = 16;
+    const int sms = sp_sm_count();
+    // one map per warp in flight. Small batches: as many warps as fit, so that (at batch 128: 2176 maps on 148 SMs
+    // = 14.7 per SM, 15 warps fit) every map is resident at once and the launch is a single round. Large launches:
+    // one warp fewer leaves the copy engine a little slack, as in the decode kernel (14 measured faster than 16).
+    int nwarps = fit;
+    if (nwarps > 14 && (long long)nmaps >= 4LL * 16 * sms) nwarps = 14;
+    nwarps = sp_knob(sp_tuning().step_warps, nwarps);
+    if (nwarps < 1) nwarps = 1;
+    if (nwarps > fit) nwarps = fit;
+    int grid = sms;
+    const int need = (nmaps + nwarps - 1) / nwarps;
+    if (grid > need) grid = need;
+    const size_t smem = kHeadBytes + kWtsBytes + (size_t)nwarps * per_warp;
+
+    sp_dec::DecodeArgs A;
+    A.hm = pred; A.hm_flip = nullptr; A.perm = nullptr; A.trans_inv = trans_inv; A.blur_w = blur_w;
+    A.coords = coords; A.maxval = maxval; A.argmax = nullptr; A.rows = nullptr; A.row_stride = 0;
+    A.nmaps = nmaps; A.K = K; A.H = H; A.W = W; A.ksize = 11; A.mode = SP_DECODE_GAUSS_TAYLOR; A.work = nullptr;
+    const double count = (double)B * (double)K * (double)H * (double)W;
+    sp_trn::MapIo io;
+    io.joints = joints; io.pred = pred; io.grad = grad; io.targets = targets; io.weights = weights;
+    io.pred_xy = reinterpret_cast<float2*>(pred_xy); io.label_xy = reinterpret_cast<float2*>(label_xy);
+    io.nmaps = nmaps; io.H = H; io.W = W; io.reach = (float)(sigma * 3.0); io.denom = 2.0 * (sigma * sigma);
+    io.norm = (float)(2.0 / count); io.half_scale = 0.5f * grad_scale; io.scale_dev = nullptr;
+    io.analytic_ok = (sigma >= 0.25 && sigma <= 64.0) ? 1 : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
+    const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
+#define SP_LAUNCH_STEP(G, T, AC) \
+    SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps))
+    switch (sel) {
+        case 0: SP_LAUNCH_STEP(false, false, false); break;
+        case 1: SP_LAUNCH_STEP(false, false, true); break;
+        case 2: SP_LAUNCH_STEP(false, true, false); break;
+        case 3: SP_LAUNCH_STEP(false, true, true); break;
+        case 4: SP_LAUNCH_STEP(true, false, false); break;
+        case 5: SP_LAUNCH_STEP(true, false, true); break;
+        case 6: SP_LAUNCH_STEP(true, true, false); break;
+        default: SP_LAUNCH_STEP(true, true, true); break;
+    }
+#undef SP_LAUNCH_STEP
+    return 0;
+}

@@ -15,6 +15,8 @@
 #include "sp_common.cuh"
 #include "sp_gauss.cuh"
 #include "sp_reduce.cuh"
+#include "sp_lowp.cuh"
+#include "sp_train_dev.cuh"
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -37,267 +39,12 @@ namespace {
 
 using namespace sp_gauss;
 using namespace sp_reduce;
-
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * SP_WARP;
-
-__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ float warp_max_f32(float v) {
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-
-// running (value, quad) argmax over the quads a lane visits in increasing order
-struct QuadBest {
-    float best;
-    int bq;
-    int bsub;          // first element of quad bq that equals best
-    float poison;
-    __device__ __forceinline__ void init() { best = -CUDART_INF_F; bq = 0x0fffffff; bsub = 0; poison = 0.f; }
-    __device__ __forceinline__ void push(float a, float b, float c, float d, int q) {
-        const float m4 = sp::fmax_nan(sp::fmax_nan(a, b), sp::fmax_nan(c, d));
-        poison = fmaf(m4, 0.f, poison);
-        if (m4 > best) {
-            best = m4;
-            bq = q;
-            bsub = (a == m4) ? 0 : (b == m4) ? 1 : (c == m4) ? 2 : 3;
-        }
-    }
-};
-
-struct MaskedPredView {          // m * pred[i], straight from global memory (exact fallback only)
-    const float* p;
-    float m;
-    __device__ __forceinline__ float at(int i) const { return __fmul_rn(m, p[i]); }
-};
-
-template <typename View>
-__device__ __noinline__ void argmax_exact_scan(const View map, int hw, int lane, float& val, int& idx) {
-    float bv = -CUDART_INF_F;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < hw; i += 32) {
-        const float v = map.at(i);
-        if (sp::better(v, i, bv, bi)) { bv = v; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(SP_FULL, bv, o);
-        const int oi = __shfl_xor_sync(SP_FULL, bi, o);
-        if (sp::better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    val = bv;
-    idx = bi;
-}
-
-// heat_map_to_axis on an index/value pair: (x, y) as floats, zeroed when the max is not > 0
-__device__ __forceinline__ float2 axis_of(float val, int idx, int W) {
-    if (!(val > 0.f)) return make_float2(0.f, 0.f);
-    const int y = idx / W;
-    return make_float2((float)(idx - y * W), (float)y);
-}
-
-struct MapIo {                 // per-launch constants of the fused kernel
-    const float* joints;
-    const float* pred;
-    float* grad;
-    float* targets;
-    float* weights;
-    float2* pred_xy;
-    float2* label_xy;
-    int nmaps, H, W;
-    float reach;
-    double denom;
-    float norm, half_scale;
-    int analytic_ok;          // sigma in the range where the target argmax can be found analytically
-};
-
-// One (person, joint) map, one warp. `src` = the predicted map, in shared memory (SMEM_PRED, staged
-// by TMA) or in global memory. Returns this lane's share of sum((m*p - m*t)^2).
-// Per-map running state of one warp while the predicted map streams by (possibly in chunks).
-struct MapState {
-    float acc;                   // this lane's share of sum((m*p - m*t)^2)
-    QuadBest bp, bt;             // running argmax of the masked predicted / target map
-    int y, xq;                   // row and quad-in-row of this lane's next quad
-    bool track, analytic_t, track_t;
-};
-
-__device__ __forceinline__ void begin_map(const MapIo& io, const JointVerdict& jv, MapState& st, int lane, bool acc_on) {
-    const int qpr = io.W >> 2;
-    st.acc = 0.f;
-    st.bp.init();
-    st.bt.init();
-    st.y = lane / qpr;
-    st.xq = lane - st.y * qpr;
-    st.track = acc_on && (jv.weight != 0.f);
-    // The target's argmax is found analytically (3x3 block around the rounded centre) when the
-    // mask and sigma are in the range where float32 rounding cannot create far-away ties.
-    st.analytic_t = st.track && jv.draw && io.analytic_ok && jv.weight >= 0.5f && jv.weight <= 4.f;
-    st.track_t = st.track && jv.draw && !st.analytic_t;
-}
-
-// Quads q = q_begin + lane, +32, ... < q_end of map m; `chunk` points at quad q_begin of the
-// predicted map (shared memory when SMEM_PRED, else global). q_begin is a multiple of 32.
-// UNIT: the mask is exactly 1.0f (the common case), so m*p == p, m*t == t and (...)*m is dropped;
-// the results are bit-identical to the general expressions.
-template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC, bool SMEM_PRED, bool UNIT>
-__device__ __forceinline__ void run_quads_impl(const MapIo& io, int m, const float4* chunk, int q_begin, int q_end,
-                                               const JointVerdict& jv, const double* ex, const double* ey,
-                                               MapState& st, int lane) {
-    const int W = io.W, hw = io.H * io.W, qpr = W >> 2;
-    const int step_y = 32 / qpr, step_x = 32 - step_y * qpr;
-    const float mk = jv.weight, norm = io.norm, half_scale = io.half_scale;
-    float4* g4 = reinterpret_cast<float4*>(io.grad + (size_t)m * hw);
-    float4* t4 = reinterpret_cast<float4*>(io.targets + (size_t)m * hw);
-    int y = st.y, xq = st.xq;
-    float acc = st.acc;
-    QuadBest bp = st.bp, bt = st.bt;
-    const bool draw = jv.draw, track = st.track, track_t = st.track_t;
-#pragma unroll 3
-    for (int q = q_begin + lane; q < q_end; q += 32) {
-        const float4 p = SMEM_PRED ? chunk[q - q_begin] : ldg_stream4(chunk + (q - q_begin));
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (draw) {
-            const double2 a = *reinterpret_cast<const double2*>(ex + 4 * xq);
-            const double2 b = *reinterpret_cast<const double2*>(ex + 4 * xq + 2);
-            const double fy = ey[y];
-            t.x = __double2float_rn(__dmul_rn(a.x, fy));
-            t.y = __double2float_rn(__dmul_rn(a.y, fy));
-            t.z = __double2float_rn(__dmul_rn(b.x, fy));
-            t.w = __double2float_rn(__dmul_rn(b.y, fy));
-        }
-        const float px = UNIT ? p.x : __fmul_rn(mk, p.x), py = UNIT ? p.y : __fmul_rn(mk, p.y);
-        const float pz = UNIT ? p.z : __fmul_rn(mk, p.z), pw = UNIT ? p.w : __fmul_rn(mk, p.w);
-        const float tx = UNIT ? t.x : __fmul_rn(mk, t.x), ty = UNIT ? t.y : __fmul_rn(mk, t.y);
-        const float tz = UNIT ? t.z : __fmul_rn(mk, t.z), tw = UNIT ? t.w : __fmul_rn(mk, t.w);
-        const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty), dz = __fsub_rn(pz, tz), dw = __fsub_rn(pw, tw);
-        acc = fmaf(dx, dx, acc);
-        acc = fmaf(dy, dy, acc);
-        acc = fmaf(dz, dz, acc);
-        acc = fmaf(dw, dw, acc);
-        if (WRITE_GRAD) {
-            float4 g;
-            g.x = __fmul_rn(__fmul_rn(norm, dx), half_scale);
-            g.y = __fmul_rn(__fmul_rn(norm, dy), half_scale);
-            g.z = __fmul_rn(__fmul_rn(norm, dz), half_scale);
-            g.w = __fmul_rn(__fmul_rn(norm, dw), half_scale);
-            if (!UNIT) {
-                g.x = __fmul_rn(g.x, mk); g.y = __fmul_rn(g.y, mk); g.z = __fmul_rn(g.z, mk); g.w = __fmul_rn(g.w, mk);
-            }
-            g4[q] = g;
-        }
-        if (WRITE_TARGETS) t4[q] = t;
-        if (ACC && track) bp.push(px, py, pz, pw, q);
-        if (ACC && track_t) bt.push(tx, ty, tz, tw, q);
-        xq += step_x;
-        y += step_y;
-        if (xq >= qpr) { xq -= qpr; ++y; }
-    }
-    st.y = y; st.xq = xq; st.acc = acc; st.bp = bp; st.bt = bt;
-}
-
-template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC, bool SMEM_PRED>
-__device__ __forceinline__ void run_quads(const MapIo& io, int m, const float4* chunk, int q_begin, int q_end,
-                                          const JointVerdict& jv, const double* ex, const double* ey, MapState& st, int lane) {
-    if (jv.weight == 1.0f) run_quads_impl<WRITE_GRAD, WRITE_TARGETS, ACC, SMEM_PRED, true>(io, m, chunk, q_begin, q_end, jv, ex, ey, st, lane);
-    else                   run_quads_impl<WRITE_GRAD, WRITE_TARGETS, ACC, SMEM_PRED, false>(io, m, chunk, q_begin, q_end, jv, ex, ey, st, lane);
-}
-
-// HeatMapAcc coordinates of both masked maps (heat_map_to_axis). The winning quad of the predicted
-// map is re-read from global memory (L2-resident: it has just streamed through), so the staged
-// copy may already have been recycled.
-__device__ __forceinline__ void end_map_acc(const MapIo& io, int m, const JointVerdict& jv, const double* ex,
-                                            const double* ey, const MapState& st, int lane) {
-    const int W = io.W, hw = io.H * io.W;
-    const float mk = jv.weight;
-    float2 pxy = make_float2(0.f, 0.f), lxy = make_float2(0.f, 0.f);
-    if (st.track) {
-        const float* src = io.pred + (size_t)m * hw;
-        float pv;
-        int pi;
-        if (__any_sync(SP_FULL, st.bp.poison != st.bp.poison)) {
-            MaskedPredView view{src, mk};
-            argmax_exact_scan(view, hw, lane, pv, pi);
-        } else {
-            // every lane tracked the first maximal element of its own quads: the smallest flat index
-            // among the lanes that hold the warp-wide maximum is torch.max's answer
-            pv = warp_max_f32(st.bp.best);
-            pi = (int)__reduce_min_sync(SP_FULL, (st.bp.best == pv) ? (unsigned)(4 * st.bp.bq + st.bp.bsub) : 0x7fffffffu);
-        }
-        pxy = axis_of(pv, pi, W);
-        // target map: fl(m * t); always finite
-        if (st.analytic_t) {
-            // factors decrease monotonically away from the centre, so every maximiser of the
-            // rounded products lies in the 3x3 block around the nearest in-map pixel
-            const int xn = min(max(__float2int_rn(jv.mx), 0), W - 1), yn = min(max(__float2int_rn(jv.my), 0), io.H - 1);
-            const int yy = yn - 1 + lane / 3, xx = xn - 1 + lane % 3;
-            const bool in = lane < 9 && yy >= 0 && yy < io.H && xx >= 0 && xx < W;
-            float v = -CUDART_INF_F;
-            if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[xx], ey[yy])));
-            const float gmax = warp_max_f32(v);
-            const unsigned gi = __reduce_min_sync(SP_FULL, (in && v == gmax) ? (unsigned)(yy * W + xx) : 0x7fffffffu);
-            lxy = axis_of(gmax, (int)gi, W);
-        } else if (jv.draw) {
-            const float gmax = warp_max_f32(st.bt.best);
-            const unsigned gi = __reduce_min_sync(SP_FULL, (st.bt.best == gmax) ? (unsigned)(4 * st.bt.bq + st.bt.bsub) : 0x7fffffffu);
-            lxy = axis_of(gmax, (int)gi, W);
-        }
-    }
-    if (lane == 0) {
-        io.pred_xy[m] = pxy;
-        io.label_xy[m] = lxy;
-    }
-}
-
-struct Joint3 {
-    float x, y, v;
-};
-__device__ __forceinline__ Joint3 load_joint(const MapIo& io, int m) {
-    Joint3 j;
-    j.x = j.y = j.v = 0.f;
-    if (m < io.nmaps) {
-        j.x = __ldg(io.joints + 3 * (size_t)m + 0);
-        j.y = __ldg(io.joints + 3 * (size_t)m + 1);
-        j.v = __ldg(io.joints + 3 * (size_t)m + 2);
-    }
-    return j;
-}
-
-// Position of x factor i in the period-tiled kernel's layout: the four factors of a quad are split
-// into two planes of (e0, e1) and (e2, e3) pairs, so that the 16-byte shared loads of eight
-// consecutive lanes (consecutive quads of a row) cover 128 contiguous bytes. With the four doubles
-// of a quad contiguous (32-byte lane stride) every such load was a 2-way bank conflict.
-template <int QPR>
-__device__ __forceinline__ int ex_slot(int i) {
-    return QPR > 0 ? (((i >> 2) << 1) + (i & 1) + ((i & 2) ? 2 * QPR : 0)) : i;
-}
-
-// joint -> verdict, weight store, float64 factors into this warp's shared-memory slice
-template <int QPR = 0>
-__device__ __forceinline__ JointVerdict prepare_map(const MapIo& io, int m, const Joint3 j, double* ex, double* ey, int lane) {
-    const float mx = j.x, my = j.y, vis = j.v;
-    const JointVerdict jv = judge_joint(mx, my, vis, io.reach, io.H, io.W);
-    if (lane == 0 && io.weights) io.weights[m] = jv.weight;
-    __syncwarp();
-    if (jv.draw) {
-        for (int i = lane; i < io.W + io.H; i += 32) {
-            if (i < io.W) ex[ex_slot<QPR>(i)] = gauss_factor(i, mx, io.denom);
-            else          ey[i - io.W] = gauss_factor(i - io.W, my, io.denom);
-        }
-    }
-    __syncwarp();
-    return jv;
-}
+using namespace sp_trn;
 
 // Variant A: predicted maps read straight from global memory (any map size).
-template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
+// PT = storage type of pred and grad (float32, or float16 / bfloat16 under torch.cuda.amp: the arithmetic stays
+// float32 as autocast runs it, the gradient is cast to PT once, after the upstream scale has been applied).
+template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC, typename PT = float>
 __global__ void __launch_bounds__(kThreads)
 encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count) {
     extern __shared__ __align__(16) double factors[];   // per warp: ex[Wpad] then ey[H]
@@ -310,6 +57,7 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
     const int total_warps = gridDim.x * kWarps;
     double sum_sq = 0.0;
     sp::grid_dep_wait();
+    const float half_scale = io.scale_dev ? __fmul_rn(io.half_scale, __ldg(io.scale_dev)) : io.half_scale;
     Joint3 jn = load_joint(io, blockIdx.x * kWarps + warp);
     for (int m = blockIdx.x * kWarps + warp; m < io.nmaps; m += total_warps) {
         const Joint3 jc = jn;
@@ -317,12 +65,13 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
         const JointVerdict jv = prepare_map(io, m, jc, ex, ey, lane);
         MapState st;
         begin_map(io, jv, st, lane, ACC);
-        run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, false>(io, m, reinterpret_cast<const float4*>(io.pred + (size_t)m * hw),
-                                                         0, hw >> 2, jv, ex, ey, st, lane);
-        if (ACC) end_map_acc(io, m, jv, ex, ey, st, lane);
+        run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, false, PT>(
+            io, m, reinterpret_cast<const float4*>(reinterpret_cast<const PT*>(io.pred) + (size_t)m * hw), 0, hw >> 2, jv, ex, ey,
+            st, lane, half_scale);
+        if (ACC) end_map_acc<PT>(io, m, jv, ex, ey, st, lane);
         sum_sq += (double)st.acc;
     }
-    finish_loss<512>(sum_sq, ws, loss, inv_count);     // every lane carries the quads it visited
+    if (loss != nullptr) finish_loss<512>(sum_sq, ws, loss, inv_count);     // every lane carries the quads it visited
 }
 
 // Variant B (default): persistent, one CTA per SM, up to 32 warps. Every warp streams its predicted
@@ -414,7 +163,7 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
             sp::mbar_wait(bars + cs, parity);
             const float4* chunk = reinterpret_cast<const float4*>(slots + (size_t)cs * chunk_bytes);
             run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, chunk, c * chunk_quads, (c + 1) * chunk_quads,
-                                                            jv, ex, ey, st, lane);
+                                                            jv, ex, ey, st, lane, io.half_scale);
             __syncwarp();
             if (lane == 0) {
                 sp::fence_proxy_async_smem();
@@ -698,7 +447,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
             if (__any_sync(SP_FULL, best != best)) {
                 float pv;
                 int pi;
-                MaskedPredView view{src, mk};
+                MaskedPredView<float> view{src, mk};
                 argmax_exact_scan(view, hw, lane, pv, pi);
                 if (lane == 0) io.pred_xy[m] = axis_of(pv, pi, io.W);
             } else {
@@ -872,11 +621,15 @@ heatmap_acc_kernel(const float2* __restrict__ pred_xy, const float2* __restrict_
 
 }  // namespace
 
-extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred, float* grad, float* targets,
-                                         float* weights, float* loss, float* pred_xy, float* label_xy,
-                                         void* workspace, size_t workspace_bytes,
-                                         int B, int K, int H, int W, double sigma, float grad_scale, void* stream) {
-    SP_RETURN_IF(!joints || !pred || !loss || !workspace, SP_ERR_BAD_ARGUMENT);
+static int encode_mse_launch(const float* joints, const void* pred_raw, int pred_dtype, void* grad_raw, float* targets,
+                             float* weights, float* loss, float* pred_xy, float* label_xy,
+                             void* workspace, size_t workspace_bytes,
+                             int B, int K, int H, int W, double sigma, float grad_scale, const float* scale_dev, void* stream) {
+    const float* pred = static_cast<const float*>(pred_raw);      // reinterpreted per dtype inside the generic kernel
+    float* grad = static_cast<float*>(grad_raw);
+    const bool plain_f32 = (pred_dtype == SP_DTYPE_F32) && !scale_dev && loss;
+    SP_RETURN_IF(pred_dtype != SP_DTYPE_F32 && pred_dtype != SP_DTYPE_F16 && pred_dtype != SP_DTYPE_BF16, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!joints || !pred || (!loss && !grad) || !workspace, SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF(B <= 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF((pred_xy == nullptr) != (label_xy == nullptr), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
@@ -897,6 +650,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     io.joints = joints; io.pred = pred; io.grad = grad; io.targets = targets; io.weights = weights;
     io.pred_xy = reinterpret_cast<float2*>(pred_xy); io.label_xy = reinterpret_cast<float2*>(label_xy);
     io.nmaps = nmaps; io.H = H; io.W = W; io.reach = reach; io.denom = denom; io.norm = norm; io.half_scale = half_scale;
+    io.scale_dev = scale_dev;
     io.analytic_ok = (sigma >= 0.25 && sigma <= 64.0) ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
@@ -915,7 +669,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     }
     // Variant C: W = 48 / 72 (12 / 18 quads per row), whole periods per map, grad wanted, targets not
     const int qpr = W >> 2;
-    if ((qpr == 12 || qpr == 18) && grad && !targets && !force_ldg && sp_knob(tune.train_no_tile, 0) == 0) {
+    if (plain_f32 && (qpr == 12 || qpr == 18) && grad && !targets && !force_ldg && sp_knob(tune.train_no_tile, 0) == 0) {
         const int period = (qpr == 12) ? Tile<12>::PERIOD : Tile<18>::PERIOD;
         const int rows = (qpr == 12) ? Tile<12>::ROWS : Tile<18>::ROWS;
         // tuned layouts (PPC periods per chunk, ring depth); SP_TRAIN_TILE_CFG picks another compiled one
@@ -974,7 +728,7 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
             }
         }
     }
-    if (chunk_quads > 0 && !force_ldg) {
+    if (plain_f32 && chunk_quads > 0 && !force_ldg) {
         const size_t chunk_bytes = (size_t)chunk_quads * 16;
         const size_t budget = 226 * 1024 - kRingHeader;        // 1 KB spare for static shared memory
         int ring = sp_knob(tune.train_ring, 2);
@@ -1013,7 +767,12 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     if (grid > kMaxPartials) grid = kMaxPartials;
 #define SP_LAUNCH_TRAIN(G, T, A)                                                                                         \
     do {                                                                                                                 \
-        SP_CUDA(sp_launch_smem(encode_mse_kernel<G, T, A>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count));       \
+        if (pred_dtype == SP_DTYPE_F16)                                                                                  \
+            SP_CUDA(sp_launch_smem(encode_mse_kernel<G, T, A, __half>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count)); \
+        else if (pred_dtype == SP_DTYPE_BF16)                                                                            \
+            SP_CUDA(sp_launch_smem(encode_mse_kernel<G, T, A, __nv_bfloat16>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count)); \
+        else                                                                                                             \
+            SP_CUDA(sp_launch_smem(encode_mse_kernel<G, T, A, float>, dim3(grid), dim3(kThreads), smem, st, io, loss, ws, 1.0 / count)); \
     } while (0)
     switch (sel) {
         case 0: SP_LAUNCH_TRAIN(false, false, false); break;
@@ -1027,6 +786,24 @@ extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred,
     }
 #undef SP_LAUNCH_TRAIN
     return 0;
+}
+
+extern "C" int sp_encode_mse_fwd_bwd_f32(const float* joints, const float* pred, float* grad, float* targets,
+                                         float* weights, float* loss, float* pred_xy, float* label_xy,
+                                         void* workspace, size_t workspace_bytes,
+                                         int B, int K, int H, int W, double sigma, float grad_scale, void* stream) {
+    SP_RETURN_IF(!loss, SP_ERR_BAD_ARGUMENT);
+    return encode_mse_launch(joints, pred, SP_DTYPE_F32, grad, targets, weights, loss, pred_xy, label_xy, workspace, workspace_bytes,
+                             B, K, H, W, sigma, grad_scale, nullptr, stream);
+}
+
+extern "C" int sp_encode_mse_fwd_bwd(const float* joints, const void* pred, int pred_dtype, void* grad, float* targets,
+                                     float* weights, float* loss, float* pred_xy, float* label_xy,
+                                     void* workspace, size_t workspace_bytes,
+                                     int B, int K, int H, int W, double sigma, float grad_scale, const float* grad_scale_dev,
+                                     void* stream) {
+    return encode_mse_launch(joints, pred, pred_dtype, grad, targets, weights, loss, pred_xy, label_xy, workspace, workspace_bytes,
+                             B, K, H, W, sigma, grad_scale, grad_scale_dev, stream);
 }
 
 extern "C" int sp_heatmap_acc_f32(const float* pred_xy, const float* label_xy, float* acc,

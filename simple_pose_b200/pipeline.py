@@ -18,6 +18,8 @@ ALGO_BYTES = {
     "flip_decode": lambda k, h, w: 2 * k * h * w * 4 + 24 + k * 12,
     # fused encode + loss fwd/bwd + HeatMapAcc argmaxes: read pred, write grad (+ joints, weights, axes)
     "train_fused": lambda k, h, w: 2 * k * h * w * 4 + k * 12 + k * 4 + k * 16,
+    # one-launch step (sp_step_f32): read pred once, write targets and grad (+ joints, weights, affine, keypoints)
+    "step": lambda k, h, w: 3 * k * h * w * 4 + k * 12 + k * 4 + 24 + k * 12,
 }
 
 
@@ -107,14 +109,47 @@ class HeatmapHotPath(object):
                                                      self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
                                                      stream), self.device, stream)
 
-    def step(self, joints, pred, trans_inv):
-        """encode(joints), decode(pred), loss/grad(pred, targets, weights): 3 launches, two orders.
-        Large batches (targets do not fit in L2): encode, decode, loss -- the decode between the two
-        kernels that touch ``targets`` measured 2.5 % faster than encode -> loss -> decode (1418 vs
-        1455 us for 8 x 1024 persons). Small batches (targets <= 64 MB, e.g. the reference's batch 128 =
-        26.7 MB): decode, encode, loss -- the loss then finds the targets the encoder just wrote in the
-        126 MB L2 (encode + loss per 1024 persons: 199.9 -> 182.7 us at batch 128, 163.3 -> 155.5 us at
-        batch 256; no difference from batch 512 up, scratch/l2_pairs.py). Same results either way."""
+    def step_one_launch(self, joints, pred, trans_inv, want_targets=True, want_grad=True, with_acc=False):
+        """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) + GaussTaylor decode of ``pred`` in ONE launch
+        (``sp_step_f32``): every map is staged in shared memory once, pred is read from HBM once and the
+        targets are written but not read back. Same outputs as ``step`` (loss up to summation order)."""
+        self._checked(joints, (self.batch, self.k, 3), "joints")
+        self._maps(pred, "pred")
+        if trans_inv is not None:
+            self._checked(trans_inv, (self.batch, 2, 3), "trans_inv")
+        if with_acc and self.pred_xy is None:
+            self.pred_xy = torch.empty((self.batch, self.k, 2), dtype=torch.float32, device=self.device)
+            self.label_xy = torch.empty_like(self.pred_xy)
+        with torch.cuda.device(self.device):
+            stream = _abi.stream_ptr(self.device)
+            ws = _workspace(self.device, stream)
+            _abi.check_ws(self._lib.sp_step_f32(
+                joints.data_ptr(), pred.data_ptr(), _abi.ptr(trans_inv), self.blur_w.data_ptr(),
+                self.targets.data_ptr() if want_targets else None, self.weights.data_ptr(),
+                self.grad.data_ptr() if want_grad else None, self.loss.data_ptr(), self.coords.data_ptr(),
+                self.maxval.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
+                _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
+                self.batch, self.k, self.h, self.w, self.sigma, self.ksize, 1.0, stream), self.device, stream)
+        return self.loss, self.coords, self.maxval
+
+    def one_launch_supported(self):
+        """``sp_step_f32`` takes W % 4 == 0, the reference's 11 x 11 blur and maps that fit in shared memory."""
+        per_warp = 1536 + 8 * (((self.w + 1) & ~1) + ((self.h + 1) & ~1)) + 4 * self.h * self.w
+        return self.w % 4 == 0 and self.ksize == 11 and per_warp <= 227 * 1024 - 2048
+
+    def step(self, joints, pred, trans_inv, one_launch=None):
+        """encode(joints), decode(pred), loss/grad(pred, targets, weights).
+
+        ``one_launch`` (default: whenever the shape allows) runs the three as one kernel, ``sp_step_f32``.
+        Otherwise 3 launches, in one of two orders. Large batches (targets do not fit in L2): encode,
+        decode, loss -- the decode between the two kernels that touch ``targets`` measured 2.5 % faster
+        than encode -> loss -> decode (1418 vs 1455 us for 8 x 1024 persons). Small batches (targets <=
+        64 MB, e.g. the reference's batch 128 = 26.7 MB): decode, encode, loss -- the loss then finds the
+        targets the encoder just wrote in the 126 MB L2 (scratch/l2_pairs.py). Same results either way."""
+        if one_launch is None:
+            one_launch = self.one_launch_supported()
+        if one_launch:
+            return self.step_one_launch(joints, pred, trans_inv)
         if self.targets.numel() * 4 <= (64 << 20):
             self.decode(pred, trans_inv)
             self.encode(joints)
@@ -125,7 +160,25 @@ class HeatmapHotPath(object):
             self.loss_fwd_bwd(pred)
         return self.loss, self.coords, self.maxval
 
-    LAUNCHES_PER_STEP = 3
+    def capture(self, joints, pred, trans_inv, one_launch=None):
+        """Capture ``step`` on these (static) input buffers into a CUDA graph and return ``replay``: a callable
+        that re-runs the step with whatever the buffers hold at that moment, for the price of one graph launch
+        instead of the Python -> ctypes -> launch path per kernel (the literal batch-128 configs are bound by
+        exactly that). Outputs land in this object's buffers as usual."""
+        stream = torch.cuda.Stream(self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(stream):
+            for _ in range(2):                       # warm-up: workspace creation, attribute caches
+                self.step(joints, pred, trans_inv, one_launch)
+        torch.cuda.current_stream(self.device).wait_stream(stream)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            self.step(joints, pred, trans_inv, one_launch)
+        self._graph = graph                          # keeps the captured buffers alive
+        return graph.replay
+
+    LAUNCHES_PER_STEP = 3          # the three stand-alone kernels (run_batches); step() via sp_step_f32 is 1
 
 
 def run_batches(paths, inputs, after_decode=None):

@@ -165,3 +165,25 @@ def test_swap_permutation():
     assert swap_permutation(4, [[0, 3]]) == [3, 1, 2, 0]
     with pytest.raises(ValueError):
         swap_permutation(4, [[0, 9]])
+
+
+class _PerSampleEncodeDataset(torch.utils.data.Dataset):
+    """What MSCOCO.__getitem__ does with the transform (reference datasets/coco.py:58-60)."""
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        import numpy as np
+        from simple_pose_b200.commons.transforms import RefineSimpleTransform
+        joints = np.array([[10.0, 20.0, 1.0]] * 17, dtype=np.float32)
+        targets, weights = RefineSimpleTransform.get_heat_map(joints)
+        return torch.from_numpy(targets), torch.from_numpy(weights)
+
+
+def test_per_sample_encoder_refuses_dataloader_workers():
+    """The per-sample drop-in cannot create a CUDA context in a forked DataLoader worker: it must say so (and
+    point at the batched path) instead of failing inside CUDA."""
+    loader = torch.utils.data.DataLoader(_PerSampleEncodeDataset(), batch_size=2, num_workers=1)
+    with pytest.raises(RuntimeError, match="DataLoader worker"):
+        next(iter(loader))

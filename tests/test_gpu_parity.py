@@ -506,6 +506,21 @@ def test_oks_nms_pair_matrix_path_equals_greedy_loop(api, mean_group):
     assert 0 < keep_np.sum() < n
 
 
+@pytest.mark.parametrize("n", [9, 17, 33, 64, 80])
+def test_oks_nms_score_ties_follow_the_documented_rule(api, n):
+    """Equal scores are visited higher index first (what `argsort()[::-1]` gives over a stable sort); the
+    reference leaves that order to NumPy's host-dependent SIMD sort (OKS-NMS). The kernel's keep
+    set and pick order equal the reference algorithm run on scores de-tied by that rule, in both kernel paths."""
+    rng = np.random.RandomState(n)
+    for trial in range(6):
+        kps, _, area, _ = synth.nms_groups(1, mean_group=float(n), seed=1000 * n + trial)
+        m = kps.shape[0]
+        tied = rng.choice([0.2, 0.4, 0.6], size=m)
+        want = [int(i) for i in O.oks_greedy_nms(kps.numpy(), O.detie_scores(tied), area.numpy(), 0.9)]
+        assert api.naive.oks_nms(kps.numpy(), tied, area.numpy(), 0.9) == want
+        assert len(want) < m                                   # duplicates with equal scores really compete
+
+
 def test_oks_nms_edge_cases(api):
     kps, box, area, seg = synth.nms_groups(3, mean_group=5.0, seed=2)
     # empty segment in the middle, single-person image, and one big image

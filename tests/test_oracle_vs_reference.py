@@ -71,6 +71,37 @@ def test_oks_and_nms(ref):
         assert np.array_equal(bits(a), bits(b))
 
 
+def test_nms_score_ties_are_the_only_freedom(ref):
+    """`oks_nms` visits `scores.argsort()[::-1]` (datasets/naive_data.py:163). With distinct scores that order
+    is unique and the restatement equals the reference for every image size. With EQUAL scores NumPy's default
+    sort decides, and its tie order depends on the SIMD sort it dispatches to on the host CPU (AVX-512 / AVX2
+    builds reorder ties even below 16 elements), so the reference's keep list is then a property of the
+    machine. Pinned here: (1) distinct scores: exact; (2) ties made explicit by `detie_scores` (higher index
+    first -- the rule the CUDA kernel implements): the reference itself, fed the de-tied scores, returns the
+    same keep list as the restatement; (3) with the reference's own visiting order injected the greedy pass is
+    reproduced exactly, i.e. nothing but the order of equal scores differs."""
+    rng = np.random.RandomState(0)
+    order_differs = keep_differs = cases = 0
+    for trial in range(120):
+        n = int(rng.choice([4, 8, 12, 17, 20, 33, 60]))
+        kps, _, area, _ = synth.nms_groups(1, mean_group=float(n), seed=trial)
+        kps, area = kps.numpy(), area.numpy()
+        m = kps.shape[0]
+        distinct = rng.permutation(m) / m
+        assert [int(i) for i in ref.oks_nms(kps, distinct, area, 0.9)] == [int(i) for i in O.oks_greedy_nms(kps, distinct, area, 0.9)]
+        tied = rng.choice([0.3, 0.5, 0.7, 0.9], size=m)
+        detied = O.detie_scores(tied)
+        assert np.array_equal(np.argsort(detied)[::-1], np.argsort(tied, kind="stable")[::-1])
+        want = [int(i) for i in O.oks_greedy_nms(kps, detied, area, 0.9)]
+        assert [int(i) for i in ref.oks_nms(kps, detied, area, 0.9)] == want
+        got = [int(i) for i in ref.oks_nms(kps, tied, area, 0.9)]
+        cases += 1
+        order_differs += int(not np.array_equal(tied.argsort()[::-1], np.argsort(tied, kind="stable")[::-1]))
+        keep_differs += int(sorted(got) != sorted(want))
+    # informational: how often this host's NumPy breaks ties differently from the stable rule
+    print("tied-score images: %d, visiting order differs in %d, keep set differs in %d" % (cases, order_differs, keep_differs))
+
+
 def test_heat_map_acc(ref):
     tgt = torch.from_numpy(O.encode_batch(synth.joints(8, seed=17).numpy())[0])
     pred = synth.predictions_like(tgt, seed=18, noise=0.3)
