@@ -65,17 +65,23 @@ def hbm_peak():
 
 
 def ncu_traffic(kernel, height, width, batch):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/r*_traffic.json), if one exists for this exact launch shape; else None."""
-    names = {"encode": "encode_refine_kernel<1, 2>", "loss": "mse_ring_kernel<1>", "decode": "decode_tma_kernel<0, 11>",
-             "train_fused": "encode_mse_tile_kernel<12, 2, 1, 1>", "flip_decode": "decode_tma_kernel<1, 11>"}
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r*_traffic.json), if one
+    exists for this exact launch shape AND was measured on the library as it is now (the file records the source
+    fingerprint of the build it profiled; a retuned kernel makes it stale and the answer None, never an old number)."""
+    from simple_pose_b200 import build as _build
+    names = {"encode": "encode_refine_kernel<1, 2>", "loss": "mse_ring_kernel<1, 0>", "decode": "decode_tma_kernel<0, 11>",
+             "train_fused": "encode_mse_tile_kernel<12, 2, 1, 1>", "flip_decode": "decode_tma_kernel<1, 11>",
+             "step": "step_kernel<1, 1, 0>"}
     key = "%s @ %dx%d,P=%d" % (names.get(kernel, kernel), height, width, batch)
     pdir = os.path.join(ROOT, "profiles")
     try:
+        fingerprint = _build._fingerprint()
         files = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json"))
         for f in reversed(files):
             with open(os.path.join(pdir, f)) as fh:
                 table = json.load(fh)
+            if table.get("_lib_fingerprint") != fingerprint:
+                continue
             if key in table:
                 return table[key]["dram_bytes_per_launch"], f
     except Exception:
@@ -251,9 +257,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2+cfg1 fused step: DarkPose encode + masked-MSE fwd/bwd + GaussTaylor decode, "
-                               "K=17, %dx%d (reference CPU algorithm, bounded sample)" % (args.height, args.width),
-                   "sample_persons_per_step": sample},
+        "config": bench_config(args, args.gpus),
+        "sample_persons_per_step": sample,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d persons per step; encode in %d worker processes (the reference's DataLoader "
                                    "workers), loss fwd+bwd and decode on %d ATen threads; per-op persons/s: encode %.0f, "
@@ -590,6 +595,29 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
             "decode_read_GBps_per_gpu": (n * (17 * height * width * 4)) / (ms * 1e-3) / 1e9}
 
 
+def step_cycles(steps):
+    """Passes over the rotating buffer sets per step, chosen from --steps alone (both arms and every rank derive the
+    same number) so that the timed region of the product arm lasts about half a second even when few steps are asked
+    for (the driver's --steps 20 used to time 27 ms, two clock samples)."""
+    return max(1, -(-500 // max(1, int(steps))))
+
+
+def bench_config(args, world):
+    """The `config` object: identical in the product and the reference arm (same workload, same sizes)."""
+    from simple_pose_b200.pipeline import ALGO_BYTES
+    H, W, B = args.height, args.width, args.batch
+    base = max(B, (args.persons // B) * B)
+    cycles = step_cycles(args.steps)
+    per_person = ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)
+    return {"workload": "cfg2+cfg1 step: DarkPose target encoding + masked joints-MSE fwd/bwd + GaussTaylor decode of the same "
+                        "predicted heatmaps (+ NCCL all-gather of the keypoints when N>1), K=17, %dx%d float32" % (H, W),
+            "persons_per_gpu_per_step": base * cycles, "persons_per_launch": B, "height": H, "width": W, "joints": 17,
+            "distinct_buffer_sets": base // B, "passes_over_the_buffer_sets_per_step": cycles,
+            "l2": "inputs larger than L2: %d distinct buffer sets of %d persons, %.0f MB of separate-kernel traffic per pass" %
+                  (base // B, B, base * per_person / 1e6),
+            "parallelism": "persons sharded, dp%d" % world}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from simple_pose_b200 import _abi
@@ -607,40 +635,78 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     _abi.lib()
     peak_gbs, peak_src = hbm_peak()
-    H, W, P, B = args.height, args.width, args.persons, args.batch
-    P = max(B, (P // B) * B)
+    config = bench_config(args, world)
+    H, W, B = args.height, args.width, args.batch
+    P = max(B, (args.persons // B) * B)          # persons per pass over the buffer sets
     nb = P // B
+    cycles = step_cycles(args.steps)
 
     sets = make_inputs(P, B, H, W, device, seed=rank * 7919)
-    # decoded keypoints of all batches land in one flat send buffer: [P*17*2 coords | P*17 scores]
-    kp_local = torch.empty(P * 17 * 3, dtype=torch.float32, device=device)
-    coords_all = kp_local[:P * 17 * 2].view(P, 17, 2)
-    maxval_all = kp_local[P * 17 * 2:].view(P, 17, 1)
-    paths = [HeatmapHotPath(B, 17, H, W, device=device, coords=coords_all[i * B:(i + 1) * B],
-                            maxval=maxval_all[i * B:(i + 1) * B]) for i in range(nb)]    # distinct outputs per batch
-    kp_all = torch.empty(world * P * 17 * 3, dtype=torch.float32, device=device) if world > 1 else None
+    # decoded keypoints of all batches of a pass land in one flat send buffer: [P*17*2 coords | P*17 scores]; two of
+    # them alternate between passes so that a pass never waits for the all-gather of the previous one
+    kp_local = [torch.empty(P * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)]
+    views = [[(kp[:P * 17 * 2].view(P, 17, 2)[i * B:(i + 1) * B], kp[P * 17 * 2:].view(P, 17, 1)[i * B:(i + 1) * B])
+              for i in range(nb)] for kp in kp_local]
+    paths = [HeatmapHotPath(B, 17, H, W, device=device, coords=views[0][i][0], maxval=views[0][i][1]) for i in range(nb)]
+    kp_all = [torch.empty(world * P * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)] if world > 1 else None
+    one_launch = paths[0].one_launch_supported()
+    pending = [None, None]
+    state = {"pass": 0}
 
-    pending = []
+    def use_buffer(side):
+        for i in range(nb):
+            paths[i].coords, paths[i].maxval = views[side][i]
 
-    def start_gather():
-        # asynchronous: NCCL's stream waits for the decodes enqueued so far; the encode and loss
-        # kernels that follow on the compute stream overlap the collective
-        if world > 1:
-            pending.append(dist.all_gather_into_tensor(kp_all, kp_local, async_op=True))
+    def finish_gather(side=None):
+        for sd in ((0, 1) if side is None else (side,)):
+            if pending[sd] is not None:
+                pending[sd].wait()        # stream-level wait (no host block): this buffer may be overwritten again
+                pending[sd] = None
 
-    def finish_gather():
-        while pending:
-            pending.pop().wait()          # stream-level wait (no host block): next decodes may overwrite kp_local
+    def one_pass(three_kernels):
+        side = state["pass"] & 1
+        state["pass"] += 1
+        finish_gather(side)
+        use_buffer(side)
 
-    def step():
-        finish_gather()
-        run_batches(paths, sets, after_decode=start_gather)
+        def start_gather():
+            # asynchronous: NCCL's stream waits for the kernels enqueued so far; whatever follows on the compute
+            # stream (the next pass, or the encode and loss kernels of this one) overlaps the collective
+            if world > 1:
+                pending[side] = dist.all_gather_into_tensor(kp_all[side], kp_local[side], async_op=True)
+        if three_kernels:
+            run_batches(paths, sets, after_decode=start_gather)
+        else:
+            for i in range(nb):
+                paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2])
+            start_gather()
+
+    def step(three_kernels=not one_launch):
+        for _ in range(cycles):
+            one_pass(three_kernels)
 
     def barrier():
         finish_gather()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
+
+    def timed(fn, steps):
+        """ms per call of `fn` over `steps` calls: CUDA events on the launching stream, max over ranks."""
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        finish_gather()                   # the last all-gather is inside the timed region
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
 
     def kernel_ms(fn, rounds):
         """Average launch duration of one kernel: CUDA events around nb back-to-back launches
@@ -662,124 +728,84 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        step()
-    finish_gather()                       # the last step's all-gather is inside the timed region
-    t_end.record()
-    barrier()
-    elapsed_ms = t_start.elapsed_time(t_end)
+    ms_per_step = timed(step, args.steps)                         # THE timed region: exactly --steps steps
+    value = world * P * cycles / (ms_per_step * 1e-3)
     # per-kernel durations, still under the clock sampler
     rounds = max(3, min(20, args.steps))
     op_ms = {"encode": kernel_ms(lambda i: paths[i].encode(sets[i][0]), rounds),
              "loss": kernel_ms(lambda i: paths[i].loss_fwd_bwd(sets[i][1]), rounds),
              "decode": kernel_ms(lambda i: paths[i].decode(sets[i][1], sets[i][2]), rounds)}
-    # the same persons through the fused training kernel (encode + loss + HeatMapAcc argmaxes in one
-    # pass, targets never materialised: SURVEY 8f ranks 1-2) followed by the decode
-    def fused_step():
+    if one_launch:
+        op_ms["step"] = kernel_ms(lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2]), rounds)
+    side_steps = max(3, min(50, args.steps))
+    # the same passes through the three stand-alone kernels (round 1's headline step: encode, loss fwd/bwd and decode
+    # launched separately, grouped by kernel, all-gather overlapped with encode/loss)
+    for _ in range(2):
+        one_pass(True)
+    three_ms = timed(lambda: one_pass(True), side_steps)
+    three = {"persons_per_s": world * P / (three_ms * 1e-3), "ms_per_pass": three_ms, "launches_per_pass": 3 * nb,
+             "algorithmic_bytes_per_person": ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W),
+             "note": "sp_encode_f32 + sp_mse_fwd_bwd_f32 + sp_decode_ws_f32 per batch (pred read twice, targets written and read back)"}
+    # ... and through the fused training kernel (encode + loss + HeatMapAcc argmaxes in one pass, targets never
+    # materialised: SURVEY 8f ranks 1-2) followed by the decode; no all-gather in this loop
+    def fused_pass():
         for i in range(nb):
             paths[i].train_fused(sets[i][0], sets[i][1])
             paths[i].decode(sets[i][1], sets[i][2])
-    for _ in range(3):
-        fused_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fsteps = max(3, min(50, args.steps))
-    f0.record()
-    for _ in range(fsteps):
-        fused_step()
-    f1.record()
-    barrier()
-    fused_ms = f0.elapsed_time(f1) / fsteps
-    # ... and through the one-launch step kernel (decode + encode + loss fwd/bwd on one staged copy of each map)
-    def one_launch_step():
-        for i in range(nb):
-            paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2])
-    one = None
-    if paths[0].one_launch_supported():
-        for _ in range(3):
-            one_launch_step()
-        barrier()
-        f0.record()
-        for _ in range(fsteps):
-            one_launch_step()
-        f1.record()
-        barrier()
-        one_ms = f0.elapsed_time(f1) / fsteps
-        if world > 1:
-            t = torch.tensor([one_ms], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            one_ms = float(t.item())
-        one_bytes = ALGO_BYTES["step"](17, H, W) * P
-        one = {"persons_per_s": world * P / (one_ms * 1e-3), "ms_per_step": one_ms, "launches_per_step": nb,
-               "algorithmic_bytes_per_person": ALGO_BYTES["step"](17, H, W),
-               "GBps": one_bytes / (one_ms * 1e-3) / 1e9, "frac": one_bytes / (one_ms * 1e-3) / 1e9 / peak_gbs,
-               "note": "same persons and the same outputs as the headline step (targets, weights, loss, grad, keypoints) from "
-                       "sp_step_f32: one launch per batch, pred read once; no all-gather in this loop"}
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = world * P / (ms_per_step * 1e-3)
-    if world > 1:
-        t = torch.tensor([fused_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fused_ms = float(t.item())
-    fused = {"persons_per_s": world * P / (fused_ms * 1e-3), "ms_per_step": fused_ms, "launches_per_step": 2 * nb,
+    for _ in range(2):
+        fused_pass()
+    fused_ms = timed(fused_pass, side_steps)
+    fused = {"persons_per_s": world * P / (fused_ms * 1e-3), "ms_per_pass": fused_ms, "launches_per_pass": 2 * nb,
              "algorithmic_bytes_per_person": ALGO_BYTES["train_fused"](17, H, W) + ALGO_BYTES["decode"](17, H, W),
              "note": "same persons, loss/grad/weights/keypoints identical; encode+loss+HeatMapAcc fused into one pass "
                      "(targets never written), then decode; no all-gather in this loop"}
+    clocks = sampler.stop() if rank == 0 else None
 
-    dominant = max(op_ms, key=op_ms.get)
-    dom_bytes = ALGO_BYTES[dominant](17, H, W) * B
-    achieved = dom_bytes / (op_ms[dominant] * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(dominant, H, W, B)
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    headline = "step" if one_launch else max(("encode", "loss", "decode"), key=op_ms.get)
+    dom_bytes = ALGO_BYTES[headline](17, H, W) * B
+    achieved = dom_bytes / (op_ms[headline] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(headline, H, W, B)
+    launch_ms = {"step": op_ms["step"]} if one_launch else {k: op_ms[k] for k in ("encode", "loss", "decode")}
+    roofline = {"bound": "hbm", "kernel": headline, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": op_ms[dominant],
-                "share_of_step": op_ms[dominant] / sum(op_ms.values()),
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": op_ms[headline],
+                "share_of_step": op_ms[headline] / sum(launch_ms.values()),
+                "step_ms_explained_by_kernel_launches": cycles * nb * sum(launch_ms.values()),
                 "all_kernels": {k: {"ms_per_launch": op_ms[k],
                                     "GBps": ALGO_BYTES[k](17, H, W) * B / (op_ms[k] * 1e-3) / 1e9,
                                     "frac": ALGO_BYTES[k](17, H, W) * B / (op_ms[k] * 1e-3) / 1e9 / peak_gbs}
                                 for k in op_ms}}
 
     # end to end through the public Python API, host buffers in, host results out
-    e2e = None
+    e2e = e2e_dev = None
     if not args.no_e2e:
         saved_affinity = os.sched_getaffinity(0)
         if not os.environ.get("SP_BENCH_NO_BIND"):
             numa["text"] = bind_near_gpu(local)          # pinned host buffers land on the GPU's NUMA node
         try:
             e2e = run_e2e(args, device, world, rank, P, B, H, W)
+            e2e_dev = run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets)
         finally:
             os.sched_setaffinity(0, saved_affinity)      # the CPU baseline below uses every core again
+    del paths, sets, views, kp_local, kp_all
+    torch.cuda.empty_cache()
 
-    ops = None
-    if rank == 0 and not args.no_ops and world == 1:
-        del paths, sets
-        torch.cuda.empty_cache()
+    # per-op sweep, literal small batches, train-side caller: one GPU's worth of numbers, measured by rank 0 at every N
+    # (the other ranks wait at the barrier below)
+    ops = small = train_side = None
+    if rank == 0 and not args.no_ops:
         ops = {"64x48": time_ops(device, 64, 48, 8192, 1024, peak_gbs),
                "96x72": time_ops(device, 96, 72, 4096, 512, peak_gbs),
                # the literal BASELINE batch sizes (launch-latency regime): cfg 1/2 = batch 128, cfg 3 = batch 256 flip test
                "64x48_batch128": time_ops(device, 64, 48, 8192, 128, peak_gbs),
                "64x48_batch256": time_ops(device, 64, 48, 8192, 256, peak_gbs, only=("flip_decode", "decode", "step"))}
-
-    small = train_side = None
-    if rank == 0 and world == 1 and not args.no_ops:
         small = small_batch_numbers(device, H, W)
         train_side = train_side_numbers(device)
+    if world > 1:
+        dist.barrier()
 
     eval_job = None
     if not args.no_ops:
-        try:
-            del paths, sets
-        except NameError:
-            pass
-        torch.cuda.empty_cache()
         eval_job = eval_job_numbers(device, world, rank, height=H, width=W)
 
     cpu = None
@@ -798,20 +824,19 @@ def run_ours(args):
         if eval_job is not None and not eval_job["matches_single_device"]:
             raise SystemExit(3)
         return
+    launches_per_pass = nb if one_launch else 3 * nb
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2+cfg1 fused step: DarkPose encode + masked-MSE fwd/bwd + GaussTaylor decode "
-                               "(+ NCCL all-gather of keypoints when N>1, overlapped with encode/loss), K=17, %dx%d" % (H, W),
-                   "launch_order": "per step: all decodes, all-gather (async), all encodes, all losses",
-                   "persons_per_gpu_per_step": P, "persons_per_launch": B,
-                   "l2": "inputs larger than L2: %d distinct buffer sets, %.0f MB touched per step per GPU" %
-                         (nb, P * (ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W)) / 1e6),
-                   "parallelism": "persons sharded, dp%d" % world, "e2e_host_binding": numa["text"]},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * nb * HeatmapHotPath.LAUNCHES_PER_STEP,
-        "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small, "eval_job": eval_job, "fused_step": fused, "one_launch_step": one,
-        "train_side": train_side,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "step_path": ("sp_step_f32: one launch per batch does decode + encode + loss fwd/bwd on one staged copy of each map "
+                      "(same outputs as the three stand-alone kernels, see three_kernel_step)") if one_launch else
+                     "three stand-alone kernels per batch, grouped by kernel",
+        "e2e_host_binding": numa["text"],
+        "clocks": clocks, "e2e": e2e, "e2e_device_heatmaps": e2e_dev,
+        "gpu_launches": args.steps * cycles * launches_per_pass,
+        "roofline": roofline, "cpu_baseline": cpu, "ops": ops, "small_batch": small, "eval_job": eval_job,
+        "three_kernel_step": three, "fused_step": fused, "train_side": train_side,
     }
     print(json.dumps(line), flush=True)
     if eval_job is not None and not eval_job["matches_single_device"]:
@@ -904,6 +929,58 @@ def run_e2e(args, device, world, rank, P, B, H, W):
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
             "note": "public API (encode_heat_maps, JointsMSELoss+backward, GaussTaylorKeyPointDecoder) on pinned host "
                     "inputs incl. the predicted heatmaps; PCIe-bound"}
+
+
+def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
+    """The realistic end-to-end leg: what a training / validation loop ships per batch is the joints and the affines
+    (H2D, pinned); the predicted heatmaps are the backbone's output and already live on the device (here: the resident
+    synthetic ones); the loss and the keypoints go back to the host (D2H). One `HeatmapHotPath.step` per batch."""
+    import torch.distributed as dist
+    from simple_pose_b200.pipeline import HeatmapHotPath
+    nb = P // B
+    h_joints = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    h_tinv = torch.empty((P, 2, 3), dtype=torch.float32).pin_memory()
+    for i in range(nb):
+        h_joints[i * B:(i + 1) * B].copy_(sets[i][0])
+        h_tinv[i * B:(i + 1) * B].copy_(sets[i][2])
+    h_kp = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    h_loss = torch.empty((nb,), dtype=torch.float32).pin_memory()
+    hp = [HeatmapHotPath(B, 17, H, W, device=device) for _ in range(2)]          # double-buffered outputs
+    d_joints = [torch.empty((B, 17, 3), device=device) for _ in range(2)]
+    d_tinv = [torch.empty((B, 2, 3), device=device) for _ in range(2)]
+    torch.cuda.synchronize(device)
+
+    def step():
+        for i in range(nb):
+            s = i & 1
+            d_joints[s].copy_(h_joints[i * B:(i + 1) * B], non_blocking=True)
+            d_tinv[s].copy_(h_tinv[i * B:(i + 1) * B], non_blocking=True)
+            loss, xy, conf = hp[s].step(d_joints[s], sets[i][1], d_tinv[s])
+            h_kp[i * B:(i + 1) * B, :, :2].copy_(xy, non_blocking=True)
+            h_kp[i * B:(i + 1) * B, :, 2:].copy_(conf, non_blocking=True)
+            h_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize(device)
+        return float(h_loss.sum())
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": world * P * steps / dt, "unit": UNIT, "h2d_bytes_per_step": P * (17 * 3 * 4 + 24),
+            "d2h_bytes_per_step": P * 17 * 3 * 4 + nb * 4, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "persons_per_step": P,
+            "note": "joints + affines H2D from pinned memory, heatmaps resident on the device (backbone output), loss + keypoints "
+                    "D2H; HeatmapHotPath.step per batch, host wall clock incl. the final synchronize"}
 
 
 def main():

@@ -29,7 +29,16 @@ for (h, w, batch) in ((64, 48, 1024), (96, 72, 512)):  # summarize.py labels lau
         hp.decode(pred, tinv)
         hp.decode(pred, tinv, flip, perm)
         hp.train_fused(joints, pred)
+        hp.step_one_launch(joints, pred, tinv)
     torch.cuda.synchronize()
+# the literal batch-128 step (BASELINE configs 1 + 2): one launch
+hp = HeatmapHotPath(128, 17, 64, 48, device=dev)
+joints = synth.joints(128, seed=3, device=dev)
+pred = synth.heatmaps(128, seed=3, device=dev)
+tinv = synth.inverse_affines(128, seed=3, device=dev)[0]
+for _ in range(reps):
+    hp.step_one_launch(joints, pred, tinv)
+torch.cuda.synchronize()
 from simple_pose_b200.commons.transforms import train_geometry  # noqa: E402
 smp = {k: v.to(dev) for k, v in synth.train_samples(8192, seed=5).items()}
 for _ in range(reps):
@@ -38,5 +47,19 @@ torch.cuda.synchronize()
 kps, box, area, seg = synth.nms_groups(512, mean_group=20.0, seed=3)
 for _ in range(reps):
     rescore_and_nms(kps.to(dev), box.to(dev), area.to(dev), seg)
+torch.cuda.synchronize()
+# the eval chain of one rank of an 8-GPU run of BASELINE config 5 (an eighth of the job): box -> affine, decode into
+# the result rows, fused rescoring + OKS-NMS on the rows
+from simple_pose_b200.eval_shard import ShardedPoseEvaluator  # noqa: E402
+es = synth.EvalSet()
+i1 = es.images // 8
+n = int(es.seg[i1])
+ev = ShardedPoseEvaluator(chunks=1)
+ev.plan(es.seg[:i1 + 1])
+hm = es.heatmaps(0, n, dev)
+boxes, bs = es.boxes[:n].to(dev), es.box_scores[:n].to(dev)
+torch.cuda.synchronize()
+for _ in range(reps):
+    ev.run(hm, None, bs, None, boxes=boxes, compact=False)
 torch.cuda.synchronize()
 print("done")

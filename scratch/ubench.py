@@ -32,7 +32,7 @@ for hw in args.hw.split(","):
     H, W = [int(x) for x in hw.split("x")]
     for batch in [int(b) for b in args.batch.split(",")]:
         per = 17 * H * W * 4 * batch
-        nb = max(2, min(16, (args.total_mb << 20) // per))
+        nb = max(2, min(64, (args.total_mb << 20) // per))
         gen = min(batch, 1024)
         sets, flips, paths = [], [], []
         for i in range(nb):
@@ -51,6 +51,7 @@ for hw in args.hw.split(","):
             "train_fused": lambda i: paths[i].train_fused(sets[i][0], sets[i][1]),
             "decode": lambda i: paths[i].decode(sets[i][1], sets[i][2]),
             "flip_decode": lambda i: paths[i].decode(sets[i][1], sets[i][2], flips[i], perm),
+            "step": lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2]),
         }
         for i in range(nb):
             paths[i].encode(sets[i][0])      # targets for the loss

@@ -73,7 +73,7 @@ __device__ __forceinline__ double joint_var(const OksParams& P, int k) {
 // oks_iou for one (pick, candidate) pair, naive_data.py:139-149. T = double (the reference's arrays) or
 // float (decoder output rows; the JSON round trip of eval.py:138-160 widens exactly these floats).
 template <typename T>
-__device__ double oks_pair_generic(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
+__device__ __noinline__ double oks_pair_generic(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
                                    double pick_area, double cand_area) {
     const double denom_area = __dadd_rn(__ddiv_rn(__dadd_rn(pick_area, cand_area), 2.0), 1e-12);
     int nvis = P.K;
@@ -137,6 +137,49 @@ __device__ __forceinline__ double oks_pair(const OksParams& P, const T* __restri
                                            double pick_area, double cand_area) {
     if (P.K == 17 && !P.use_vis && P.sigmas == nullptr) return oks_pair_coco17(pick, cand, pick_area, cand_area);
     return oks_pair_generic(P, pick, cand, pick_area, cand_area);
+}
+
+// The NMS only needs the DECISION oks > thresh. The float64 chain above (two divisions and an exp per joint) made
+// the NMS kernel float64-pipe bound: 221 us for the 104 k persons of BASELINE config 5, ~50 % of the FP64 issue
+// rate. This float32 evaluation of the same expression costs an eighth of the instructions on a pipe twice as
+// wide, and its error is bounded: the joint differences are formed exactly in float64 and rounded once, so the
+// exponent e carries a relative error < 5e-7, each term exp(-e) an absolute error < 5e-7 (e * exp(-e) <= 1/e), the
+// mean of 17 terms < 2e-6 in total. A pair is decided here when the result is further than kOksMargin = 1e-4 from
+// the threshold -- 50 times the bound -- and re-evaluated with the exact chain otherwise (also when anything is
+// NaN). The decisions, hence keep sets and pick order, are the float64 ones.
+constexpr float kOksMargin = 1e-4f;
+__device__ __constant__ float kCocoInvVar[17] = {
+    // 1 / (2 * sigma_k / 10)^2
+    1.0f / (0.052f * 0.052f), 1.0f / (0.050f * 0.050f), 1.0f / (0.050f * 0.050f), 1.0f / (0.070f * 0.070f), 1.0f / (0.070f * 0.070f),
+    1.0f / (0.158f * 0.158f), 1.0f / (0.158f * 0.158f), 1.0f / (0.144f * 0.144f), 1.0f / (0.144f * 0.144f), 1.0f / (0.124f * 0.124f),
+    1.0f / (0.124f * 0.124f), 1.0f / (0.214f * 0.214f), 1.0f / (0.214f * 0.214f), 1.0f / (0.174f * 0.174f), 1.0f / (0.174f * 0.174f),
+    1.0f / (0.178f * 0.178f), 1.0f / (0.178f * 0.178f)};
+
+template <typename T>
+__device__ __forceinline__ float oks_pair_fast17(const T* __restrict__ pick, const T* __restrict__ cand, double pick_area,
+                                                 double cand_area) {
+    const float inv_area = 0.5f / (0.5f * ((float)pick_area + (float)cand_area) + 1e-12f);    // 1 / denom_area / 2
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+        const float dx = (float)((double)cand[3 * k + 0] - (double)pick[3 * k + 0]);
+        const float dy = (float)((double)cand[3 * k + 1] - (double)pick[3 * k + 1]);
+        const float e = (dx * dx + dy * dy) * kCocoInvVar[k] * inv_area;
+        sum += expf(-e);
+    }
+    return sum * (1.0f / 17.0f);
+}
+
+// oks > thresh with the float64 chain's verdict
+template <typename T>
+__device__ __forceinline__ bool oks_exceeds(const OksParams& P, const T* __restrict__ pick, const T* __restrict__ cand,
+                                            double pick_area, double cand_area, double thresh) {
+    if (P.K == 17 && !P.use_vis && P.sigmas == nullptr) {
+        const float v = oks_pair_fast17(pick, cand, pick_area, cand_area);
+        const float gap = v - (float)thresh;
+        if (fabsf(gap) > kOksMargin) return gap > 0.f;            // false for NaN: falls through to the exact chain
+    }
+    return oks_pair_generic(P, pick, cand, pick_area, cand_area) > thresh;    // rare: a rolled loop keeps the kernel's registers low
 }
 
 // eval.py:168-175 for one person: box_score * mean(conf[conf > thr]) (0 if none)
@@ -212,8 +255,8 @@ __device__ __forceinline__ void nms_image(const T* __restrict__ kps, size_t stri
             while (p > 0 && p * n - p * (p + 1) / 2 > idx) --p;
             const int c = p + 1 + (idx - (p * n - p * (p + 1) / 2));
             const int i = order[p], j = order[c];
-            const double oks = oks_pair(P, kps + (size_t)i * stride, kps + (size_t)j * stride, area[i], area[j]);
-            if (oks > thresh) atomicOr(&rows[p], 1ull << c);
+            if (oks_exceeds(P, kps + (size_t)i * stride, kps + (size_t)j * stride, area[i], area[j], thresh))
+                atomicOr(&rows[p], 1ull << c);
         }
         __syncthreads();
         if (tid == 0) {
@@ -233,8 +276,7 @@ __device__ __forceinline__ void nms_image(const T* __restrict__ kps, size_t stri
             for (int c = p + 1 + tid; c < n; c += kNmsThreads) {
                 if (!alive[c]) continue;
                 const int j = order[c];
-                const double oks = oks_pair(P, pick, kps + (size_t)j * stride, pick_area, area[j]);
-                if (oks > thresh) alive[c] = 0;        // survivors satisfy oks <= thresh
+                if (oks_exceeds(P, pick, kps + (size_t)j * stride, pick_area, area[j], thresh)) alive[c] = 0;   // survivors: oks <= thresh
             }
             __syncthreads();
         }

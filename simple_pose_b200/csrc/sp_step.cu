@@ -28,11 +28,11 @@ constexpr int kHeadBytes = 1024;     // mbarriers (one per warp), claimed-map sl
 constexpr int kWtsBytes = 1024;      // 11 x 11 blur weights
 constexpr int kPatchBytes = 1536;    // zero-padded 15 x 15 patch for peaks near the border
 
-// dynamic shared memory: [head][blur weights] then per warp [patch][float64 factors][the map]
+// dynamic shared memory: [head][blur weights] then per warp [patch][float64 factors][stages x the map]
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
 __global__ void __launch_bounds__(512, 1)
 step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
-            double inv_count, int nwarps) {
+            double inv_count, int nwarps, int stages) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KS = 11;
     const int lane = threadIdx.x & 31;
@@ -41,72 +41,97 @@ step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restric
     const uint32_t map_bytes = (uint32_t)hw * 4u;
     const int wpad = (A.W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + ((A.H + 1) & ~1)) * sizeof(double);
-    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
+    const size_t per_warp = kPatchBytes + fac_bytes + (size_t)stages * map_bytes;
 
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * stages;          // <= 16 warps x 2 stages x 8 B
     int& next_map = *reinterpret_cast<int*>(smem + kHeadBytes - 8);
     float* wts = reinterpret_cast<float*>(smem + kHeadBytes);
     unsigned char* mine = smem + kHeadBytes + kWtsBytes + (size_t)warp * per_warp;
     float* patch = reinterpret_cast<float*>(mine);
     double* ex = reinterpret_cast<double*>(mine + kPatchBytes);
     double* ey = ex + wpad;
-    float* a = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
+    float* stage0 = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
 
     const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
     const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
     if (threadIdx.x == 0) next_map = range_lo + nwarps;      // the first nwarps maps of the range are assigned statically
     if (lane == 0) {
-        sp::mbar_init(bar, 1);
+        for (int s = 0; s < stages; ++s) sp::mbar_init(bars + s, 1);
         sp::mbar_fence_init();
     }
     __syncthreads();
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
 
-    auto issue = [&](int m) {       // lane 0: start the copy of map m
-        sp::mbar_expect_tx(bar, map_bytes);
-        sp::bulk_g2s(a, A.hm + (size_t)m * hw, map_bytes, bar);
+    auto issue = [&](int s, int m) {       // lane 0: start the copy of map m into stage s
+        sp::mbar_expect_tx(bars + s, map_bytes);
+        sp::bulk_g2s(stage0 + (size_t)s * hw, A.hm + (size_t)m * hw, map_bytes, bars + s);
     };
-    int m = range_lo + warp;
-    if (m >= range_hi) m = -1;
-    if (lane == 0 && m >= 0) issue(m);
+    auto claim = [&]() {                   // lane 0: next unclaimed map of this CTA's range, or -1
+        const int m = atomicAdd(&next_map, 1);
+        return (m < range_hi) ? m : -1;
+    };
+    // lane 0 keeps the map held by each stage; the warp learns it by shuffle when the stage comes up
+    int held0 = -1, held1 = -1;
+    if (lane == 0) {
+        held0 = range_lo + warp;
+        if (held0 >= range_hi) held0 = -1;
+        if (held0 >= 0) issue(0, held0);
+        if (stages > 1 && held0 >= 0) {
+            held1 = claim();
+            if (held1 >= 0) issue(1, held1);
+        }
+    }
     for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
     sp_dec::LaneTaps<KS> taps;
     taps.load(wts, lane);
 
     double sum_sq = 0.0;
-    uint32_t parity = 0;
-    while (m >= 0) {
+    int s = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+    for (;;) {
+        const int m = __shfl_sync(SP_FULL, s == 0 ? held0 : held1, 0);
+        if (m < 0) break;                                  // maps are handed out in order: nothing follows
+        float* a = stage0 + (size_t)s * hw;
         const sp_dec::Affine T = sp_dec::load_affine(A, m);
         const sp_trn::Joint3 jc = sp_trn::load_joint(io, m);
         // float64 Gaussian factors of this map's target while its copy is in flight
         const sp_gauss::JointVerdict jv = sp_trn::prepare_map<0>(io, m, jc, ex, ey, lane);
-        sp::mbar_wait(bar, parity);
-        parity ^= 1u;
-        // ---- decode (argmax on the raw map, blur at the 13 stencil points, Taylor step, affine)
-        const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
-        sp_dec::DirectView view{a};
-        sp_dec::finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
-            return sp_dec::taylor_refine_smem<KS>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
-        });
-        // ---- target, masked difference, loss partial, gradient (+ target map, + HeatMapAcc argmaxes)
-        sp_trn::MapState st;
-        sp_trn::begin_map(io, jv, st, lane, ACC);
-        sp_trn::run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, reinterpret_cast<const float4*>(a), 0, hw >> 2, jv, ex, ey,
-                                                                st, lane, io.half_scale);
-        if (ACC) sp_trn::end_map_acc(io, m, jv, ex, ey, st, lane);
-        sum_sq += (double)st.acc;
-        __syncwarp();               // every lane is done with the staged map and the factors
-        int nm = -1;
-        if (lane == 0) {
-            nm = atomicAdd(&next_map, 1);
-            if (nm >= range_hi) nm = -1;
-            if (nm >= 0) {
-                sp::fence_proxy_async_smem();
-                issue(nm);
+        sp::mbar_wait(bars + s, s == 0 ? parity0 : parity1);
+        if (s == 0) parity0 ^= 1u; else parity1 ^= 1u;
+        // Two passes over the staged map, in an order that alternates between neighbouring warps: the loss pass is
+        // where the bytes leave (two map-sized store streams), the decode pass is arithmetic only. If every warp
+        // decoded first, HBM would idle for the first third of a small launch and be saturated by all the stores at
+        // once afterwards.
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if ((pass == 0) == ((warp & 1) != 0)) {
+                // ---- target, masked difference, loss partial, gradient (+ target map, + HeatMapAcc argmaxes)
+                sp_trn::MapState st;
+                sp_trn::begin_map(io, jv, st, lane, ACC);
+                sp_trn::run_quads<WRITE_GRAD, WRITE_TARGETS, ACC, true>(io, m, reinterpret_cast<const float4*>(a), 0, hw >> 2, jv,
+                                                                        ex, ey, st, lane, io.half_scale);
+                if (ACC) sp_trn::end_map_acc(io, m, jv, ex, ey, st, lane);
+                sum_sq += (double)st.acc;
+            } else {
+                // ---- decode (argmax on the raw map, blur at the 13 stencil points, Taylor step, affine)
+                const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
+                sp_dec::DirectView view{a};
+                sp_dec::finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
+                    return sp_dec::taylor_refine_smem<KS>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
+                });
             }
         }
-        m = __shfl_sync(SP_FULL, nm, 0);
+        __syncwarp();               // every lane is done with the staged map and the factors
+        if (lane == 0) {
+            const int nm = claim();
+            if (nm >= 0) {
+                sp::fence_proxy_async_smem();
+                issue(s, nm);
+            }
+            if (s == 0) held0 = nm; else held1 = nm;
+        }
+        if (stages > 1) s ^= 1;
     }
     sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
 }
@@ -129,20 +154,30 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     const size_t map_bytes = (size_t)H * W * 4;
     const int wpad = (W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + ((H + 1) & ~1)) * sizeof(double);
-    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
     const size_t budget = 227 * 1024 - kHeadBytes - kWtsBytes;
-    int fit = (int)(budget / per_warp);
+    const size_t per_warp1 = kPatchBytes + fac_bytes + map_bytes;
+    int fit = (int)(budget / per_warp1);
     SP_RETURN_IF(fit < 1, SP_ERR_UNSUPPORTED);
     if (fit > 16) fit = 16;
     const int sms = sp_sm_count();
-    // one map per warp in flight. Small batches: as many warps as fit, so that (at batch 128: 2176 maps on 148 SMs
-    // = 14.7 per SM, 15 warps fit) every map is resident at once and the launch is a single round. Large launches:
-    // one warp fewer leaves the copy engine a little slack, as in the decode kernel (14 measured faster than 16).
-    int nwarps = fit;
-    if (nwarps > 14 && (long long)nmaps >= 4LL * 16 * sms) nwarps = 14;
-    nwarps = sp_knob(sp_tuning().step_warps, nwarps);
+    // Small launches (at batch 128: 2176 maps on 148 SMs = 14.7 per SM, and 15 warps fit): one map per warp, as
+    // many warps as fit, so that every map is resident at once and the launch is a single round (20.0 us at
+    // batch 128 with 15 warps, 22-23 us with 8-12). Large launches: FEWER, double-buffered warps -- at 1024 x 64x48
+    // 8 warps measured 112.7 us against 125 us for 10-15 (0.87 vs 0.78 of the HBM peak), at 512 x 96x72 6 warps
+    // 131 us against 141 us for 7: every warp reads one stream and writes two, and ~3500 concurrent streams is
+    // about what the memory system sustains at full rate (the loss kernel saw the same, sp_loss.cu).
+    const SpTuning& tune = sp_tuning();
+    const bool large = (long long)nmaps >= 3LL * fit * sms;
+    int nwarps = large ? (fit >= 14 ? 8 : (fit + 1) / 2 + (fit >= 6 ? 2 : 0)) : fit;
+    nwarps = sp_knob(tune.step_warps, nwarps);
     if (nwarps < 1) nwarps = 1;
     if (nwarps > fit) nwarps = fit;
+    int stages = (large && (size_t)nwarps * (per_warp1 + map_bytes) <= budget) ? 2 : 1;
+    stages = sp_knob(tune.step_stages, stages);
+    if (stages < 1) stages = 1;
+    if (stages > 2) stages = 2;
+    while (stages > 1 && (size_t)nwarps * (per_warp1 + (stages - 1) * map_bytes) > budget) --stages;
+    const size_t per_warp = per_warp1 + (size_t)(stages - 1) * map_bytes;
     int grid = sms;
     const int need = (nmaps + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
@@ -163,7 +198,7 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
     const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
 #define SP_LAUNCH_STEP(G, T, AC) \
-    SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps))
+    SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps, stages))
     switch (sel) {
         case 0: SP_LAUNCH_STEP(false, false, false); break;
         case 1: SP_LAUNCH_STEP(false, false, true); break;

@@ -108,6 +108,12 @@ def row_keypoints(rows):
     return rows[:, :-ROW_EXTRA].reshape(rows.shape[0], -1, 3)
 
 
+def rows_equal(a, b):
+    """Bit-for-bit equality of two result tables. The two score slots hold halves of a float64 and may look like
+    NaNs when read as float32, so ``torch.equal`` on the float view would say "different" for identical rows."""
+    return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
 def chunk_cuts(seg_offsets, cuts, chunks):
     """Per rank, cut its image range into ``chunks`` contiguous image-aligned pieces balanced by person
     count. Returns int64 [world, chunks+1] image indices (row r starts at cuts[r], ends at cuts[r+1])."""
@@ -219,11 +225,15 @@ class ShardedPoseEvaluator(object):
     @torch.no_grad()
     def run(self, heat_map, trans_inv, box_scores, areas, heat_map_flip=None, joint_pairs=None, boxes=None,
             input_shape=(192, 256), compact=True):
-        """``boxes`` [n,4] (x1, y1, x2, y2) may replace ``trans_inv``/``areas``: both are then derived
-        on the device exactly as ``BasicTransform`` does (``naive_data.box_affines``). Returns the dense
-        [N, 3K+3] float32 table (``compact=True``) or the ``ShardedTable`` it would be built from."""
+        """``boxes`` [n,4] float64 (x1, y1, x2, y2) may replace ``trans_inv``/``areas``: both are then derived
+        on the device exactly as ``BasicTransform`` does (``sp_box_affine_f64``). Returns the dense
+        [N, 3K+3] float32 table (``compact=True``) or the ``ShardedTable`` it would be built from.
+
+        The host side is kept short on purpose -- at 8 GPUs a rank's whole shard decodes in ~0.4 ms, so every
+        10 us of Python between the first launch and the decode launch is 2 % of the job: inputs that already
+        are dense device tensors of the right dtype are used as they are, outputs are preallocated, and the
+        arguments of the second kernel are prepared while the first one runs."""
         from . import _abi
-        from .datasets.naive_data import box_affines
         world, rank = self._world_rank()
         lo, hi = person_range(self.seg, self.cuts, rank)
         n = hi - lo
@@ -231,50 +241,62 @@ class ShardedPoseEvaluator(object):
             raise ValueError("this rank owns persons [%d, %d): heat_map must be [%d, %d, H, W]" % (lo, hi, n, self.num_joints))
         dev = _abi.require_cuda(heat_map, heat_map_flip, trans_inv)
         k, h, w = self.num_joints, int(heat_map.shape[2]), int(heat_map.shape[3])
-        hm = _abi.dense(heat_map, torch.float32)
+        hm = heat_map if (heat_map.dtype == torch.float32 and heat_map.is_contiguous()) else _abi.dense(heat_map, torch.float32)
         hf = perm = None
         if heat_map_flip is not None:
             if tuple(heat_map_flip.shape) != tuple(heat_map.shape):
                 raise ValueError("heat_map_flip must have the shape of heat_map")
             hf = _abi.dense(heat_map_flip, torch.float32)
             perm = self.decoder._perm_on(dev, k, joint_pairs)
-        area32 = area64 = None
-        if boxes is not None:
-            aff = box_affines(boxes, input_shape, (w, h))
-            ti, area32 = aff["trans_inv"], aff["area"]
-        else:
-            ti = _abi.dense(_abi.to_device(trans_inv, torch.float32, dev), torch.float32)
-            area64 = _abi.to_device(areas, torch.float64, dev).reshape(-1)
-        bs = _abi.to_device(box_scores, torch.float64, dev).reshape(-1)
-        if tuple(ti.shape) != (n, 2, 3) or bs.shape[0] != n or (area64 is not None and area64.shape[0] != n):
-            raise ValueError("trans_inv / box_scores / areas must describe this rank's %d persons" % n)
         st = self._state(dev)
         buf = st["buffer"]
         width = buf.shape[-1]
-        blur = self.decoder._weights_on(dev)
         lib = _abi.lib()
         stream = _abi.stream_ptr(dev)
-        ws = _abi.scratch(dev, stream, 16, "decode")
-        map_elems = k * h * w
-        handles = []
-        a = 0
+        area32 = area64 = None
         with torch.cuda.device(dev):
+            if boxes is not None:
+                bx = boxes if (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype == torch.float64
+                               and boxes.is_contiguous()) else _abi.to_device(boxes, torch.float64, dev)
+                if tuple(bx.shape) != (n, 4):
+                    raise ValueError("boxes must be [%d, 4]" % n)
+                if "tinv" not in st:
+                    st["tinv"] = torch.empty((max(n, 1), 2, 3), dtype=torch.float32, device=dev)
+                    st["area"] = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
+                ti, area32 = st["tinv"], st["area"]
+                _abi.check(lib.sp_box_affine_f64(bx.data_ptr(), _abi.SP_BOX_XYXY, None, None, area32.data_ptr(), ti.data_ptr(),
+                                                 None, None, n, float(input_shape[0]) / float(input_shape[1]), w, h, 1.25, stream))
+            else:
+                ti = _abi.dense(_abi.to_device(trans_inv, torch.float32, dev), torch.float32)
+                if tuple(ti.shape) != (n, 2, 3):
+                    raise ValueError("trans_inv must be [%d, 2, 3]" % n)
+            blur = self.decoder._weights_on(dev)
+            ws = _abi.scratch(dev, stream, 16, "decode")
+            ksize = int(self.decoder.kernel_size)
+            map_elems = k * h * w
+            bs = None
+            handles = []
+            a = 0
             for c, cnt in enumerate(self.counts[rank]):
                 slot = buf[c, rank]
                 if cnt > 0:
-                    b = a + cnt
                     _abi.check_ws(lib.sp_decode_rows_f32(
                         hm.data_ptr() + 4 * a * map_elems, None if hf is None else hf.data_ptr() + 4 * a * map_elems,
                         _abi.ptr(perm), ti.data_ptr() + 24 * a, blur.data_ptr(), slot.data_ptr(), width, None, None,
-                        cnt, k, h, w, int(self.decoder.kernel_size), _abi.SP_DECODE_GAUSS_TAYLOR,
-                        ws.data_ptr(), ws.numel() * 8, stream), dev, stream)
+                        cnt, k, h, w, ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8, stream), dev, stream)
+                    if bs is None:                   # prepared while the decode kernel runs
+                        bs = _abi.to_device(box_scores, torch.float64, dev).reshape(-1)
+                        if area32 is None:
+                            area64 = _abi.to_device(areas, torch.float64, dev).reshape(-1)
+                        if bs.shape[0] != n or (area64 is not None and area64.shape[0] != n):
+                            raise ValueError("box_scores / areas must describe this rank's %d persons" % n)
                     _abi.check(lib.sp_eval_rows_nms_f32(
                         slot.data_ptr(), width, bs.data_ptr() + 8 * a,
                         None if area64 is None else area64.data_ptr() + 8 * a,
                         None if area32 is None else area32.data_ptr() + 4 * a,
                         st["seg"][c].data_ptr(), None, None, cnt, st["images"][c], k, st["max_seg"][c],
                         self.in_vis_thre, self.oks_thre, stream))
-                    a = b
+                    a += cnt
                 if world > 1:
                     # in place: this rank's slot already lies where the collective puts it; NCCL's stream waits for
                     # the two kernels above and runs while the next chunk is being decoded on this stream

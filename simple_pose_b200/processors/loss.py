@@ -93,8 +93,8 @@ def _scale_saved_grad(ctx, grad, grad_out):
 
 class _MaskedMSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target, mask, skip_masked, defer_grad):
-        need = ctx.needs_input_grad[0]                 # False under torch.no_grad() and for detached inputs
+    def forward(ctx, pred, target, mask, skip_masked, defer_grad, grad_mode):
+        need = grad_mode and pred.requires_grad        # grad_mode: torch.is_grad_enabled() at the call site (it is off in here)
         deferred = need and (defer_grad or pred.dtype in (torch.float16, torch.bfloat16))
         loss, grad = mse_forward_backward(pred, target, mask, need_grad=need and not deferred, skip_masked=skip_masked)
         ctx.deferred, ctx.skip_masked, ctx.pred_dtype = deferred, skip_masked, pred.dtype
@@ -110,12 +110,12 @@ class _MaskedMSE(torch.autograd.Function):
             pred, target, mask = ctx.saved_tensors
             _, grad = mse_forward_backward(pred, target, mask, need_grad=True, need_loss=False, skip_masked=ctx.skip_masked,
                                            grad_scale_dev=grad_out.detach().to(pred.device).reshape(()))
-            return grad.to(ctx.pred_dtype).view_as(pred), None, None, None, None
+            return grad.to(ctx.pred_dtype).view_as(pred), None, None, None, None, None
         (grad,) = ctx.saved_tensors
         if grad is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         out = _scale_saved_grad(ctx, grad, grad_out)
-        return (out if ctx.pred_dtype == torch.float32 else out.to(ctx.pred_dtype)), None, None, None, None
+        return (out if ctx.pred_dtype == torch.float32 else out.to(ctx.pred_dtype)), None, None, None, None, None
 
 
 class JointsMSELoss(torch.nn.Module):
@@ -133,7 +133,7 @@ class JointsMSELoss(torch.nn.Module):
         self.defer_grad = bool(defer_grad)
 
     def forward(self, pred, target, mask):
-        return _MaskedMSE.apply(pred, target, mask, self.skip_masked, self.defer_grad)
+        return _MaskedMSE.apply(pred, target, mask, self.skip_masked, self.defer_grad, torch.is_grad_enabled())
 
 
 def encode_mse_forward_backward(joints, pred, sigma=2.0, need_grad=True, want_targets=False, want_axes=False,
@@ -182,8 +182,8 @@ def encode_mse_forward_backward(joints, pred, sigma=2.0, need_grad=True, want_ta
 
 class _EncodeMaskedMSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, joints, sigma, want_targets, want_axes, holder, defer_grad):
-        need = ctx.needs_input_grad[0]
+    def forward(ctx, pred, joints, sigma, want_targets, want_axes, holder, defer_grad, grad_mode):
+        need = grad_mode and pred.requires_grad
         deferred = need and (defer_grad or pred.dtype in (torch.float16, torch.bfloat16))
         out = encode_mse_forward_backward(joints, pred, sigma, need_grad=need and not deferred, want_targets=want_targets,
                                           want_axes=want_axes)
@@ -197,7 +197,7 @@ class _EncodeMaskedMSE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        none = (None,) * 6
+        none = (None,) * 7
         if ctx.deferred:
             pred, joints = ctx.saved_tensors
             out = encode_mse_forward_backward(joints, pred, ctx.sigma, need_grad=True, need_loss=False,
@@ -229,7 +229,8 @@ class EncodeJointsMSELoss(torch.nn.Module):
 
     def forward(self, pred, joints):
         holder = {}
-        loss = _EncodeMaskedMSE.apply(pred, joints, self.sigma, self.keep_targets, self.with_acc, holder, self.defer_grad)
+        loss = _EncodeMaskedMSE.apply(pred, joints, self.sigma, self.keep_targets, self.with_acc, holder, self.defer_grad,
+                                      torch.is_grad_enabled())
         self.weights, self.targets = holder["weights"], holder["targets"]
         if not self.with_acc:
             return loss

@@ -27,7 +27,7 @@ def main():
     # single-device result computed on this rank's GPU without any collective, through the separate kernels
     solo = ShardedPoseEvaluator()
     from simple_pose_b200.datasets.naive_data import pack_keypoints, rescore_and_nms
-    from simple_pose_b200.eval_shard import pack_results, row_keep, row_scores, row_keypoints
+    from simple_pose_b200.eval_shard import pack_results, row_keep, row_scores, row_keypoints, rows_equal
     c, m = solo.decoder.flip_call(hm.to(dev), hf.to(dev), tinv.to(dev))
     keep, scores, _ = rescore_and_nms(pack_keypoints(c, m), box, area, seg.numpy())
     want = pack_results(c, m, keep, scores)
@@ -46,13 +46,13 @@ def main():
         # transport layout without the final concatenation
         raw = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev),
                      compact=False)
-        assert raw.persons == n and torch.equal(raw.rows(), table)
-    assert all(torch.equal(t, tables[0]) for t in tables)
+        assert raw.persons == n and rows_equal(raw.rows(), table)
+    assert all(rows_equal(t, tables[0]) for t in tables)
     table = tables[0]
     # every rank holds the same table
     ref = table.clone()
     dist.broadcast(ref, src=0)
-    assert torch.equal(ref, table)
+    assert rows_equal(ref, table)
     dist.barrier()
     if rank == 0:
         print("sharded eval ok: %d persons, %d images, world %d, kept %d" % (n, len(seg) - 1, world, int(row_keep(table).sum())))

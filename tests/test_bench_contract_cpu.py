@@ -24,6 +24,13 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "persons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    # both arms print the same config object (same workload, same sizes, derived from the same flags)
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    want = bench.bench_config(argparse.Namespace(height=64, width=48, batch=1024, persons=8192, steps=1), 1)
+    assert d["config"] == want and want["persons_per_gpu_per_step"] == 8192 * bench.step_cycles(1)
+    assert bench.step_cycles(20) == 25 and bench.step_cycles(200) == 3 and bench.step_cycles(10000) == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -521,6 +521,41 @@ def test_oks_nms_score_ties_follow_the_documented_rule(api, n):
         assert len(want) < m                                   # duplicates with equal scores really compete
 
 
+def test_oks_nms_decisions_at_the_threshold(api):
+    """The kernel decides oks > thresh from a float32 evaluation when that is further than 1e-4 from the threshold and
+    re-evaluates with the reference's float64 chain otherwise. Thresholds AT a pair's exact OKS value, one ulp either
+    side and a few 1e-5 either side must all give the float64 verdict (both kernel paths, both entry points)."""
+    kps, _, area, _ = synth.nms_groups(1, mean_group=40.0, seed=3, dup_frac=0.7, jitter=3.0)
+    kps_np, area_np = kps.numpy(), area.numpy()
+    tested = 0
+    for j in range(1, kps_np.shape[0]):
+        v = float(O.oks_similarity(kps_np[0], kps_np[j:j + 1], area_np[0], area_np[j:j + 1])[0])
+        if not 0.05 < v < 0.9995:
+            continue
+        pair_k, pair_a = kps_np[[0, j]], area_np[[0, j]]
+        for thr in (v, np.nextafter(v, 0.0), np.nextafter(v, 1.0), v + 5e-5, v - 5e-5, v + 2e-4, v - 2e-4):
+            want = [int(i) for i in O.oks_greedy_nms(pair_k, np.array([0.9, 0.8]), pair_a, thr)]
+            assert api.naive.oks_nms(pair_k, np.array([0.9, 0.8]), pair_a, thr) == want, (j, v, thr)
+            tested += 1
+        if tested >= 140:
+            break
+    assert tested >= 70
+    # the fused rows kernel takes the same decisions on float32 keypoints
+    from simple_pose_b200 import _abi
+    k32 = kps.float()
+    v = float(O.oks_similarity(k32[0].double().numpy(), k32[1:2].double().numpy(), area_np[0], area_np[1:2])[0])
+    for thr in (v, np.nextafter(v, 0.0), np.nextafter(v, 1.0)):
+        rows = torch.zeros(2, 54, device=DEV)
+        rows[:, :51] = k32[:2].reshape(2, 51).to(DEV)
+        seg = torch.tensor([0, 2], dtype=torch.int32, device=DEV)
+        bs = torch.tensor([0.9, 0.8], dtype=torch.float64, device=DEV)
+        ar = torch.from_numpy(area_np[:2]).to(DEV)
+        _abi.check(_abi.lib().sp_eval_rows_nms_f32(rows.data_ptr(), 54, bs.data_ptr(), ar.data_ptr(), None, seg.data_ptr(), None, None,
+                                                   2, 1, 17, 2, -1.0, float(thr), _abi.stream_ptr(torch.device(DEV))))
+        keep = (rows[:, 51] > 0.5).cpu().tolist()
+        assert keep == [True, not (v > thr)], (v, thr)
+
+
 def test_oks_nms_edge_cases(api):
     kps, box, area, seg = synth.nms_groups(3, mean_group=5.0, seed=2)
     # empty segment in the middle, single-person image, and one big image
@@ -600,10 +635,11 @@ def test_sharded_evaluator_single_rank_fused_rows(api, chunks, use_boxes, flip):
     o_keep, o_scores, _ = O.rescore_and_nms(kps.cpu().numpy(), es.box_scores.numpy(), area_np.astype(np.float64), es.seg.astype(np.int32))
     assert np.array_equal(eval_shard.row_keep(rows).cpu().numpy(), o_keep)
     assert np.allclose(eval_shard.row_scores(rows).cpu().numpy(), o_scores, rtol=1e-15, atol=0)
-    assert 0 < int(o_keep.sum()) < n - 50                       # the duplicate detections are really suppressed
+    if not flip:
+        assert 0 < int(o_keep.sum()) < n - 50                   # the duplicate detections are really suppressed
     raw = ev.run(hm.to(DEV), tinv, es.box_scores, torch.from_numpy(area_np).double(),
                  heat_map_flip=None if hf is None else hf.to(DEV), compact=False)
-    assert raw.buffer.shape[:2] == (chunks, 1) and raw.persons == n and torch.equal(raw.rows(), rows)
+    assert raw.buffer.shape[:2] == (chunks, 1) and raw.persons == n and eval_shard.rows_equal(raw.rows(), rows)
     with pytest.raises(ValueError):
         ev.run(hm[:-1].to(DEV), tinv[:-1], es.box_scores[:-1], torch.from_numpy(area_np[:-1]).double())
 

@@ -95,6 +95,8 @@ def test_float32_loss_node_is_single_use_unless_deferred():
     (l2 * 4.0).backward()
     assert l2.item() == loss.item() and torch.equal(q.grad, 2 * want)      # accumulated twice, each exact
     # under no_grad nothing the size of pred is allocated or written
+    with torch.no_grad():
+        JointsMSELoss()(p, tgt, msk)                  # (the reduction workspace of this stream exists from here on)
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
     before = torch.cuda.memory_allocated()
@@ -102,7 +104,7 @@ def test_float32_loss_node_is_single_use_unless_deferred():
         l3 = JointsMSELoss()(p, tgt, msk)
     torch.cuda.synchronize()
     assert l3.item() == loss.item()
-    assert torch.cuda.max_memory_allocated() - before < pred.numel() * 4 // 2
+    assert torch.cuda.max_memory_allocated() - before < pred.numel() * 4 // 2      # no gradient-sized buffer
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -214,9 +216,9 @@ def test_val_loop_of_the_hrnet_solver():
             targets, mask = encode_heat_maps(joints)
             tran_inv = synth.inverse_affines(6, seed=70 + it)[0].to(DEV)
             img_ids = list(range(10 * it, 10 * it + 6))
-            predicts = model(input_img)
-            # a trained network emits peaked maps; give the stand-in's output one so that the Taylor step is exercised
-            predicts = predicts + 0.5 * targets
+            # a trained network emits one clear peak per joint; the random stand-in alone gives flat noise whose Taylor
+            # step is ill-conditioned (offsets of thousands of pixels), so its output rides on synthetic peaks
+            predicts = 0.02 * model(input_img) + synth.heatmaps(6, seed=80 + it, noise=0.0).to(DEV)
             loss = creterion(predicts.clone(), targets, mask)
             acc = acc_func(predicts.mul(mask[..., None, None]), targets.mul(mask[..., None, None]))
             pred_kps, scores = decoder(predicts, tran_inv)
