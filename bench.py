@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=256, help="persons in the cpu_baseline sample")
     ap.add_argument("--no-ops", action="store_true", help="skip the per-op sweep (64x48 and 96x72)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the cfg-5 eval job")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -805,7 +806,7 @@ def run_ours(args):
         dist.barrier()
 
     eval_job = None
-    if not args.no_ops:
+    if not args.no_eval:
         eval_job = eval_job_numbers(device, world, rank, height=H, width=W)
 
     cpu = None

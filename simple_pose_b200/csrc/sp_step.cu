@@ -162,7 +162,7 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     const int sms = sp_sm_count();
     // Small launches (at batch 128: 2176 maps on 148 SMs = 14.7 per SM, and 15 warps fit): one map per warp, as
     // many warps as fit, so that every map is resident at once and the launch is a single round (20.0 us at
-    // batch 128 with 15 warps, 22-23 us with 8-12). Large launches: FEWER, double-buffered warps -- at 1024 x 64x48
+    // batch 128 with 15 warps, 22-23 us with 8-12). Large launches: FEWER warps -- at 1024 x 64x48
     // 8 warps measured 112.7 us against 125 us for 10-15 (0.87 vs 0.78 of the HBM peak), at 512 x 96x72 6 warps
     // 131 us against 141 us for 7: every warp reads one stream and writes two, and ~3500 concurrent streams is
     // about what the memory system sustains at full rate (the loss kernel saw the same, sp_loss.cu).
@@ -172,8 +172,9 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     nwarps = sp_knob(tune.step_warps, nwarps);
     if (nwarps < 1) nwarps = 1;
     if (nwarps > fit) nwarps = fit;
-    int stages = (large && (size_t)nwarps * (per_warp1 + map_bytes) <= budget) ? 2 : 1;
-    stages = sp_knob(tune.step_stages, stages);
+    // a second stage per warp (the next map's copy in flight while this one is processed) measured SLOWER: 123.5 vs
+    // 114.0 us at 1024 x 64x48 with 8 warps -- more bytes in flight than the memory system wants. Kept as a knob.
+    int stages = sp_knob(tune.step_stages, 1);
     if (stages < 1) stages = 1;
     if (stages > 2) stages = 2;
     while (stages > 1 && (size_t)nwarps * (per_warp1 + (stages - 1) * map_bytes) > budget) --stages;

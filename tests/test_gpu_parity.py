@@ -523,8 +523,9 @@ def test_oks_nms_score_ties_follow_the_documented_rule(api, n):
 
 def test_oks_nms_decisions_at_the_threshold(api):
     """The kernel decides oks > thresh from a float32 evaluation when that is further than 1e-4 from the threshold and
-    re-evaluates with the reference's float64 chain otherwise. Thresholds AT a pair's exact OKS value, one ulp either
-    side and a few 1e-5 either side must all give the float64 verdict (both kernel paths, both entry points)."""
+    re-evaluates with the reference's float64 chain otherwise. Thresholds a relative 1e-12 either side of a pair's exact
+    OKS value (the float64 chain itself agrees with NumPy to 1e-14: CUDA's and NumPy's exp may differ in the last bit)
+    and a few 1e-5 either side must all give the float64 verdict (both entry points)."""
     kps, _, area, _ = synth.nms_groups(1, mean_group=40.0, seed=3, dup_frac=0.7, jitter=3.0)
     kps_np, area_np = kps.numpy(), area.numpy()
     tested = 0
@@ -533,18 +534,18 @@ def test_oks_nms_decisions_at_the_threshold(api):
         if not 0.05 < v < 0.9995:
             continue
         pair_k, pair_a = kps_np[[0, j]], area_np[[0, j]]
-        for thr in (v, np.nextafter(v, 0.0), np.nextafter(v, 1.0), v + 5e-5, v - 5e-5, v + 2e-4, v - 2e-4):
+        for thr in (v * (1 - 1e-12), v * (1 + 1e-12), v + 5e-5, v - 5e-5, v + 2e-4, v - 2e-4):
             want = [int(i) for i in O.oks_greedy_nms(pair_k, np.array([0.9, 0.8]), pair_a, thr)]
             assert api.naive.oks_nms(pair_k, np.array([0.9, 0.8]), pair_a, thr) == want, (j, v, thr)
             tested += 1
         if tested >= 140:
             break
-    assert tested >= 70
+    assert tested >= 60
     # the fused rows kernel takes the same decisions on float32 keypoints
     from simple_pose_b200 import _abi
     k32 = kps.float()
     v = float(O.oks_similarity(k32[0].double().numpy(), k32[1:2].double().numpy(), area_np[0], area_np[1:2])[0])
-    for thr in (v, np.nextafter(v, 0.0), np.nextafter(v, 1.0)):
+    for thr in (v * (1 - 1e-12), v * (1 + 1e-12), v - 3e-5, v + 3e-5):
         rows = torch.zeros(2, 54, device=DEV)
         rows[:, :51] = k32[:2].reshape(2, 51).to(DEV)
         seg = torch.tensor([0, 2], dtype=torch.int32, device=DEV)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_sharded_eval_matches_single_device():
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_worker.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
