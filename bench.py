@@ -511,7 +511,7 @@ def single_device_rows(es, lo, hi, device, height, width):
     return torch.cat([xy, conf], dim=-1).reshape(hi - lo, -1), keep.bool(), scores
 
 
-def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5):
+def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5, chunks=None):
     """BASELINE config 5: a COCO-val-sized eval job (~104 k person boxes in ~5 k images, 30 % of them
     near-duplicate detections) through ``ShardedPoseEvaluator``: per rank box -> affine, then per chunk
     GaussTaylor decode into the result rows, rescoring + OKS-NMS on the rows, NCCL all-gather of the chunk
@@ -526,7 +526,7 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
     from simple_pose_b200.eval_shard import ShardedPoseEvaluator, row_keep, row_keypoints, row_scores
     es = synth.EvalSet(persons=persons, mean_group=mean_group, height=height, width=width)
     total, images = es.persons, es.images
-    ev = ShardedPoseEvaluator()
+    ev = ShardedPoseEvaluator(chunks=chunks)
     ev.plan(es.seg)
     lo, hi = ev.my_persons()
     n = hi - lo
@@ -600,6 +600,8 @@ def step_cycles(steps):
     """Passes over the rotating buffer sets per step, chosen from --steps alone (both arms and every rank derive the
     same number) so that the timed region of the product arm lasts about half a second even when few steps are asked
     for (the driver's --steps 20 used to time 27 ms, two clock samples)."""
+    if os.environ.get("SP_BENCH_CYCLES"):          # profiling aid (ncu launch lists): fewer launches per step
+        return max(1, int(os.environ["SP_BENCH_CYCLES"]))
     return max(1, -(-500 // max(1, int(steps))))
 
 

@@ -40,7 +40,11 @@ def short(name):
 
 def main():
     rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):        # `ncu -i X.ncu-rep --page raw --csv` already run on the GPU box (reports > 64 MB do not travel)
+        with open(rep) as fh:
+            raw = fh.read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}

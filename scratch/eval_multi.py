@@ -1,0 +1,14 @@
+"""torchrun worker (scratch): the cfg-5 eval job at N GPUs for several chunk counts, with the parity flag."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+import bench
+local = int(os.environ["LOCAL_RANK"]); dev = torch.device("cuda", local); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+rank, world = dist.get_rank(), dist.get_world_size()
+for chunks in [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "1,2,4").split(",")]:
+    r = bench.eval_job_numbers(dev, world, rank, chunks=chunks, reps=9)
+    if rank == 0:
+        print(json.dumps({k: r[k] for k in ("n_gpus", "chunks_per_rank", "ms", "persons_per_s", "kept_after_nms", "table_checksum", "matches_single_device", "compact_ms")}), flush=True)
+dist.barrier(); dist.destroy_process_group()

@@ -105,6 +105,34 @@ while time.time() < t_end:
                 return "fused argmax axes mismatch"
         row("fused", fused_case, b, k, h, w, seed)
 
+        def step_case():
+            # the one-launch step kernel (K = 17 layouts only: HeatmapHotPath's decoder is built per joint count)
+            from simple_pose_b200.pipeline import HeatmapHotPath
+            if w % 4 != 0:
+                return None
+            hp = HeatmapHotPath(b, k, h, w, device=DEV)
+            if not hp.one_launch_supported():
+                return None
+            j = synth.joints(b, num_joints=k, height=h, width=w, seed=seed + 9)
+            ot, ow = O.encode_batch(j.numpy(), 2.0, (w, h))
+            pred = synth.predictions_like(torch.from_numpy(ot), seed=seed + 1, noise=0.01) + hm
+            hp.step_one_launch(j.to(DEV), pred.to(DEV), tinv.to(DEV), with_acc=True)
+            ol, og = O.masked_mse_loss_and_grad(pred, torch.from_numpy(ot), torch.from_numpy(ow))
+            if abs(hp.loss.item() - ol.item()) > 1e-5 * abs(ol.item()) + 1e-12 or not torch.allclose(hp.grad.cpu(), og, rtol=1e-5, atol=1e-12):
+                return "step loss/grad mismatch %.8g vs %.8g" % (hp.loss.item(), ol.item())
+            d = ulp(hp.targets.cpu().numpy(), ot)
+            if d.max() > 1 or (d != 0).mean() > 1e-4 or not np.array_equal(hp.weights.cpu().numpy(), ow):
+                return "step targets/weights mismatch"
+            oc, om = O.gauss_taylor_decode(pred, tinv)
+            mag = float(tinv[:, 0, 0].abs().max())
+            if not torch.equal(hp.maxval.cpu(), om) or np.nanmax((hp.coords.cpu() - oc).abs().numpy()) > 1e-4 * mag + 2e-3:
+                return "step decode err %.3g" % np.nanmax((hp.coords.cpu() - oc).abs().numpy())
+            m = torch.from_numpy(ow)[..., None, None]
+            pa, _ = O.argmax_coords(pred * m); la, _ = O.argmax_coords(torch.from_numpy(ot) * m)
+            if not torch.equal(hp.pred_xy.cpu(), pa) or not torch.equal(hp.label_xy.cpu(), la):
+                return "step argmax axes mismatch"
+        row("step", step_case, b, k, h, w, seed)
+
     def nms_case():
         mean_group = float(rng.choice([1.0, 6.0, 30.0, 80.0]))
         kps, box, area, seg = synth.nms_groups(int(rng.integers(1, 6)), mean_group=mean_group, seed=seed % 100003)
@@ -113,6 +141,26 @@ while time.time() < t_end:
         if not np.array_equal(keep.cpu().numpy().astype(bool), ok) or not np.allclose(scores.cpu().numpy(), osc, rtol=1e-15, atol=0):
             return "nms keep/scores mismatch (groups of ~%g)" % mean_group
     row("nms", nms_case, seed)
+
+    def rows_nms_case():
+        # fused rescoring + NMS on float32 result rows (the float32 OKS filter with its float64 fallback)
+        from simple_pose_b200 import _abi
+        mean_group = float(rng.choice([1.0, 6.0, 30.0, 70.0]))
+        kps, box, area, seg = synth.nms_groups(int(rng.integers(1, 6)), mean_group=mean_group, seed=seed % 100019, jitter=float(rng.choice([0.5, 2.0, 6.0])))
+        k32 = kps.float()
+        n = k32.shape[0]
+        rows = torch.zeros(n, 54, device=DEV)
+        rows[:, :51] = k32.reshape(n, 51).to(DEV)
+        thr = float(rng.choice([0.9, 0.5, 0.75]))
+        mx = int(np.diff(seg.numpy()).max())
+        _abi.check(_abi.lib().sp_eval_rows_nms_f32(rows.data_ptr(), 54, box.to(DEV).data_ptr(), area.to(DEV).data_ptr(), None, seg.to(DEV).data_ptr(),
+                                                   None, None, n, len(seg) - 1, 17, mx, 0.2, thr, _abi.stream_ptr(DEV)))
+        ok, osc, _ = O.rescore_and_nms(k32.double().numpy(), box.numpy(), area.numpy(), seg.numpy(), 0.2, thr)
+        got_keep = (rows[:, 51] > 0.5).cpu().numpy()
+        got_sc = rows[:, 52:54].contiguous().view(torch.float64).reshape(-1).cpu().numpy()
+        if not np.array_equal(got_keep, ok) or not np.allclose(got_sc, osc, rtol=1e-15, atol=0):
+            return "rows nms keep/scores mismatch (groups of ~%g, thr %g)" % (mean_group, thr)
+    row("rows_nms", rows_nms_case, seed)
 
     def geometry_case():
         n = int(rng.integers(1, 40))

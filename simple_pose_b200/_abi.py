@@ -199,10 +199,17 @@ def drop_scratch(device, stream_id=None):
         del _scratch[key]
 
 
-def check_ws(code, device, stream_id):
-    """``check`` for calls that were handed a cached workspace."""
+def check_ws(code, device, stream_id, owner=None):
+    """``check`` for calls that were handed a workspace: on failure the cached per-stream scratch is dropped and an
+    ``owner`` that keeps its own (``HeatmapHotPath.ws`` / ``.dws``) gets it re-zeroed."""
     if code != 0:
         drop_scratch(device, stream_id)
+        if owner is not None:
+            try:
+                owner.ws.zero_()
+                owner.dws.zero_()
+            except Exception:
+                pass
     check(code)
 
 

@@ -303,6 +303,30 @@ struct TileRing {
         }
         return slot0 + cs * (uint32_t)CHUNK_BYTES;
     }
+    // BULK variant of release: the lanes have overwritten the chunk in place with the gradient; lane 0 hands the
+    // slot to the copy engine (cp.async.bulk shared -> global) and, one release later, re-arms it -- after
+    // cp.async.bulk.wait_group.read 1 has confirmed that every store but the newest has left shared memory.
+    // Of RING slots one is being consumed, one is draining, RING - 2 are being filled.
+    int stores;
+    __device__ __forceinline__ void release_store(int lane, void* gdst) {
+        __syncwarp();
+        if (lane == 0) {
+            sp::fence_proxy_async_smem();
+            const uint32_t src_slot = slot0 + cs * (uint32_t)CHUNK_BYTES;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_slot), "n"(CHUNK_BYTES) : "memory");
+            sp::bulk_commit();
+            --inflight;
+            if (stores++ > 0) {
+                sp::bulk_wait_read<1>();
+                issue_next();
+            }
+        }
+        if (RING > 1) {
+            if (++cs == RING) { cs = 0; parity ^= 1u; }
+        } else {
+            parity ^= 1u;
+        }
+    }
     __device__ __forceinline__ void release(int lane) {
         __syncwarp();
         if (lane == 0) {
@@ -337,7 +361,11 @@ __device__ __forceinline__ void flush_pending(const MapIo& io, PendingAxis& pd, 
 // MODE 0: Gaussian drawn, mask == 1, argmax tracked iff ACC (the common case);
 // MODE 1: nothing drawn and mask == 0 (invisible / culled joint): target 0, no tracking;
 // MODE 2: anything else (odd mask values, sigma outside the analytic range): run-time flags.
-template <int QPR, int PPC, int RING, bool ACC, int MODE>
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int QPR, int PPC, int RING, bool ACC, int MODE, bool BULK = false>
 __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVerdict& jv, const double* ex, const double* ey,
                                           TileRing<RING, PPC * 32 * Tile<QPR>::PERIOD * 16>& rg, PendingAxis& pd, int lane) {
     using T = Tile<QPR>;
@@ -420,7 +448,8 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
                 if (!unit) {
                     g.x = __fmul_rn(g.x, mk); g.y = __fmul_rn(g.y, mk); g.z = __fmul_rn(g.z, mk); g.w = __fmul_rn(g.w, mk);
                 }
-                g4[32 * step] = g;
+                if (BULK) sts128(chunk + 512u * step, g);      // in place: this lane has just read these 16 bytes
+                else      g4[32 * step] = g;
                 if (track) {
                     const float m4 = sp::fmax_nan(sp::fmax_nan(px, py), sp::fmax_nan(pz, pw));
                     if (m4 > best) bq = qlane + 32 * step;
@@ -432,11 +461,12 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
                 }
             }
         }
+        if (BULK) rg.release_store(lane, g4 - lane);
+        else      rg.release(lane);
         g4 += CHUNK_QUADS;
         qlane += CHUNK_QUADS;
 #pragma unroll
         for (int j = 0; j < PERIOD; ++j) eya[j] += 8u * (uint32_t)(PPC * ROWS);
-        rg.release(lane);
     }
 
     if (ACC) {
@@ -490,7 +520,7 @@ __device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVer
 }
 
 // dynamic smem: same layout as variant B
-template <int QPR, int PPC, int RING, bool ACC>
+template <int QPR, int PPC, int RING, bool ACC, bool BULK = false>
 __global__ void __launch_bounds__(512, 1)
 encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws, double inv_count, int nwarps,
                        int depth, int static_maps) {
@@ -512,7 +542,7 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
     rg.bar0 = base + (uint32_t)(warp * RING * 8);
     rg.slot0 = base + (uint32_t)(kRingHeader + (size_t)nwarps * fac_bytes + (size_t)warp * RING * CHUNK_BYTES);
     rg.cs = 0; rg.parity = 0; rg.ps = 0; rg.tail = 0; rg.left = 0; rg.pnext = -1; rg.src = nullptr;
-    rg.inflight = 0; rg.depth = depth;
+    rg.inflight = 0; rg.depth = depth; rg.stores = 0;
     rg.fifo = fifo; rg.next_work = &ws->next_work;
     rg.nmaps = io.nmaps;
     rg.static_stride = (int)gridDim.x * nwarps;
@@ -556,17 +586,18 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         const JointVerdict jv = prepare_map<QPR>(io, m, jc, ex, ey, lane);
         float acc;
         if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
-            acc = tile_map<QPR, PPC, RING, ACC, 0>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, RING, ACC, 0, BULK>(io, m, jv, ex, ey, rg, pd, lane);
         else if (!jv.draw && jv.weight == 0.0f)
-            acc = tile_map<QPR, PPC, RING, ACC, 1>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, RING, ACC, 1, BULK>(io, m, jv, ex, ey, rg, pd, lane);
         else
-            acc = tile_map<QPR, PPC, RING, ACC, 2>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, RING, ACC, 2, BULK>(io, m, jv, ex, ey, rg, pd, lane);
         sum_sq += (double)acc;
         __syncwarp();
         ++head;
         m = m_next;
     }
     if (ACC) flush_pending(io, pd, lane);
+    if (BULK && lane == 0) sp::bulk_wait_all<0>();           // every gradient byte of this warp is in global memory
 #ifdef SP_TRAIN_TRACE
     tr[3] = gtime(); tr[5] = head; tr[6] = clock64() - c0;
     { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid; }
@@ -715,6 +746,19 @@ static int encode_mse_launch(const float* joints, const void* pred_raw, int pred
             SP_CUDA(sp_launch_smem(encode_mse_tile_kernel<Q, P, R, false>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, depth, static_maps)); \
         }                                                                                                                    \
     } while (0)
+                // SP_TRAIN_BULK_STORE=1: the gradient leaves through the TMA too (ring >= 2; the start-up depth is the whole ring)
+                const bool bulk = sp_knob(tune.train_bulk_store, 0) == 1 && ring >= 2 && ((qpr == 12 && ppc == 2 && ring <= 4) || (qpr == 18 && ring <= 3));
+                if (bulk) {
+#define SP_LAUNCH_TILE_BULK(Q, P, R)                                                                                         \
+    do {                                                                                                                     \
+        if (pred_xy) SP_CUDA(sp_launch_smem(encode_mse_tile_kernel<Q, P, R, true, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, R, static_maps)); \
+        else         SP_CUDA(sp_launch_smem(encode_mse_tile_kernel<Q, P, R, false, true>, dim3(grid), dim3(nwarps * 32), smem, st, io, loss, ws, 1.0 / count, nwarps, R, static_maps)); \
+    } while (0)
+                    if (qpr == 12) { if (ring == 2) SP_LAUNCH_TILE_BULK(12, 2, 2); else if (ring == 3) SP_LAUNCH_TILE_BULK(12, 2, 3); else SP_LAUNCH_TILE_BULK(12, 2, 4); }
+                    else           { if (ring == 2) SP_LAUNCH_TILE_BULK(18, 1, 2); else SP_LAUNCH_TILE_BULK(18, 1, 3); }
+#undef SP_LAUNCH_TILE_BULK
+                    return 0;
+                }
                 if (qpr == 12) {
                     if (ppc == 1) SP_LAUNCH_TILE(12, 1, 2); else if (ppc == 2 && ring == 2) SP_LAUNCH_TILE(12, 2, 2);
                     else if (ppc == 2 && ring == 3) SP_LAUNCH_TILE(12, 2, 3); else if (ppc == 2 && ring == 4) SP_LAUNCH_TILE(12, 2, 4);

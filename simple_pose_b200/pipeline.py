@@ -8,7 +8,6 @@ import torch
 
 from . import _abi
 from .metrics.pose_metrics import GaussTaylorKeyPointDecoder
-from .processors.loss import _workspace
 
 ALGO_BYTES = {
     # algorithmic bytes per person, K joints, H x W float32 maps
@@ -45,6 +44,11 @@ class HeatmapHotPath(object):
         self.ksize = int(kernel_size)
         self.pred_xy = self.label_xy = None
         self._lib = _abi.lib()
+        # reduction / work-counter scratch of THIS object (zeroed once; the kernels restore the zero state). Per object
+        # rather than per stream: a captured CUDA graph bakes these pointers in and may be replayed on any stream while
+        # other callers use the per-stream scratch of the wrappers; one object must not run on two streams at once.
+        self.ws = torch.zeros((int(self._lib.sp_mse_workspace_bytes()) + 7) // 8, dtype=torch.int64, device=dev)
+        self.dws = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def _checked(self, t, shape, name, dtype=torch.float32):
         """The raw-pointer calls below read ``t`` as a dense tensor of exactly this shape and dtype on
@@ -71,11 +75,11 @@ class HeatmapHotPath(object):
         self._maps(pred, "pred")
         with torch.cuda.device(self.device):
             stream = _abi.stream_ptr(self.device)
-            ws = _workspace(self.device, stream)
+            ws = self.ws
             _abi.check_ws(self._lib.sp_mse_fwd_bwd_f32(pred.data_ptr(), self.targets.data_ptr(), self.weights.data_ptr(),
                                                        self.grad.data_ptr(), self.loss.data_ptr(), ws.data_ptr(),
                                                        ws.numel() * 8, self.batch, self.k, self.h * self.w, 1.0, 0, stream),
-                          self.device, stream)
+                          self.device, stream, self)
 
     def train_fused(self, joints, pred, with_acc=True):
         """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) in one launch; targets never materialised."""
@@ -86,12 +90,12 @@ class HeatmapHotPath(object):
         self._maps(pred, "pred")
         with torch.cuda.device(self.device):
             stream = _abi.stream_ptr(self.device)
-            ws = _workspace(self.device, stream)
+            ws = self.ws
             _abi.check_ws(self._lib.sp_encode_mse_fwd_bwd_f32(
                 joints.data_ptr(), pred.data_ptr(), self.grad.data_ptr(), None, self.weights.data_ptr(),
                 self.loss.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
                 _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
-                self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream), self.device, stream)
+                self.batch, self.k, self.h, self.w, self.sigma, 1.0, stream), self.device, stream, self)
 
     def decode(self, pred, trans_inv, pred_flip=None, perm=None):
         self._maps(pred, "pred")
@@ -102,12 +106,12 @@ class HeatmapHotPath(object):
             self._checked(perm, (self.k,), "perm", torch.int32)
         with torch.cuda.device(self.device):
             stream = _abi.stream_ptr(self.device)
-            ws = _abi.scratch(self.device, stream, 16, "decode")
+            ws = self.dws
             _abi.check_ws(self._lib.sp_decode_ws_f32(pred.data_ptr(), _abi.ptr(pred_flip), _abi.ptr(perm),
                                                      _abi.ptr(trans_inv), self.blur_w.data_ptr(), self.coords.data_ptr(),
                                                      self.maxval.data_ptr(), None, self.batch, self.k, self.h, self.w,
                                                      self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
-                                                     stream), self.device, stream)
+                                                     stream), self.device, stream, self)
 
     def step_one_launch(self, joints, pred, trans_inv, want_targets=True, want_grad=True, with_acc=False):
         """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) + GaussTaylor decode of ``pred`` in ONE launch
@@ -122,14 +126,14 @@ class HeatmapHotPath(object):
             self.label_xy = torch.empty_like(self.pred_xy)
         with torch.cuda.device(self.device):
             stream = _abi.stream_ptr(self.device)
-            ws = _workspace(self.device, stream)
+            ws = self.ws
             _abi.check_ws(self._lib.sp_step_f32(
                 joints.data_ptr(), pred.data_ptr(), _abi.ptr(trans_inv), self.blur_w.data_ptr(),
                 self.targets.data_ptr() if want_targets else None, self.weights.data_ptr(),
                 self.grad.data_ptr() if want_grad else None, self.loss.data_ptr(), self.coords.data_ptr(),
                 self.maxval.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
                 _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
-                self.batch, self.k, self.h, self.w, self.sigma, self.ksize, 1.0, stream), self.device, stream)
+                self.batch, self.k, self.h, self.w, self.sigma, self.ksize, 1.0, stream), self.device, stream, self)
         return self.loss, self.coords, self.maxval
 
     def one_launch_supported(self):

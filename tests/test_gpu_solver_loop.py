@@ -296,10 +296,7 @@ def test_one_launch_step_equals_the_three_kernels(b, hw):
     loss, coords, maxval = one.step(joints, pred, tinv)
     torch.cuda.synchronize()
     assert torch.equal(coords.nan_to_num(nan=7.5), want["coords"].nan_to_num(nan=7.5))
-    from simple_pose_b200.processors.loss import _workspace
-    from simple_pose_b200 import _abi
-    ws = _workspace(torch.device(DEV), _abi.stream_ptr(torch.device(DEV)))
-    assert int(ws[:2].abs().sum().item()) == 0
+    assert int(one.ws[:2].abs().sum().item()) == 0 and int(one.dws.abs().sum().item()) == 0
 
 
 def test_one_launch_step_vs_oracle_and_graph_replay():
