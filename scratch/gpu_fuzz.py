@@ -115,7 +115,7 @@ while time.time() < t_end:
                 return None
             j = synth.joints(b, num_joints=k, height=h, width=w, seed=seed + 9)
             ot, ow = O.encode_batch(j.numpy(), 2.0, (w, h))
-            pred = synth.predictions_like(torch.from_numpy(ot), seed=seed + 1, noise=0.01) + hm
+            pred = hm + (synth.predictions_like(torch.from_numpy(ot), seed=seed + 1, noise=0.005) - torch.from_numpy(ot))   # one clear peak + noise
             hp.step_one_launch(j.to(DEV), pred.to(DEV), tinv.to(DEV), with_acc=True)
             ol, og = O.masked_mse_loss_and_grad(pred, torch.from_numpy(ot), torch.from_numpy(ow))
             if abs(hp.loss.item() - ol.item()) > 1e-5 * abs(ol.item()) + 1e-12 or not torch.allclose(hp.grad.cpu(), og, rtol=1e-5, atol=1e-12):
@@ -153,8 +153,10 @@ while time.time() < t_end:
         rows[:, :51] = k32.reshape(n, 51).to(DEV)
         thr = float(rng.choice([0.9, 0.5, 0.75]))
         mx = int(np.diff(seg.numpy()).max())
-        _abi.check(_abi.lib().sp_eval_rows_nms_f32(rows.data_ptr(), 54, box.to(DEV).data_ptr(), area.to(DEV).data_ptr(), None, seg.to(DEV).data_ptr(),
+        d_box, d_area, d_seg = box.to(DEV), area.to(DEV), seg.to(DEV)          # kept alive across the asynchronous launch
+        _abi.check(_abi.lib().sp_eval_rows_nms_f32(rows.data_ptr(), 54, d_box.data_ptr(), d_area.data_ptr(), None, d_seg.data_ptr(),
                                                    None, None, n, len(seg) - 1, 17, mx, 0.2, thr, _abi.stream_ptr(DEV)))
+        torch.cuda.synchronize()
         ok, osc, _ = O.rescore_and_nms(k32.double().numpy(), box.numpy(), area.numpy(), seg.numpy(), 0.2, thr)
         got_keep = (rows[:, 51] > 0.5).cpu().numpy()
         got_sc = rows[:, 52:54].contiguous().view(torch.float64).reshape(-1).cpu().numpy()

@@ -136,6 +136,106 @@ step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restric
     sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
 }
 
+// Large launches of the two map sizes the reference trains on (W = 48 -> 12 quads per row, W = 72 -> 18): the same
+// kernel with the loss pass compiled as in the fused training kernel -- the (row, quad-in-row) pattern of a lane
+// repeats every Tile<QPR>::PERIOD warp steps, so the pass over the staged map is unrolled over whole periods with
+// per-lane constants, the x factors of a lane live in registers (W = 48) and the float64 factors sit in the
+// bank-conflict-free two-plane layout (sp_train.cu, variant C). About half the instructions of the generic pass,
+// which is what bounds a warp here: few warps (8 / 6) each walking one 12 / 27 KB map at a time. At most 9 warps,
+// so the register budget is 224 per thread instead of 128.
+template <int QPR, int PPC, bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
+__global__ void __launch_bounds__(288, 1)
+step_tile_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
+                 double inv_count, int nwarps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int KS = 11;
+    constexpr int CHUNK_BYTES = PPC * 32 * sp_trn::Tile<QPR>::PERIOD * 16;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int hw = A.H * A.W;
+    const uint32_t map_bytes = (uint32_t)hw * 4u;
+    const int wpad = (A.W + 1) & ~1;
+    const size_t fac_bytes = (size_t)(wpad + ((A.H + 1) & ~1)) * sizeof(double);
+    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
+    int& next_map = *reinterpret_cast<int*>(smem + kHeadBytes - 8);
+    float* wts = reinterpret_cast<float*>(smem + kHeadBytes);
+    unsigned char* mine = smem + kHeadBytes + kWtsBytes + (size_t)warp * per_warp;
+    float* patch = reinterpret_cast<float*>(mine);
+    double* ex = reinterpret_cast<double*>(mine + kPatchBytes);
+    double* ey = ex + wpad;
+    float* a = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
+
+    const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
+    const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
+    if (threadIdx.x == 0) next_map = range_lo + nwarps;
+    if (lane == 0) {
+        sp::mbar_init(bar, 1);
+        sp::mbar_fence_init();
+    }
+    __syncthreads();
+    sp::grid_dep_wait();
+
+    auto issue = [&](int m) {
+        sp::mbar_expect_tx(bar, map_bytes);
+        sp::bulk_g2s(a, A.hm + (size_t)m * hw, map_bytes, bar);
+    };
+    int m = range_lo + warp;
+    if (m >= range_hi) m = -1;
+    if (lane == 0 && m >= 0) issue(m);
+    for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
+    __syncthreads();
+    sp_dec::LaneTaps<KS> taps;
+    taps.load(wts, lane);
+
+    double sum_sq = 0.0;
+    uint32_t parity = 0;
+    sp_trn::PendingAxis pd;
+    pd.m = -1; pd.quad = 0; pd.gmax = 0.f; pd.mk = 0.f; pd.v = make_float4(0.f, 0.f, 0.f, 0.f);
+    while (m >= 0) {
+        const sp_dec::Affine T = sp_dec::load_affine(A, m);
+        const sp_trn::Joint3 jc = sp_trn::load_joint(io, m);
+        const sp_gauss::JointVerdict jv = sp_trn::prepare_map<QPR>(io, m, jc, ex, ey, lane);   // while the copy is in flight
+        sp::mbar_wait(bar, parity);
+        parity ^= 1u;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if ((pass == 0) == ((warp & 1) != 0)) {
+                sp_trn::StagedMap<CHUNK_BYTES> sm;
+                sm.next = sp::smem_u32(a);
+                float acc;
+                if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
+                    acc = sp_trn::tile_map<QPR, PPC, ACC, 0, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
+                else if (!jv.draw && jv.weight == 0.0f)
+                    acc = sp_trn::tile_map<QPR, PPC, ACC, 1, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
+                else
+                    acc = sp_trn::tile_map<QPR, PPC, ACC, 2, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
+                sum_sq += (double)acc;
+            } else {
+                const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
+                sp_dec::DirectView view{a};
+                sp_dec::finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
+                    return sp_dec::taylor_refine_smem<KS>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
+                });
+            }
+        }
+        __syncwarp();
+        int nm = -1;
+        if (lane == 0) {
+            nm = atomicAdd(&next_map, 1);
+            if (nm >= range_hi) nm = -1;
+            if (nm >= 0) {
+                sp::fence_proxy_async_smem();
+                issue(nm);
+            }
+        }
+        m = __shfl_sync(SP_FULL, nm, 0);
+    }
+    if (ACC) sp_trn::flush_pending(io, pd, lane);
+    sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
+}
+
 }  // namespace
 
 extern "C" int sp_step_f32(const float* joints, const float* pred, const float* trans_inv, const float* blur_w,
@@ -154,7 +254,7 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     const size_t map_bytes = (size_t)H * W * 4;
     const int wpad = (W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + ((H + 1) & ~1)) * sizeof(double);
-    const size_t budget = 227 * 1024 - kHeadBytes - kWtsBytes;
+    const size_t budget = 226 * 1024 - kHeadBytes - kWtsBytes;      // 1 KB spare for static shared memory (loss reduction)
     const size_t per_warp1 = kPatchBytes + fac_bytes + map_bytes;
     int fit = (int)(budget / per_warp1);
     SP_RETURN_IF(fit < 1, SP_ERR_UNSUPPORTED);
@@ -198,6 +298,35 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
     const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
+    // period-tiled loss pass for large launches of 64x48 / 96x72-shaped maps (stages == 1, <= 9 warps)
+    const int qpr = W >> 2;
+    // (opt-in, SP_STEP_TILE=1: measured 123 vs 113 us at 1024 x 64x48 with 8 warps, 111 us with 7; 139 vs 131 us at
+    // 512 x 96x72 -- the step kernel is bound by the memory system and its per-map tail, not by instruction count)
+    if (large && stages == 1 && nwarps <= 9 && (qpr == 12 || qpr == 18) && sp_knob(tune.step_tile, 0) == 1) {
+        const int rows = (qpr == 12) ? sp_trn::Tile<12>::ROWS : sp_trn::Tile<18>::ROWS;
+        const int period = (qpr == 12) ? sp_trn::Tile<12>::PERIOD : sp_trn::Tile<18>::PERIOD;
+        const int ppc = (qpr == 12) ? 2 : 1;
+        const int nq = (H * W) >> 2;
+        if (H % rows == 0 && nq % (32 * period * ppc) == 0) {
+#define SP_LAUNCH_STEP_TILE(Q, P, G, T, AC) \
+    SP_CUDA(sp_launch_smem(step_tile_kernel<Q, P, G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps))
+#define SP_STEP_TILE_SEL(Q, P)                                                  \
+    switch (sel) {                                                              \
+        case 0: SP_LAUNCH_STEP_TILE(Q, P, false, false, false); break;          \
+        case 1: SP_LAUNCH_STEP_TILE(Q, P, false, false, true); break;           \
+        case 2: SP_LAUNCH_STEP_TILE(Q, P, false, true, false); break;           \
+        case 3: SP_LAUNCH_STEP_TILE(Q, P, false, true, true); break;            \
+        case 4: SP_LAUNCH_STEP_TILE(Q, P, true, false, false); break;           \
+        case 5: SP_LAUNCH_STEP_TILE(Q, P, true, false, true); break;            \
+        case 6: SP_LAUNCH_STEP_TILE(Q, P, true, true, false); break;            \
+        default: SP_LAUNCH_STEP_TILE(Q, P, true, true, true); break;            \
+    }
+            if (qpr == 12) { SP_STEP_TILE_SEL(12, 2) } else { SP_STEP_TILE_SEL(18, 1) }
+#undef SP_STEP_TILE_SEL
+#undef SP_LAUNCH_STEP_TILE
+            return 0;
+        }
+    }
 #define SP_LAUNCH_STEP(G, T, AC) \
     SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps, stages))
     switch (sel) {

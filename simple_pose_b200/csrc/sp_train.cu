@@ -85,8 +85,6 @@ encode_mse_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* __rest
 // claim maps from a shared-memory counter (lane 0, one map ahead of the copies it is issuing) and
 // pass the claimed indices to the consuming lanes through a small per-warp FIFO.
 // dynamic smem: [mbarriers 1024 B][claim FIFOs + work counter 2048 B][factors per warp][ring slots per warp]
-constexpr int kFifo = 16;          // entries per warp; the producer is never more than ring+2 <= 10 maps ahead
-constexpr int kRingHeader = 1024 + 2048 + 64;
 
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
 __global__ void __launch_bounds__(512, 1)
@@ -192,333 +190,6 @@ encode_mse_ring_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
 // of the NEXT map from a 16-byte re-read that has had a whole map to complete.
 // Why it matters: with 16 warps per SM each warp issues about one instruction every 8 cycles, so
 // the kernel's time is (instructions per quad) x latency until the copy engine becomes the limit.
-constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
-
-template <int QPR>
-struct Tile {
-    static constexpr int G = cgcd(32, QPR);
-    static constexpr int PERIOD = QPR / G;
-    static constexpr int ROWS = 32 / G;
-    static constexpr bool EX_IN_REGS = PERIOD <= 3;
-};
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ double lds64f(uint32_t addr) {
-    double r;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ double2 lds128d(uint32_t addr) {
-    double2 r;
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-// Per-warp ring of RING slots of CHUNK_BYTES, all shared-memory addresses 32-bit.
-template <int RING, int CHUNK_BYTES>
-struct TileRing {
-    uint32_t bar0, slot0;        // shared addresses of this warp's first barrier / slot
-    uint32_t cs, parity;         // consumer slot and phase
-    // producer side (lane 0): next chunk to request
-    const char* src;             // global address of the next chunk
-    int left;                    // chunks of the current map still to request (0: no map)
-    int pnext;                   // map claimed after the current one (-1: none)
-    uint32_t ps;
-    int tail, nmaps;
-    int inflight, depth;         // copies in flight / copies kept in flight while there are unclaimed maps
-    int static_next, static_left, static_stride, dyn_base;
-    volatile int* fifo;
-    unsigned int* next_work;     // grid-wide counter in the caller's workspace
-    const char* pred;
-    size_t map_bytes;
-    int chunks_per_map;
-
-    // Maps are dealt GRID-WIDE: the first two of every warp are fixed (no atomic storm at launch), the
-    // rest come from one counter in the caller's workspace, one map ahead of the copies being issued.
-    // A per-CTA range would make the slowest SM the critical path, and the SMs are far from equal once
-    // the memory system queues: at 96x72 half the TPCs finished equal ranges in ~58 us and the other
-    // half in ~86 us (per-warp timestamps, profiles/r1f_fused_timeline.md).
-    __device__ __forceinline__ int claim() {
-        int m;
-        if (static_left > 0) {
-            m = static_next;
-            static_next += static_stride;
-            --static_left;
-        } else {
-            m = dyn_base + (int)atomicAdd(next_work, 1u);
-        }
-        const int got = (m >= 0 && m < nmaps) ? m : -1;
-        fifo[tail & (kFifo - 1)] = got;
-        ++tail;
-        return got;
-    }
-    __device__ __forceinline__ void start(int m) {           // lane 0
-        left = 0;
-        pnext = -1;
-        if (m >= 0) {
-            src = pred + (size_t)m * map_bytes;
-            left = chunks_per_map;
-            pnext = claim();
-        }
-    }
-    __device__ __forceinline__ void issue_next() {           // lane 0
-        if (left == 0) return;
-        const uint32_t bar = bar0 + ps * 8u, dst = slot0 + ps * (uint32_t)CHUNK_BYTES;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(CHUNK_BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst), "l"(src), "n"(CHUNK_BYTES), "r"(bar) : "memory");
-        src += CHUNK_BYTES;
-        ++inflight;
-        if (--left == 0 && pnext >= 0) {
-            src = pred + (size_t)pnext * map_bytes;
-            left = chunks_per_map;
-            pnext = claim();
-        }
-        if (RING > 1) ps = (ps + 1 == RING) ? 0u : ps + 1;
-    }
-    // Keep `depth` copies in flight while the CTA has maps left to hand out; once this warp is on its
-    // last map (nothing claimed behind it) use every slot: the SM's other warps are running dry, a
-    // lone warp at depth 1 pulls ~1.3 KB/us of the SM's 22 KB/us, and the deeper ring that is slower
-    // under full load (HBM read/write turnarounds) is what shortens the launch tail.
-    __device__ __forceinline__ void top_up() {               // lane 0
-        const int want = (pnext < 0) ? RING : depth;
-        while (inflight < want && left > 0) issue_next();
-    }
-    __device__ __forceinline__ uint32_t wait() {             // returns the shared address of the chunk
-        const uint32_t bar = bar0 + cs * 8u;
-        while (!mbar_try_wait_a(bar, parity)) {
-        }
-        return slot0 + cs * (uint32_t)CHUNK_BYTES;
-    }
-    // BULK variant of release: the lanes have overwritten the chunk in place with the gradient; lane 0 hands the
-    // slot to the copy engine (cp.async.bulk shared -> global) and, one release later, re-arms it -- after
-    // cp.async.bulk.wait_group.read 1 has confirmed that every store but the newest has left shared memory.
-    // Of RING slots one is being consumed, one is draining, RING - 2 are being filled.
-    int stores;
-    __device__ __forceinline__ void release_store(int lane, void* gdst) {
-        __syncwarp();
-        if (lane == 0) {
-            sp::fence_proxy_async_smem();
-            const uint32_t src_slot = slot0 + cs * (uint32_t)CHUNK_BYTES;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_slot), "n"(CHUNK_BYTES) : "memory");
-            sp::bulk_commit();
-            --inflight;
-            if (stores++ > 0) {
-                sp::bulk_wait_read<1>();
-                issue_next();
-            }
-        }
-        if (RING > 1) {
-            if (++cs == RING) { cs = 0; parity ^= 1u; }
-        } else {
-            parity ^= 1u;
-        }
-    }
-    __device__ __forceinline__ void release(int lane) {
-        __syncwarp();
-        if (lane == 0) {
-            sp::fence_proxy_async_smem();
-            --inflight;
-            top_up();                                        // refills the slot just drained (and more in the tail)
-        }
-        if (RING > 1) {
-            if (++cs == RING) { cs = 0; parity ^= 1u; }
-        } else {
-            parity ^= 1u;
-        }
-    }
-};
-
-// The predicted-map argmax of one map whose winning quad is still on its way back from L2.
-struct PendingAxis {
-    int m;              // < 0: nothing pending
-    int quad;
-    float gmax, mk;
-    float4 v;
-};
-
-__device__ __forceinline__ void flush_pending(const MapIo& io, PendingAxis& pd, int lane) {
-    if (pd.m < 0) return;
-    const float a = __fmul_rn(pd.mk, pd.v.x), b = __fmul_rn(pd.mk, pd.v.y), c = __fmul_rn(pd.mk, pd.v.z);
-    const int sub = (a == pd.gmax) ? 0 : (b == pd.gmax) ? 1 : (c == pd.gmax) ? 2 : 3;
-    if (lane == 0) io.pred_xy[pd.m] = axis_of(pd.gmax, 4 * pd.quad + sub, io.W);
-    pd.m = -1;
-}
-
-// MODE 0: Gaussian drawn, mask == 1, argmax tracked iff ACC (the common case);
-// MODE 1: nothing drawn and mask == 0 (invisible / culled joint): target 0, no tracking;
-// MODE 2: anything else (odd mask values, sigma outside the analytic range): run-time flags.
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-template <int QPR, int PPC, int RING, bool ACC, int MODE, bool BULK = false>
-__device__ __forceinline__ float tile_map(const MapIo& io, int m, const JointVerdict& jv, const double* ex, const double* ey,
-                                          TileRing<RING, PPC * 32 * Tile<QPR>::PERIOD * 16>& rg, PendingAxis& pd, int lane) {
-    using T = Tile<QPR>;
-    constexpr int PERIOD = T::PERIOD, ROWS = T::ROWS;
-    constexpr int CHUNK_QUADS = PPC * 32 * PERIOD;
-    const int hw = io.H * io.W;
-    const bool draw = (MODE == 0) ? true : (MODE == 1) ? false : jv.draw;
-    const bool unit = (MODE == 0);
-    const bool track = ACC && ((MODE == 0) ? true : (MODE == 1) ? false : (jv.weight != 0.f));
-    const bool analytic_t = track && draw && io.analytic_ok && jv.weight >= 0.5f && jv.weight <= 4.f;
-    const bool track_t = (MODE == 2) && track && draw && !analytic_t;
-    const float mk = unit ? 1.0f : jv.weight, norm = io.norm, half_scale = io.half_scale;
-
-    // per-lane constants of one period: shared addresses of the row factor and of the x factors
-    const uint32_t ex_a = sp::smem_u32(ex), ey_a = sp::smem_u32(ey);
-    uint32_t eya[PERIOD], exa[PERIOD];
-#pragma unroll
-    for (int j = 0; j < PERIOD; ++j) {
-        const int q = lane + 32 * j;
-        const int y = q / QPR;
-        eya[j] = ey_a + 8u * (uint32_t)y;
-        exa[j] = ex_a + 16u * (uint32_t)(q - y * QPR);           // (e0, e1) plane; (e2, e3) is 16*QPR bytes further
-    }
-    double exr[T::EX_IN_REGS ? PERIOD : 1][4];
-    if (T::EX_IN_REGS && draw) {
-#pragma unroll
-        for (int j = 0; j < PERIOD; ++j) {
-            const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u * QPR);
-            exr[j][0] = a.x; exr[j][1] = a.y; exr[j][2] = b.x; exr[j][3] = b.y;
-        }
-    }
-
-    float acc = 0.f;
-    float best = -CUDART_INF_F, tbest = -CUDART_INF_F;
-    int bq = lane, tbq = lane;
-    int qlane = lane;                                   // this lane's quad at step 0 of the current chunk
-    float4* g4 = reinterpret_cast<float4*>(io.grad + (size_t)m * hw) + lane;
-    const int chunks = (hw >> 2) / CHUNK_QUADS;
-
-#pragma unroll 1
-    for (int c = 0; c < chunks; ++c) {
-        const uint32_t chunk = rg.wait() + 16u * (uint32_t)lane;
-#pragma unroll
-        for (int it = 0; it < PPC; ++it) {
-#pragma unroll
-            for (int j = 0; j < PERIOD; ++j) {
-                constexpr int kDummy = 0;
-                (void)kDummy;
-                const int step = it * PERIOD + j;
-                const float4 p = lds128(chunk + 512u * step);
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (draw) {
-                    const double fy = lds64f(eya[j] + 8u * (uint32_t)(it * ROWS));
-                    double e0, e1, e2, e3;
-                    if (T::EX_IN_REGS) {
-                        e0 = exr[j][0]; e1 = exr[j][1]; e2 = exr[j][2]; e3 = exr[j][3];
-                    } else {
-                        const double2 a = lds128d(exa[j]), b = lds128d(exa[j] + 16u * QPR);
-                        e0 = a.x; e1 = a.y; e2 = b.x; e3 = b.y;
-                    }
-                    t.x = __double2float_rn(__dmul_rn(e0, fy));
-                    t.y = __double2float_rn(__dmul_rn(e1, fy));
-                    t.z = __double2float_rn(__dmul_rn(e2, fy));
-                    t.w = __double2float_rn(__dmul_rn(e3, fy));
-                }
-                const float px = unit ? p.x : __fmul_rn(mk, p.x), py = unit ? p.y : __fmul_rn(mk, p.y);
-                const float pz = unit ? p.z : __fmul_rn(mk, p.z), pw = unit ? p.w : __fmul_rn(mk, p.w);
-                const float tx = unit ? t.x : __fmul_rn(mk, t.x), ty = unit ? t.y : __fmul_rn(mk, t.y);
-                const float tz = unit ? t.z : __fmul_rn(mk, t.z), tw = unit ? t.w : __fmul_rn(mk, t.w);
-                const float dx = __fsub_rn(px, tx), dy = __fsub_rn(py, ty), dz = __fsub_rn(pz, tz), dw = __fsub_rn(pw, tw);
-                acc = fmaf(dx, dx, acc);
-                acc = fmaf(dy, dy, acc);
-                acc = fmaf(dz, dz, acc);
-                acc = fmaf(dw, dw, acc);
-                float4 g;
-                g.x = __fmul_rn(__fmul_rn(norm, dx), half_scale);
-                g.y = __fmul_rn(__fmul_rn(norm, dy), half_scale);
-                g.z = __fmul_rn(__fmul_rn(norm, dz), half_scale);
-                g.w = __fmul_rn(__fmul_rn(norm, dw), half_scale);
-                if (!unit) {
-                    g.x = __fmul_rn(g.x, mk); g.y = __fmul_rn(g.y, mk); g.z = __fmul_rn(g.z, mk); g.w = __fmul_rn(g.w, mk);
-                }
-                if (BULK) sts128(chunk + 512u * step, g);      // in place: this lane has just read these 16 bytes
-                else      g4[32 * step] = g;
-                if (track) {
-                    const float m4 = sp::fmax_nan(sp::fmax_nan(px, py), sp::fmax_nan(pz, pw));
-                    if (m4 > best) bq = qlane + 32 * step;
-                    best = sp::fmax_nan(best, m4);          // NaN sticks: resolved by the exact scan below
-                }
-                if (track_t) {
-                    const float m4 = fmaxf(fmaxf(tx, ty), fmaxf(tz, tw));
-                    if (m4 > tbest) { tbest = m4; tbq = qlane + 32 * step; }
-                }
-            }
-        }
-        if (BULK) rg.release_store(lane, g4 - lane);
-        else      rg.release(lane);
-        g4 += CHUNK_QUADS;
-        qlane += CHUNK_QUADS;
-#pragma unroll
-        for (int j = 0; j < PERIOD; ++j) eya[j] += 8u * (uint32_t)(PPC * ROWS);
-    }
-
-    if (ACC) {
-        flush_pending(io, pd, lane);                 // the previous map's quad arrived long ago
-        float2 lxy = make_float2(0.f, 0.f);
-        if (track) {
-            const float* src = io.pred + (size_t)m * hw;
-            if (__any_sync(SP_FULL, best != best)) {
-                float pv;
-                int pi;
-                MaskedPredView<float> view{src, mk};
-                argmax_exact_scan(view, hw, lane, pv, pi);
-                if (lane == 0) io.pred_xy[m] = axis_of(pv, pi, io.W);
-            } else {
-                // every lane kept the first quad holding its own maximum: the smallest quad among
-                // the lanes that hold the warp-wide maximum contains torch.max's answer
-                const float gmax = warp_max_f32(best);
-                const int gq = (int)__reduce_min_sync(SP_FULL, (best == gmax) ? (unsigned)bq : 0x7fffffffu);
-                pd.m = m;
-                pd.quad = gq;
-                pd.gmax = gmax;
-                pd.mk = mk;
-                pd.v = __ldg(reinterpret_cast<const float4*>(src) + gq);
-            }
-            if (analytic_t) {
-                const int W = io.W;
-                const int xn = min(max(__float2int_rn(jv.mx), 0), W - 1), yn = min(max(__float2int_rn(jv.my), 0), io.H - 1);
-                const int yy = yn - 1 + lane / 3, xx = xn - 1 + lane % 3;
-                const bool in = lane < 9 && yy >= 0 && yy < io.H && xx >= 0 && xx < W;
-                float v = -CUDART_INF_F;
-                if (in) v = __fmul_rn(mk, __double2float_rn(__dmul_rn(ex[ex_slot<QPR>(xx)], ey[yy])));
-                const float gmax = warp_max_f32(v);
-                const unsigned gi = __reduce_min_sync(SP_FULL, (in && v == gmax) ? (unsigned)(yy * W + xx) : 0x7fffffffu);
-                lxy = axis_of(gmax, (int)gi, W);
-            } else if (track_t) {
-                const float gmax = warp_max_f32(tbest);
-                const int gq = (int)__reduce_min_sync(SP_FULL, (tbest == gmax) ? (unsigned)tbq : 0x7fffffffu);
-                const int y = gq / QPR, x4 = 4 * (gq - y * QPR);
-                int sub = 3;
-#pragma unroll
-                for (int e = 2; e >= 0; --e)
-                    if (__fmul_rn(mk, __double2float_rn(__dmul_rn(ex[ex_slot<QPR>(x4 + e)], ey[y]))) == gmax) sub = e;
-                lxy = axis_of(gmax, 4 * gq + sub, io.W);
-            }
-        } else if (lane == 0) {
-            io.pred_xy[m] = make_float2(0.f, 0.f);
-        }
-        if (lane == 0) io.label_xy[m] = lxy;
-    }
-    return acc;
-}
-
 // dynamic smem: same layout as variant B
 template <int QPR, int PPC, int RING, bool ACC, bool BULK = false>
 __global__ void __launch_bounds__(512, 1)
@@ -586,11 +257,11 @@ encode_mse_tile_kernel(const MapIo io, float* __restrict__ loss, MseWorkspace* _
         const JointVerdict jv = prepare_map<QPR>(io, m, jc, ex, ey, lane);
         float acc;
         if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
-            acc = tile_map<QPR, PPC, RING, ACC, 0, BULK>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, ACC, 0, BULK, true, false>(io, m, jv, ex, ey, rg, pd, lane);
         else if (!jv.draw && jv.weight == 0.0f)
-            acc = tile_map<QPR, PPC, RING, ACC, 1, BULK>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, ACC, 1, BULK, true, false>(io, m, jv, ex, ey, rg, pd, lane);
         else
-            acc = tile_map<QPR, PPC, RING, ACC, 2, BULK>(io, m, jv, ex, ey, rg, pd, lane);
+            acc = tile_map<QPR, PPC, ACC, 2, BULK, true, false>(io, m, jv, ex, ey, rg, pd, lane);
         sum_sq += (double)acc;
         __syncwarp();
         ++head;

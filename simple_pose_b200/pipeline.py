@@ -139,7 +139,7 @@ class HeatmapHotPath(object):
     def one_launch_supported(self):
         """``sp_step_f32`` takes W % 4 == 0, the reference's 11 x 11 blur and maps that fit in shared memory."""
         per_warp = 1536 + 8 * (((self.w + 1) & ~1) + ((self.h + 1) & ~1)) + 4 * self.h * self.w
-        return self.w % 4 == 0 and self.ksize == 11 and per_warp <= 227 * 1024 - 2048
+        return self.w % 4 == 0 and self.ksize == 11 and per_warp <= 226 * 1024 - 2048
 
     def step(self, joints, pred, trans_inv, one_launch=None):
         """encode(joints), decode(pred), loss/grad(pred, targets, weights).

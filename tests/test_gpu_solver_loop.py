@@ -4,6 +4,8 @@ Replays the structure of the reference's ``processors/dp_pose_hrnet_solver.py`` 
 ``amp.autocast`` + ``GradScaler`` branches) and ``val()`` :150-161 (loss, ``HeatMapAcc``, decoder, ``kps_to_dict_``)
 -- with a one-convolution stand-in for the backbone. Every quantity the loop produces from ``predicts`` is
 compared with the oracle evaluated on exactly those predictions (copied to the host)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -297,6 +299,37 @@ def test_one_launch_step_equals_the_three_kernels(b, hw):
     torch.cuda.synchronize()
     assert torch.equal(coords.nan_to_num(nan=7.5), want["coords"].nan_to_num(nan=7.5))
     assert int(one.ws[:2].abs().sum().item()) == 0 and int(one.dws.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("b,hw", [(520, (64, 48)), (200, (96, 72))])
+@pytest.mark.parametrize("env", [{}, {"SP_STEP_TILE": "1"}, {"SP_STEP_TILE": "1", "SP_STEP_WARPS": "7"}, {"SP_STEP_STAGES": "2"},
+                                 {"SP_STEP_WARPS": "3", "SP_STEP_STAGES": "2"}])
+def test_one_launch_step_large_launch_layouts(b, hw, env):
+    """Launches large enough for the few-warps configuration of sp_step_f32, its two-stage ring and the opt-in
+    period-tiled loss pass: all write the bits of the stand-alone kernels."""
+    from simple_pose_b200 import _abi
+    from simple_pose_b200.pipeline import HeatmapHotPath
+    h, w = hw
+    joints = synth.joints(b, height=h, width=w, seed=b).to(DEV)
+    joints[3, :, 2] = 0.75
+    pred = synth.heatmaps(b, height=h, width=w, seed=b + 1, noise=0.02).to(DEV)
+    pred[1, 2, 3, 4] = float("nan")
+    pred[2, 3] = -1.0
+    tinv = synth.inverse_affines(b, height=h, width=w, seed=b)[0].to(DEV)
+    want = _separate_kernels(HeatmapHotPath(b, 17, h, w, device=DEV), joints, pred, tinv)
+    one = HeatmapHotPath(b, 17, h, w, device=DEV)
+    os.environ.update(env)
+    _abi.reload_tuning()
+    try:
+        one.step_one_launch(joints, pred, tinv, with_acc=True)
+        torch.cuda.synchronize()
+    finally:
+        for k in env:
+            del os.environ[k]
+        _abi.reload_tuning()
+    eq = lambda x, y: torch.equal(x.nan_to_num(nan=7.5), y.nan_to_num(nan=7.5))
+    for key in ("targets", "weights", "grad", "coords", "maxval", "pred_xy", "label_xy"):
+        assert eq(getattr(one, key), want[key]), key
 
 
 def test_one_launch_step_vs_oracle_and_graph_replay():
