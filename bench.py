@@ -511,7 +511,8 @@ def single_device_rows(es, lo, hi, device, height, width):
     return torch.cat([xy, conf], dim=-1).reshape(hi - lo, -1), keep.bool(), scores
 
 
-def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5, chunks=None):
+def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, height=64, width=48, reps=5, chunks=None,
+                     transport="auto"):
     """BASELINE config 5: a COCO-val-sized eval job (~104 k person boxes in ~5 k images, 30 % of them
     near-duplicate detections) through ``ShardedPoseEvaluator``: per rank box -> affine, then per chunk
     GaussTaylor decode into the result rows, rescoring + OKS-NMS on the rows, NCCL all-gather of the chunk
@@ -526,7 +527,7 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
     from simple_pose_b200.eval_shard import ShardedPoseEvaluator, row_keep, row_keypoints, row_scores
     es = synth.EvalSet(persons=persons, mean_group=mean_group, height=height, width=width)
     total, images = es.persons, es.images
-    ev = ShardedPoseEvaluator(chunks=chunks)
+    ev = ShardedPoseEvaluator(chunks=chunks, transport=transport)
     ev.plan(es.seg)
     lo, hi = ev.my_persons()
     n = hi - lo
@@ -591,7 +592,7 @@ def eval_job_numbers(device, world, rank, persons=104000, mean_group=20.0, heigh
     return {"workload": "cfg5: box->affine + GaussTaylor decode + rescoring + OKS-NMS + all-gather of result rows",
             "persons": total, "images": images, "duplicate_detections": es.duplicates, "n_gpus": world, "scaling": "strong",
             "ms": ms, "persons_per_s": total / (ms * 1e-3), "kept_after_nms": kept, "chunks_per_rank": int(ev.ccuts.shape[1] - 1),
-            "compact_ms": compact_ms, "table_checksum": "%016x" % (checksum & 0xffffffffffffffff),
+            "transport": ev.transport, "compact_ms": compact_ms, "table_checksum": "%016x" % (checksum & 0xffffffffffffffff),
             "matches_single_device": bool(ok), "persons_rechecked_per_rank": checked,
             "decode_read_GBps_per_gpu": (n * (17 * height * width * 4)) / (ms * 1e-3) / 1e9}
 
@@ -645,20 +646,19 @@ def run_ours(args):
     cycles = step_cycles(args.steps)
 
     sets = make_inputs(P, B, H, W, device, seed=rank * 7919)
-    # decoded keypoints of all batches of a pass land in one flat send buffer: [P*17*2 coords | P*17 scores]; two of
-    # them alternate between passes so that a pass never waits for the all-gather of the previous one
-    kp_local = [torch.empty(P * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)]
-    views = [[(kp[:P * 17 * 2].view(P, 17, 2)[i * B:(i + 1) * B], kp[P * 17 * 2:].view(P, 17, 1)[i * B:(i + 1) * B])
-              for i in range(nb)] for kp in kp_local]
-    paths = [HeatmapHotPath(B, 17, H, W, device=device, coords=views[0][i][0], maxval=views[0][i][1]) for i in range(nb)]
-    kp_all = [torch.empty(world * P * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)] if world > 1 else None
+    # decoded keypoints of all batches of all passes of a step land in one flat send buffer: [N*17*2 coords | N*17
+    # scores], N = P * cycles persons; ONE all-gather per step (few large collectives beat many small ones), and two
+    # send / receive buffers alternate between steps so that a step never waits for the previous step's all-gather
+    N = P * cycles
+    kp_local = [torch.empty(N * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)]
+    views = [[[(kp[:N * 17 * 2].view(N, 17, 2)[(c * nb + i) * B:(c * nb + i + 1) * B],
+                kp[N * 17 * 2:].view(N, 17, 1)[(c * nb + i) * B:(c * nb + i + 1) * B]) for i in range(nb)]
+              for c in range(cycles)] for kp in kp_local]
+    paths = [HeatmapHotPath(B, 17, H, W, device=device, coords=views[0][0][i][0], maxval=views[0][0][i][1]) for i in range(nb)]
+    kp_all = [torch.empty(world * N * 17 * 3, dtype=torch.float32, device=device) for _ in range(2)] if world > 1 else None
     one_launch = paths[0].one_launch_supported()
     pending = [None, None]
-    state = {"pass": 0}
-
-    def use_buffer(side):
-        for i in range(nb):
-            paths[i].coords, paths[i].maxval = views[side][i]
+    state = {"step": 0}
 
     def finish_gather(side=None):
         for sd in ((0, 1) if side is None else (side,)):
@@ -666,27 +666,27 @@ def run_ours(args):
                 pending[sd].wait()        # stream-level wait (no host block): this buffer may be overwritten again
                 pending[sd] = None
 
-    def one_pass(three_kernels):
-        side = state["pass"] & 1
-        state["pass"] += 1
-        finish_gather(side)
-        use_buffer(side)
+    def step(three_kernels=not one_launch):
+        side = state["step"] & 1
+        state["step"] += 1
+        finish_gather(side)               # the all-gather that read this send buffer two steps ago
 
         def start_gather():
             # asynchronous: NCCL's stream waits for the kernels enqueued so far; whatever follows on the compute
-            # stream (the next pass, or the encode and loss kernels of this one) overlaps the collective
+            # stream (the rest of this step, the next step) overlaps the collective
             if world > 1:
                 pending[side] = dist.all_gather_into_tensor(kp_all[side], kp_local[side], async_op=True)
-        if three_kernels:
-            run_batches(paths, sets, after_decode=start_gather)
-        else:
+        for c in range(cycles):
             for i in range(nb):
-                paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2])
-            start_gather()
-
-    def step(three_kernels=not one_launch):
-        for _ in range(cycles):
-            one_pass(three_kernels)
+                paths[i].coords, paths[i].maxval = views[side][c][i]
+            last = c == cycles - 1
+            if three_kernels:
+                run_batches(paths, sets, after_decode=start_gather if last else None)
+            else:
+                for i in range(nb):
+                    paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2])
+                if last:
+                    start_gather()
 
     def barrier():
         finish_gather()
@@ -741,11 +741,10 @@ def run_ours(args):
     if one_launch:
         op_ms["step"] = kernel_ms(lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2]), rounds)
     side_steps = max(3, min(50, args.steps))
-    # the same passes through the three stand-alone kernels (round 1's headline step: encode, loss fwd/bwd and decode
-    # launched separately, grouped by kernel, all-gather overlapped with encode/loss)
-    for _ in range(2):
-        one_pass(True)
-    three_ms = timed(lambda: one_pass(True), side_steps)
+    # the same step through the three stand-alone kernels (round 1's headline: encode, loss fwd/bwd and decode launched
+    # separately, grouped by kernel, the all-gather overlapped with the last pass's encode/loss kernels)
+    step(True)
+    three_ms = timed(lambda: step(True), 3) / cycles
     three = {"persons_per_s": world * P / (three_ms * 1e-3), "ms_per_pass": three_ms, "launches_per_pass": 3 * nb,
              "algorithmic_bytes_per_person": ALGO_BYTES["encode"](17, H, W) + ALGO_BYTES["loss"](17, H, W) + ALGO_BYTES["decode"](17, H, W),
              "note": "sp_encode_f32 + sp_mse_fwd_bwd_f32 + sp_decode_ws_f32 per batch (pred read twice, targets written and read back)"}
@@ -790,7 +789,7 @@ def run_ours(args):
             e2e_dev = run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets)
         finally:
             os.sched_setaffinity(0, saved_affinity)      # the CPU baseline below uses every core again
-    del paths, sets, views, kp_local, kp_all
+    del paths, sets, views, kp_local, kp_all, pending
     torch.cuda.empty_cache()
 
     # per-op sweep, literal small batches, train-side caller: one GPU's worth of numbers, measured by rank 0 at every N

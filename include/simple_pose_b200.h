@@ -269,6 +269,21 @@ int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* box_scores, 
                          const float* areas_f32, const int* seg, const double* sigmas, int* rank,
                          int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, void* stream);
 
+/* The same kernel doing the multi-GPU all-gather of the result rows itself (one process per GPU; the reference
+ * evaluates on one device, processors/ddp_pose_resnet_solver.py:155-156): `rows` is this rank's slot inside a
+ * SYMMETRIC gather buffer that every rank has mapped (cuMem peer mappings over NVLink, e.g. torch's
+ * torch.distributed._symmetric_memory), at float offset `slot_offset_floats` from the buffer's base. As soon as an
+ * image's rows are complete the CTA that owns the image stores them into the same place of every rank's buffer:
+ * through `multicast_base` (the NVLS multicast mapping of the buffer: one multimem.st is replicated to all ranks by
+ * the NVSwitch) when it is non-NULL, else through `peer_bases` (DEVICE array [world] of the buffer's base address as
+ * mapped for each rank) one peer at a time. No collective follows; the caller only needs a cross-rank barrier after
+ * the kernel before any rank reads other ranks' rows. row_stride and slot_offset_floats must be even. */
+int sp_eval_rows_nms_fanout_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                                const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                                int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre,
+                                void* multicast_base, const void* const* peer_bases, int world, int my_rank,
+                                long long slot_offset_floats, void* stream);
+
 /* A10 kps_to_dict_ (metrics/pose_metrics.py:172-179) as one table for a single device->host copy:
  * rows [N, 3K+1] f32 = (x, y, conf) * K from coords [N,K,2] / maxval [N,K], then the person score
  * mean(conf) + max(conf) (mean accumulated in float64, rounded once; NaN propagates). */

@@ -53,6 +53,8 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_size, c_void]),
     "sp_eval_rows_nms_f32": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_void,
                                      c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
+    "sp_eval_rows_nms_fanout_f32": (c_int, [c_void, c_int, c_void, c_void, c_void, c_void, c_void, c_void,
+                                            c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_void, c_void, c_int, c_int, c_ll, c_void]),
     "sp_person_rows_f32": (c_int, [c_void, c_void, c_void, c_int, c_int, c_void]),
     "sp_oks_iou_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_dbl, c_void]),
     "sp_oks_nms_f64": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_void,

@@ -313,11 +313,27 @@ oks_nms_kernel(const double* __restrict__ kps, const double* __restrict__ scores
 // (box_score * mean(conf > thr)), runs the greedy OKS-NMS and completes the rows in place:
 //   row[3K] = keep flag (0/1), row[3K+1], row[3K+2] = low / high 32 bits of the float64 score.
 // No float64 keypoint copy (pack_kps), no separate rescoring pass, no pack_rows pass.
+// Where the completed rows of an image go besides the local table: nowhere (world == 1), or into the same slot of
+// every rank's copy of the gather buffer -- the all-gather of the multi-GPU evaluation done by this kernel's own
+// stores over NVLink / NVSwitch instead of a collective after it. `mc_base` is the NVLS multicast mapping of the
+// symmetric buffer (one multimem.st lands in all ranks' memories, replicated by the switch); without it the rows
+// are stored to each peer's unicast mapping in turn. `slot` = float offset of this rank's slot in the buffer.
+struct RowFanout {
+    float* mc_base;
+    float* const* peer_base;     // device array [world] of the buffer's address in each rank
+    int world, me;
+    long long slot;
+};
+
+__device__ __forceinline__ void multimem_st_v2(float2* mc_addr, float2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc_addr), "f"(v.x), "f"(v.y) : "memory");
+}
+
 __global__ void __launch_bounds__(kNmsThreads)
 eval_rows_nms_kernel(float* __restrict__ rows_io, int row_stride, const double* __restrict__ box_scores,
                      const double* __restrict__ areas_f64, const float* __restrict__ areas_f32,
                      const int* __restrict__ seg, int* __restrict__ rank, int max_seg, double vis_thr, double thresh,
-                     OksParams P, int force_serial) {
+                     OksParams P, int force_serial, RowFanout out) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     double* sc = reinterpret_cast<double*>(nms_smem);
     double* ar = sc + max_seg;
@@ -343,6 +359,23 @@ eval_rows_nms_kernel(float* __restrict__ rows_io, int row_stride, const double* 
                   r[1] = __uint_as_float((unsigned)(bits & 0xffffffffull));
                   r[2] = __uint_as_float((unsigned)(bits >> 32));
               });
+    if (out.world <= 1) return;
+    // ---- fan the image's completed rows out to every rank (8-byte pieces; a row is 3K+3 floats, 8-byte aligned for
+    // odd K and an even row_stride, which the host checks)
+    __syncthreads();                                   // keep / score slots above were written by other threads
+    const int pieces = n * row_stride / 2;
+    const size_t off = (size_t)out.slot + (size_t)lo * row_stride;
+    const float2* src = reinterpret_cast<const float2*>(base);
+    if (out.mc_base != nullptr) {
+        float2* dst = reinterpret_cast<float2*>(out.mc_base + off);
+        for (int i = threadIdx.x; i < pieces; i += kNmsThreads) multimem_st_v2(dst + i, src[i]);
+    } else {
+        for (int p = 0; p < out.world; ++p) {
+            if (p == out.me) continue;
+            float2* dst = reinterpret_cast<float2*>(out.peer_base[p] + off);
+            for (int i = threadIdx.x; i < pieces; i += kNmsThreads) dst[i] = src[i];
+        }
+    }
 }
 
 // eval.py:168-175
@@ -423,9 +456,9 @@ extern "C" int sp_person_rows_f32(const float* coords, const float* maxval, floa
     return 0;
 }
 
-extern "C" int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
-                                    const float* areas_f32, const int* seg, const double* sigmas, int* rank,
-                                    int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, void* stream) {
+static int eval_rows_nms_launch(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                                const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                                int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, RowFanout out, void* stream) {
     SP_RETURN_IF(N < 0 || I < 0 || K <= 0 || K > kMaxJoints || max_seg < 0 || row_stride < 3 * K + 3, SP_ERR_BAD_ARGUMENT);
     if (N == 0 || I == 0) return 0;
     SP_RETURN_IF(!rows || !box_scores || !seg || (!areas_f64 && !areas_f32), SP_ERR_BAD_ARGUMENT);
@@ -435,8 +468,29 @@ extern "C" int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* b
     OksParams P{sigmas, K, 0, 0.0};
     SP_CUDA(sp_launch_smem(eval_rows_nms_kernel, dim3(I), dim3(kNmsThreads), smem, static_cast<cudaStream_t>(stream),
                            rows, row_stride, box_scores, areas_f64, areas_f32, seg, rank, max_seg, in_vis_thre, oks_thre, P,
-                           sp_knob(sp_tuning().nms_serial, 0)));
+                           sp_knob(sp_tuning().nms_serial, 0), out));
     return 0;
+}
+
+extern "C" int sp_eval_rows_nms_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                                    const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                                    int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre, void* stream) {
+    RowFanout out{nullptr, nullptr, 1, 0, 0};
+    return eval_rows_nms_launch(rows, row_stride, box_scores, areas_f64, areas_f32, seg, sigmas, rank, N, I, K, max_seg,
+                                in_vis_thre, oks_thre, out, stream);
+}
+
+extern "C" int sp_eval_rows_nms_fanout_f32(float* rows, int row_stride, const double* box_scores, const double* areas_f64,
+                                           const float* areas_f32, const int* seg, const double* sigmas, int* rank,
+                                           int N, int I, int K, int max_seg, double in_vis_thre, double oks_thre,
+                                           void* multicast_base, const void* const* peer_bases, int world, int my_rank,
+                                           long long slot_offset_floats, void* stream) {
+    SP_RETURN_IF(world < 1 || my_rank < 0 || my_rank >= world || slot_offset_floats < 0, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(world > 1 && !multicast_base && !peer_bases, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(world > 1 && ((row_stride & 1) || (slot_offset_floats & 1) || (reinterpret_cast<uintptr_t>(rows) & 7u)), SP_ERR_BAD_ALIGNMENT);
+    RowFanout out{static_cast<float*>(multicast_base), reinterpret_cast<float* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_bases))), world, my_rank, slot_offset_floats};
+    return eval_rows_nms_launch(rows, row_stride, box_scores, areas_f64, areas_f32, seg, sigmas, rank, N, I, K, max_seg,
+                                in_vis_thre, oks_thre, out, stream);
 }
 
 extern "C" int sp_pack_rows_f32(const float* coords, const float* maxval, const unsigned char* keep, const double* scores,

@@ -5,9 +5,11 @@ The reference evaluates on a single device (DDP ``val()`` runs on rank 0 only,
 ``dp_pose_hrnet_solver.py:83-84,160``). Persons are independent for decode and images are
 independent for OKS-NMS, so here every rank owns a contiguous range of *images* (balanced by
 person count), decodes and NMS-filters its own persons with the CUDA kernels, and the only
-exchange is an ``all_gather_into_tensor`` of the packed per-person result rows
-(K*3 + 3 float32 = 216 B per person at K = 17) over NCCL/NVLink, issued per chunk of the shard so that
-it runs on NCCL's stream while the next chunk is being decoded.
+exchange is the all-gather of the packed per-person result rows (K*3 + 3 float32 = 216 B per person at K = 17)
+over NVLink. Two transports: ``fanout`` (default where torch's symmetric memory is available) -- the gather
+buffer is mapped by every rank and the NMS kernel itself stores each completed row into every rank's copy
+(NVLS multicast stores, or peer by peer), followed by one cross-rank barrier; ``nccl`` -- an in-place
+``all_gather_into_tensor`` per chunk of the shard on NCCL's stream while the next chunk is being decoded.
 
 Result row (``ROW_EXTRA`` = 3 trailing floats): ``(x, y, conf) * K, keep, score_lo, score_hi`` -- the last
 two are the two 32-bit halves of the float64 rescored score (``row_scores`` reassembles them), so the
@@ -17,6 +19,8 @@ One process per GPU (``torchrun``); the sharding / padding / ordering logic (``s
 ``person_range``, ``gather_rows``) is device-agnostic and runs under ``gloo`` on CPU tensors in the
 host-side tests -- the kernels themselves (decode, NMS, ``pack_results``) need CUDA.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -140,6 +144,30 @@ def gather_chunk(chunk_buffer, rank, group=None, async_op=False):
     return dist.all_gather_into_tensor(chunk_buffer.view(world * chunk_len, width), slot, group=group, async_op=async_op)
 
 
+def _symmetric_buffer(shape, device, group, required=False):
+    """A zeroed float32 buffer of ``shape`` that every rank of ``group`` has mapped into its address space (torch's
+    symmetric memory: cuMem allocations exchanged between the processes, peer mappings over NVLink and, where the
+    fabric supports it, an NVLS multicast mapping). Returns a dict (buffer, handle, peer_ptrs_dev, multicast) or None
+    when symmetric memory cannot be set up here (then the NCCL transport is used, unless ``required``). Collective:
+    every rank must call it at the same point."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = group if group is not None else dist.group.WORLD
+        buf = symm_mem.empty(shape, dtype=torch.float32, device=device)
+        handle = symm_mem.rendezvous(buf, pg)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+        handle.barrier(channel=0)
+        multicast = int(getattr(handle, "multicast_ptr", 0) or 0)
+        if os.environ.get("SP_EVAL_NO_MULTICAST"):
+            multicast = 0
+        return {"buffer": buf, "handle": handle, "peer_ptrs_dev": int(handle.buffer_ptrs_dev), "multicast": multicast}
+    except Exception:
+        if required:
+            raise
+        return None
+
+
 class ShardedTable(object):
     """The all-gathered result rows in their transport layout: ``buffer`` [chunks, world, chunk_len, width]
     (rank r's c-th chunk of persons sits in ``buffer[c, r, :counts[r][c]]``; the rest of a slot is zero
@@ -171,13 +199,18 @@ class ShardedPoseEvaluator(object):
     Three launches per chunk (``sp_decode_rows_f32``, ``sp_eval_rows_nms_f32``, the NCCL all-gather) plus
     one ``sp_box_affine_f64`` per run when boxes are given; all buffers are allocated at the first run."""
 
-    def __init__(self, kernel_size=11, num_joints=17, in_vis_thre=0.2, oks_thre=0.9, group=None, chunks=None):
+    def __init__(self, kernel_size=11, num_joints=17, in_vis_thre=0.2, oks_thre=0.9, group=None, chunks=None,
+                 transport="auto"):
         from .metrics.pose_metrics import GaussTaylorKeyPointDecoder
         self.decoder = GaussTaylorKeyPointDecoder(kernel_size, num_joints)
         self.num_joints = int(num_joints)
         self.in_vis_thre, self.oks_thre = float(in_vis_thre), float(oks_thre)
         self.group = group
         self.chunks = chunks
+        if transport not in ("auto", "fanout", "nccl"):
+            raise ValueError("transport must be 'auto', 'fanout' or 'nccl'")
+        self._requested = transport
+        self.transport = transport       # after the first run: the transport in use ('fanout', 'fanout-unicast', 'nccl', 'local')
         self.seg = self.cuts = self.ccuts = None
         self._dev_state = {}
 
@@ -192,7 +225,9 @@ class ShardedPoseEvaluator(object):
         self.cuts = shard_images(self.seg, world)
         nchunks = chunks if chunks is not None else self.chunks
         if nchunks is None:
-            nchunks = 1 if world == 1 else 2        # one chunk's NMS + all-gather hides behind the next chunk's decode
+            # fan-out transport: the NMS kernel itself stores the rows into every rank's table, nothing to pipeline.
+            # NCCL transport: 2 chunks, so that one chunk's all-gather hides behind the next chunk's decode
+            nchunks = 1 if (world == 1 or self._requested != "nccl") else 2
         nchunks = max(1, int(nchunks))
         self.ccuts = chunk_cuts(self.seg, self.cuts, nchunks)
         self.counts = [[int(self.seg[self.ccuts[r, c + 1]] - self.seg[self.ccuts[r, c]]) for c in range(nchunks)]
@@ -211,8 +246,20 @@ class ShardedPoseEvaluator(object):
             world, rank = self._world_rank()
             nchunks = self.ccuts.shape[1] - 1
             width = row_width(self.num_joints)
-            st = {"buffer": torch.zeros((nchunks, world, self.chunk_len, width), dtype=torch.float32, device=dev),
-                  "seg": [], "max_seg": [], "images": []}
+            st = {"seg": [], "max_seg": [], "images": [], "symm": None, "runs": 0}
+            shape = (nchunks, world, self.chunk_len, width)
+            if world > 1 and self._requested in ("auto", "fanout"):
+                # TWO symmetric buffers, used alternately: a fast rank's stores of run k+1 must not land in the table a
+                # slow rank is still reading from run k. With two buffers a buffer is rewritten only after the barrier
+                # of the run in between, which every rank reaches (in stream order) after its reads of the older table.
+                first = _symmetric_buffer(shape, dev, self.group, required=self._requested == "fanout")
+                if first is not None:
+                    st["symm"] = [first, _symmetric_buffer(shape, dev, self.group, required=True)]
+            if st["symm"] is not None:
+                self.transport = "fanout" if st["symm"][0]["multicast"] else "fanout-unicast"
+            else:
+                st["buffer"] = torch.zeros(shape, dtype=torch.float32, device=dev)
+                self.transport = "nccl" if world > 1 else "local"
             for c in range(nchunks):
                 i0, i1 = int(self.ccuts[rank, c]), int(self.ccuts[rank, c + 1])
                 local = (self.seg[i0:i1 + 1] - self.seg[i0]).astype(np.int32)
@@ -249,7 +296,11 @@ class ShardedPoseEvaluator(object):
             hf = _abi.dense(heat_map_flip, torch.float32)
             perm = self.decoder._perm_on(dev, k, joint_pairs)
         st = self._state(dev)
-        buf = st["buffer"]
+        symm = None
+        if st["symm"] is not None:
+            symm = st["symm"][st["runs"] & 1]
+            st["runs"] += 1
+        buf = symm["buffer"] if symm is not None else st["buffer"]
         width = buf.shape[-1]
         lib = _abi.lib()
         stream = _abi.stream_ptr(dev)
@@ -290,21 +341,35 @@ class ShardedPoseEvaluator(object):
                             area64 = _abi.to_device(areas, torch.float64, dev).reshape(-1)
                         if bs.shape[0] != n or (area64 is not None and area64.shape[0] != n):
                             raise ValueError("box_scores / areas must describe this rank's %d persons" % n)
-                    _abi.check(lib.sp_eval_rows_nms_f32(
-                        slot.data_ptr(), width, bs.data_ptr() + 8 * a,
-                        None if area64 is None else area64.data_ptr() + 8 * a,
-                        None if area32 is None else area32.data_ptr() + 4 * a,
-                        st["seg"][c].data_ptr(), None, None, cnt, st["images"][c], k, st["max_seg"][c],
-                        self.in_vis_thre, self.oks_thre, stream))
+                    if symm is None:
+                        _abi.check(lib.sp_eval_rows_nms_f32(
+                            slot.data_ptr(), width, bs.data_ptr() + 8 * a,
+                            None if area64 is None else area64.data_ptr() + 8 * a,
+                            None if area32 is None else area32.data_ptr() + 4 * a,
+                            st["seg"][c].data_ptr(), None, None, cnt, st["images"][c], k, st["max_seg"][c],
+                            self.in_vis_thre, self.oks_thre, stream))
+                    else:
+                        # the kernel stores every completed row into the same slot of every rank's buffer (NVLS
+                        # multicast when the fabric offers it, else peer by peer): the all-gather is its epilogue
+                        _abi.check(lib.sp_eval_rows_nms_fanout_f32(
+                            slot.data_ptr(), width, bs.data_ptr() + 8 * a,
+                            None if area64 is None else area64.data_ptr() + 8 * a,
+                            None if area32 is None else area32.data_ptr() + 4 * a,
+                            st["seg"][c].data_ptr(), None, None, cnt, st["images"][c], k, st["max_seg"][c],
+                            self.in_vis_thre, self.oks_thre, symm["multicast"] or None, symm["peer_ptrs_dev"], world, rank,
+                            (c * world + rank) * self.chunk_len * width, stream))
                     a += cnt
-                if world > 1:
+                if world > 1 and symm is None:
                     # in place: this rank's slot already lies where the collective puts it; NCCL's stream waits for
                     # the two kernels above and runs while the next chunk is being decoded on this stream
                     handles.append(gather_chunk(buf[c], rank, self.group, async_op=True))
+            if world > 1 and symm is not None:
+                symm["handle"].barrier(channel=0)            # every rank's rows have landed in every rank's buffer
         for hnd in handles:
             hnd.wait()                               # stream-level: later work on this stream sees the gathered rows
         table = ShardedTable(buf, self.counts)
         if not compact:
-            return table                             # the transport buffer itself: valid until the next run()
+            return table                             # the transport buffer itself: valid until the next run() (fan-out
+                                                     # transport: until the run after next), for readers on this stream
         rows = table.rows()
         return rows.clone() if rows.data_ptr() == buf.data_ptr() and rows.numel() else rows

@@ -32,11 +32,14 @@ def main():
     keep, scores, _ = rescore_and_nms(pack_keypoints(c, m), box, area, seg.numpy())
     want = pack_results(c, m, keep, scores)
     tables = []
-    for chunks in (1, 2, 5):                     # 5 > images of some ranks: empty chunks take part in the collectives
-        ev = ShardedPoseEvaluator(group=None, chunks=chunks)
+    used = set()
+    for transport, chunks in (("nccl", 1), ("nccl", 2), ("nccl", 5), ("auto", None), ("auto", 3)):
+        # 5 chunks > images of some ranks: empty chunks take part in the collectives. "auto" = the fan-out transport (the
+        # NMS kernel stores the rows into every rank's symmetric buffer) where torch's symmetric memory is available
+        ev = ShardedPoseEvaluator(group=None, chunks=chunks, transport=transport)
         ev.plan(seg.numpy())
         lo, hi = ev.my_persons()
-        for _ in range(2):                       # the transport buffer is reused by the second run
+        for _ in range(3):                       # the transport buffers are reused by later runs
             table = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev))
         assert table.shape == (n, 54), table.shape
         assert torch.equal(row_keypoints(table).reshape(n, 51), want[:, :51])
@@ -47,6 +50,7 @@ def main():
         raw = ev.run(hm[lo:hi].to(dev), tinv[lo:hi].to(dev), box[lo:hi], area[lo:hi], heat_map_flip=hf[lo:hi].to(dev),
                      compact=False)
         assert raw.persons == n and rows_equal(raw.rows(), table)
+        used.add(ev.transport)
     assert all(rows_equal(t, tables[0]) for t in tables)
     table = tables[0]
     # every rank holds the same table
@@ -55,7 +59,8 @@ def main():
     assert rows_equal(ref, table)
     dist.barrier()
     if rank == 0:
-        print("sharded eval ok: %d persons, %d images, world %d, kept %d" % (n, len(seg) - 1, world, int(row_keep(table).sum())))
+        print("sharded eval ok: %d persons, %d images, world %d, kept %d, transports %s" %
+              (n, len(seg) - 1, world, int(row_keep(table).sum()), sorted(used)))
     dist.destroy_process_group()
 
 
