@@ -19,3 +19,4 @@ def test_sharded_eval_matches_single_device():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "sharded eval ok" in p.stdout
+    print([ln for ln in p.stdout.splitlines() if "sharded eval ok" in ln][-1])      # shown with pytest -rP: world size, transports
