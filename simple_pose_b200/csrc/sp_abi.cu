@@ -68,9 +68,9 @@ void load_tuning_locked() {
     t.decode_stages = env_or_unset("SP_DECODE_STAGES");
     t.decode_grid_wide = env_or_unset("SP_DECODE_GRID_WIDE");
     t.decode_runtime_ksize = env_or_unset("SP_DECODE_RUNTIME_KSIZE");
+    t.decode_static_pct = env_or_unset("SP_DECODE_STATIC_PCT");
     t.step_warps = env_or_unset("SP_STEP_WARPS");
-    t.step_stages = env_or_unset("SP_STEP_STAGES");
-    t.step_tile = env_or_unset("SP_STEP_TILE");
+    t.step_static_pct = env_or_unset("SP_STEP_STATIC_PCT");
     t.nms_serial = env_or_unset("SP_NMS_SERIAL");
     g_tuning = t;
     g_tuning_loaded.store(true, std::memory_order_release);

@@ -37,8 +37,8 @@ struct SpTuning {
     int loss_force_ldg, loss_chunk_quads, loss_ring, loss_warps, loss_bulk_store;
     int train_force_ldg, train_chunk_quads, train_no_tile, train_tile_cfg, train_depth, train_static_pct,
         train_warps, train_ring, train_bulk_store;
-    int decode_force_generic, decode_warps, decode_stages, decode_grid_wide, decode_runtime_ksize;
-    int step_warps, step_stages, step_tile;
+    int decode_force_generic, decode_warps, decode_stages, decode_grid_wide, decode_runtime_ksize, decode_static_pct;
+    int step_warps, step_static_pct;
     int nms_serial;
 };
 const SpTuning& sp_tuning();                                     // sp_abi.cu

@@ -69,7 +69,7 @@ constexpr int kPatchBytes = 1536;
 // the tail of a launch is one map per warp instead of a whole stride of the grid.
 template <bool FLIP, int KS>
 __global__ void __launch_bounds__(512, 1)
-decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
+decode_tma_kernel(const DecodeArgs A, int nwarps, int stages, int static_maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -100,14 +100,29 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
 #endif
 
     // Work distribution. Without a workspace: the CTA's own range, claimed from shared memory. With one
-    // (sp_decode_ws_f32): maps are dealt GRID-WIDE -- the first `stages` maps of every warp are fixed,
-    // the rest come from the counter in the workspace -- because the SMs do not drain HBM at equal
-    // rates once the memory system queues (profiles/r1f_fused_timeline.md) and equal ranges make the
-    // slowest SM the critical path. The global atomic is issued one map ahead (`ahead` holds its raw
-    // result while the current map is processed), so its round trip is never waited for.
+    // (sp_decode_ws_f32): maps are dealt GRID-WIDE -- warp w of CTA c owns maps k*grid*nwarps + c*nwarps + w for
+    // k < static_maps (>= stages; interleaved across the whole grid, no atomics), the rest come from the counter in
+    // the workspace -- because the SMs do not drain HBM at equal rates once the memory system queues
+    // (profiles/r1f_fused_timeline.md) and equal ranges make the slowest SM the critical path. The global atomic
+    // is issued one map ahead (`ahead` holds its raw result while the current map is processed), so its round trip
+    // is never waited for.
     const bool grid_wide = (A.work != nullptr);
     const int round = (int)gridDim.x * nwarps;
     unsigned int ahead = 0;
+    long long static_next = (long long)stages * round + (long long)blockIdx.x * nwarps + warp;
+    int static_left = static_maps - stages;
+    auto claim_grid = [&]() {                       // lane 0, grid-wide mode: this warp's next map or -1
+        long long m;
+        if (static_left > 0) {
+            m = static_next;
+            static_next += round;
+            if (--static_left == 0) ahead = atomicAdd(A.work, 1u);          // the first dynamic claim, one map ahead
+        } else {
+            m = (long long)static_maps * round + (long long)ahead;
+            if (m < A.nmaps) ahead = atomicAdd(A.work, 1u);
+        }
+        return (m < A.nmaps) ? (int)m : -1;
+    };
     auto issue = [&](int s, int m) {                // lane 0: start the copy of map m into stage s (or park -1)
         if (m < 0) {
             claimed[s] = -1;
@@ -139,7 +154,7 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
                 issue(s, claim_local());
             }
         }
-        if (grid_wide) ahead = atomicAdd(A.work, 1u);
+        if (grid_wide && static_left <= 0) ahead = atomicAdd(A.work, 1u);
     }
     if (A.mode == SP_DECODE_GAUSS_TAYLOR || A.mode == SP_DECODE_DARK_ORIGINAL)
         for (int t = threadIdx.x; t < A.ksize * A.ksize; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
@@ -164,13 +179,7 @@ decode_tma_kernel(const DecodeArgs A, int nwarps, int stages) {
         __syncwarp();
         if (lane == 0) {
             sp::fence_proxy_async_smem();
-            if (grid_wide) {
-                const long long nm = (long long)stages * round + (long long)ahead;
-                issue(s, nm < A.nmaps ? (int)nm : -1);
-                if (nm < A.nmaps) ahead = atomicAdd(A.work, 1u);
-            } else {
-                issue(s, claim_local());
-            }
+            issue(s, grid_wide ? claim_grid() : claim_local());
         }
         if (++s == stages) { s = 0; parity ^= 1u; }
 #ifdef SP_TRAIN_TRACE
@@ -292,17 +301,31 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
         int grid = sp_sm_count();
         const int need = (A.nmaps + nwarps - 1) / nwarps;
         if (grid > need) grid = need;
-        // Grid-wide dealing costs one global atomic per map, all on one address (~3 ns each): it pays when
-        // a map is long enough to hide that -- the flip decode of 96x72 maps (55 KB per item: 81.5 -> 78.2 us
-        // for 512 persons) -- and loses below (64x48: 36 -> 61 us), so smaller items keep the equal ranges.
-        // SP_DECODE_GRID_WIDE=1/0 forces either.
+        // Work distribution (needs the caller's workspace, sp_decode_ws_f32 / sp_decode_rows_f32):
+        //  * launches of >= 4 maps per warp slot: maps dealt GRID-WIDE, 85 % of a warp's share interleaved statically
+        //    (no atomic), the tail claimed from the workspace counter one map ahead. Against equal per-CTA ranges:
+        //    1024 x 64x48 36.3 -> 36.0 us, flip 67.8 -> 66.4 us (0.986 of the HBM peak); 4096 x 64x48 130.7 -> 127.2 us;
+        //    512 x 96x72 40.1 -> 39.5 us, flip 83.3 -> 80.8 us. Without the static share every map costs a global atomic
+        //    on one address (~3 ns each), which loses for 12 KB items (64x48: 36 -> 39 us; 4096 persons: 131 -> 203 us);
+        //  * smaller launches: equal per-CTA ranges claimed from shared memory (256 x 64x48: 12.4 us vs 16.1 us
+        //    grid-wide), except items >= 40 KB (flip decode of 96x72 maps), which keep the all-dynamic dealing.
+        // SP_DECODE_GRID_WIDE=1/0 forces either, SP_DECODE_STATIC_PCT sets the static share.
+        int static_pct = 0;
         {
             const int force = sp_knob(tune.decode_grid_wide, -1);
-            if (force == 0 || (force < 0 && stage_bytes < 40 * 1024)) A.work = nullptr;
+            const bool large = (long long)A.nmaps >= 4LL * nwarps * sp_sm_count();
+            if (force == 0 || (force < 0 && !large && stage_bytes < 40 * 1024)) A.work = nullptr;
+            if (large) static_pct = 85;
+            static_pct = sp_knob(tune.decode_static_pct, static_pct);
+        }
+        int static_maps = stages;
+        if (A.work != nullptr) {
+            const int share = (int)((long long)A.nmaps * static_pct / 100 / ((long long)grid * nwarps));
+            if (share > static_maps) static_maps = share;
         }
 #define SP_LAUNCH_DECODE(F, KS)                                                                                     \
     do {                                                                                                            \
-        SP_CUDA(sp_launch_smem(decode_tma_kernel<F, KS>, dim3(grid), dim3(nwarps * 32), smem, st, A, nwarps, stages));   \
+        SP_CUDA(sp_launch_smem(decode_tma_kernel<F, KS>, dim3(grid), dim3(nwarps * 32), smem, st, A, nwarps, stages, static_maps)); \
     } while (0)
         const bool ks11 = (ksize == 11) && sp_knob(tune.decode_runtime_ksize, 0) == 0;
         if (flip) { if (ks11) SP_LAUNCH_DECODE(true, 11); else SP_LAUNCH_DECODE(true, 0); }

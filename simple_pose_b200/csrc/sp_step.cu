@@ -28,11 +28,18 @@ constexpr int kHeadBytes = 1024;     // mbarriers (one per warp), claimed-map sl
 constexpr int kWtsBytes = 1024;      // 11 x 11 blur weights
 constexpr int kPatchBytes = 1536;    // zero-padded 15 x 15 patch for peaks near the border
 
-// dynamic shared memory: [head][blur weights] then per warp [patch][float64 factors][stages x the map]
+// dynamic shared memory: [head][blur weights] then per warp [patch][float64 factors][the map]
+//
+// Work distribution. static_maps == 0: CTA c owns the contiguous map range [c*nmaps/grid, (c+1)*nmaps/grid) and its
+// warps claim maps from a shared-memory counter (small launches: nothing to balance, no global atomics).
+// static_maps > 0: maps are dealt GRID-WIDE -- warp w of CTA c owns maps k*grid*nwarps + c*nwarps + w for
+// k < static_maps, the rest come one at a time from the counter in the caller's workspace (claimed one map ahead, so
+// the atomic's round trip is never waited for). The SMs do not drain HBM at equal rates once the memory system
+// queues (profiles/r1f_fused_timeline.md), and with equal ranges the slowest SM is the critical path.
 template <bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
 __global__ void __launch_bounds__(512, 1)
 step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
-            double inv_count, int nwarps, int stages) {
+            double inv_count, int nwarps, int static_maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KS = 11;
     const int lane = threadIdx.x & 31;
@@ -41,64 +48,69 @@ step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restric
     const uint32_t map_bytes = (uint32_t)hw * 4u;
     const int wpad = (A.W + 1) & ~1;
     const size_t fac_bytes = (size_t)(wpad + ((A.H + 1) & ~1)) * sizeof(double);
-    const size_t per_warp = kPatchBytes + fac_bytes + (size_t)stages * map_bytes;
+    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * stages;          // <= 16 warps x 2 stages x 8 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
     int& next_map = *reinterpret_cast<int*>(smem + kHeadBytes - 8);
     float* wts = reinterpret_cast<float*>(smem + kHeadBytes);
     unsigned char* mine = smem + kHeadBytes + kWtsBytes + (size_t)warp * per_warp;
     float* patch = reinterpret_cast<float*>(mine);
     double* ex = reinterpret_cast<double*>(mine + kPatchBytes);
     double* ey = ex + wpad;
-    float* stage0 = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
+    float* a = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
 
+    const bool grid_wide = static_maps > 0;
+    const int round = (int)gridDim.x * nwarps;
     const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
     const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
-    if (threadIdx.x == 0) next_map = range_lo + nwarps;      // the first nwarps maps of the range are assigned statically
+    if (threadIdx.x == 0) next_map = range_lo + nwarps;      // per-CTA mode: the first nwarps maps are assigned statically
     if (lane == 0) {
-        for (int s = 0; s < stages; ++s) sp::mbar_init(bars + s, 1);
+        sp::mbar_init(bar, 1);
         sp::mbar_fence_init();
     }
     __syncthreads();
     sp::grid_dep_wait();            // everything above overlapped the previous kernel's tail
 
-    auto issue = [&](int s, int m) {       // lane 0: start the copy of map m into stage s
-        sp::mbar_expect_tx(bars + s, map_bytes);
-        sp::bulk_g2s(stage0 + (size_t)s * hw, A.hm + (size_t)m * hw, map_bytes, bars + s);
+    auto issue = [&](int m) {       // lane 0: start the copy of map m
+        sp::mbar_expect_tx(bar, map_bytes);
+        sp::bulk_g2s(a, A.hm + (size_t)m * hw, map_bytes, bar);
     };
-    auto claim = [&]() {                   // lane 0: next unclaimed map of this CTA's range, or -1
-        const int m = atomicAdd(&next_map, 1);
-        return (m < range_hi) ? m : -1;
-    };
-    // lane 0 keeps the map held by each stage; the warp learns it by shuffle when the stage comes up
-    int held0 = -1, held1 = -1;
-    if (lane == 0) {
-        held0 = range_lo + warp;
-        if (held0 >= range_hi) held0 = -1;
-        if (held0 >= 0) issue(0, held0);
-        if (stages > 1 && held0 >= 0) {
-            held1 = claim();
-            if (held1 >= 0) issue(1, held1);
+    long long static_next = (long long)blockIdx.x * nwarps + warp + round;      // grid-wide mode: this warp's second static map
+    int static_left = static_maps - 1;
+    auto claim = [&]() {            // lane 0: the map after the ones this warp already holds, or -1
+        if (!grid_wide) {
+            const int m = atomicAdd(&next_map, 1);
+            return (m < range_hi) ? m : -1;
         }
-    }
+        long long m;
+        if (static_left > 0) {
+            m = static_next;
+            static_next += round;
+            --static_left;
+        } else {
+            m = (long long)static_maps * round + (long long)atomicAdd(&ws->next_work, 1u);
+        }
+        return (m < A.nmaps) ? (int)m : -1;
+    };
+    int m = grid_wide ? (int)blockIdx.x * nwarps + warp : range_lo + warp;
+    if (m >= (grid_wide ? A.nmaps : range_hi)) m = -1;
+    if (lane == 0 && m >= 0) issue(m);
     for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
     __syncthreads();
     sp_dec::LaneTaps<KS> taps;
     taps.load(wts, lane);
 
     double sum_sq = 0.0;
-    int s = 0;
-    uint32_t parity0 = 0, parity1 = 0;
-    for (;;) {
-        const int m = __shfl_sync(SP_FULL, s == 0 ? held0 : held1, 0);
-        if (m < 0) break;                                  // maps are handed out in order: nothing follows
-        float* a = stage0 + (size_t)s * hw;
+    uint32_t parity = 0;
+    while (m >= 0) {
+        int ahead = -1;
+        if (lane == 0) ahead = claim();                    // its latency hides behind this map's work
         const sp_dec::Affine T = sp_dec::load_affine(A, m);
         const sp_trn::Joint3 jc = sp_trn::load_joint(io, m);
         // float64 Gaussian factors of this map's target while its copy is in flight
         const sp_gauss::JointVerdict jv = sp_trn::prepare_map<0>(io, m, jc, ex, ey, lane);
-        sp::mbar_wait(bars + s, s == 0 ? parity0 : parity1);
-        if (s == 0) parity0 ^= 1u; else parity1 ^= 1u;
+        sp::mbar_wait(bar, parity);
+        parity ^= 1u;
         // Two passes over the staged map, in an order that alternates between neighbouring warps: the loss pass is
         // where the bytes leave (two map-sized store streams), the decode pass is arithmetic only. If every warp
         // decoded first, HBM would idle for the first third of a small launch and be saturated by all the stores at
@@ -123,117 +135,13 @@ step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restric
             }
         }
         __syncwarp();               // every lane is done with the staged map and the factors
-        if (lane == 0) {
-            const int nm = claim();
-            if (nm >= 0) {
-                sp::fence_proxy_async_smem();
-                issue(s, nm);
-            }
-            if (s == 0) held0 = nm; else held1 = nm;
+        if (lane == 0 && ahead >= 0) {
+            sp::fence_proxy_async_smem();
+            issue(ahead);
         }
-        if (stages > 1) s ^= 1;
+        m = __shfl_sync(SP_FULL, ahead, 0);
     }
-    sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
-}
-
-// Large launches of the two map sizes the reference trains on (W = 48 -> 12 quads per row, W = 72 -> 18): the same
-// kernel with the loss pass compiled as in the fused training kernel -- the (row, quad-in-row) pattern of a lane
-// repeats every Tile<QPR>::PERIOD warp steps, so the pass over the staged map is unrolled over whole periods with
-// per-lane constants, the x factors of a lane live in registers (W = 48) and the float64 factors sit in the
-// bank-conflict-free two-plane layout (sp_train.cu, variant C). About half the instructions of the generic pass,
-// which is what bounds a warp here: few warps (8 / 6) each walking one 12 / 27 KB map at a time. At most 9 warps,
-// so the register budget is 224 per thread instead of 128.
-template <int QPR, int PPC, bool WRITE_GRAD, bool WRITE_TARGETS, bool ACC>
-__global__ void __launch_bounds__(288, 1)
-step_tile_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restrict__ loss, MseWorkspace* __restrict__ ws,
-                 double inv_count, int nwarps) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int KS = 11;
-    constexpr int CHUNK_BYTES = PPC * 32 * sp_trn::Tile<QPR>::PERIOD * 16;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int hw = A.H * A.W;
-    const uint32_t map_bytes = (uint32_t)hw * 4u;
-    const int wpad = (A.W + 1) & ~1;
-    const size_t fac_bytes = (size_t)(wpad + ((A.H + 1) & ~1)) * sizeof(double);
-    const size_t per_warp = kPatchBytes + fac_bytes + map_bytes;
-
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem) + warp;
-    int& next_map = *reinterpret_cast<int*>(smem + kHeadBytes - 8);
-    float* wts = reinterpret_cast<float*>(smem + kHeadBytes);
-    unsigned char* mine = smem + kHeadBytes + kWtsBytes + (size_t)warp * per_warp;
-    float* patch = reinterpret_cast<float*>(mine);
-    double* ex = reinterpret_cast<double*>(mine + kPatchBytes);
-    double* ey = ex + wpad;
-    float* a = reinterpret_cast<float*>(mine + kPatchBytes + fac_bytes);
-
-    const int range_lo = (int)((long long)blockIdx.x * A.nmaps / gridDim.x);
-    const int range_hi = (int)((long long)(blockIdx.x + 1) * A.nmaps / gridDim.x);
-    if (threadIdx.x == 0) next_map = range_lo + nwarps;
-    if (lane == 0) {
-        sp::mbar_init(bar, 1);
-        sp::mbar_fence_init();
-    }
-    __syncthreads();
-    sp::grid_dep_wait();
-
-    auto issue = [&](int m) {
-        sp::mbar_expect_tx(bar, map_bytes);
-        sp::bulk_g2s(a, A.hm + (size_t)m * hw, map_bytes, bar);
-    };
-    int m = range_lo + warp;
-    if (m >= range_hi) m = -1;
-    if (lane == 0 && m >= 0) issue(m);
-    for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) wts[t] = __ldg(A.blur_w + t);
-    __syncthreads();
-    sp_dec::LaneTaps<KS> taps;
-    taps.load(wts, lane);
-
-    double sum_sq = 0.0;
-    uint32_t parity = 0;
-    sp_trn::PendingAxis pd;
-    pd.m = -1; pd.quad = 0; pd.gmax = 0.f; pd.mk = 0.f; pd.v = make_float4(0.f, 0.f, 0.f, 0.f);
-    while (m >= 0) {
-        const sp_dec::Affine T = sp_dec::load_affine(A, m);
-        const sp_trn::Joint3 jc = sp_trn::load_joint(io, m);
-        const sp_gauss::JointVerdict jv = sp_trn::prepare_map<QPR>(io, m, jc, ex, ey, lane);   // while the copy is in flight
-        sp::mbar_wait(bar, parity);
-        parity ^= 1u;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            if ((pass == 0) == ((warp & 1) != 0)) {
-                sp_trn::StagedMap<CHUNK_BYTES> sm;
-                sm.next = sp::smem_u32(a);
-                float acc;
-                if (jv.draw && jv.weight == 1.0f && (!ACC || io.analytic_ok))
-                    acc = sp_trn::tile_map<QPR, PPC, ACC, 0, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
-                else if (!jv.draw && jv.weight == 0.0f)
-                    acc = sp_trn::tile_map<QPR, PPC, ACC, 1, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
-                else
-                    acc = sp_trn::tile_map<QPR, PPC, ACC, 2, false, WRITE_GRAD, WRITE_TARGETS>(io, m, jv, ex, ey, sm, pd, lane);
-                sum_sq += (double)acc;
-            } else {
-                const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
-                sp_dec::DirectView view{a};
-                sp_dec::finish_map(A, view, m, pk, lane, T, [&](int px, int py, float ori_max, float& ox, float& oy) {
-                    return sp_dec::taylor_refine_smem<KS>(a, wts, patch, taps, A.H, A.W, px, py, ori_max, lane, ox, oy);
-                });
-            }
-        }
-        __syncwarp();
-        int nm = -1;
-        if (lane == 0) {
-            nm = atomicAdd(&next_map, 1);
-            if (nm >= range_hi) nm = -1;
-            if (nm >= 0) {
-                sp::fence_proxy_async_smem();
-                issue(nm);
-            }
-        }
-        m = __shfl_sync(SP_FULL, nm, 0);
-    }
-    if (ACC) sp_trn::flush_pending(io, pd, lane);
-    sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);
+    sp_reduce::finish_loss<512>(sum_sq, ws, loss, inv_count);      // the last block also returns ws->next_work to zero
 }
 
 }  // namespace
@@ -260,29 +168,31 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     SP_RETURN_IF(fit < 1, SP_ERR_UNSUPPORTED);
     if (fit > 16) fit = 16;
     const int sms = sp_sm_count();
-    // Small launches (at batch 128: 2176 maps on 148 SMs = 14.7 per SM, and 15 warps fit): one map per warp, as
-    // many warps as fit, so that every map is resident at once and the launch is a single round (20.0 us at
-    // batch 128 with 15 warps, 22-23 us with 8-12). Large launches: FEWER warps -- at 1024 x 64x48
-    // 8 warps measured 112.7 us against 125 us for 10-15 (0.87 vs 0.78 of the HBM peak), at 512 x 96x72 6 warps
-    // 131 us against 141 us for 7: every warp reads one stream and writes two, and ~3500 concurrent streams is
-    // about what the memory system sustains at full rate (the loss kernel saw the same, sp_loss.cu).
+    // Small launches (at batch 128: 2176 maps on 148 SMs = 14.7 per SM, and 15 warps fit): one map per warp, as many
+    // warps as fit, so that every map is resident at once and the launch is a single round (20.0 us at batch 128 with
+    // 15 warps, 22-23 us with 8-12), maps taken from per-CTA ranges. Larger launches: FEWER warps (every warp reads one
+    // stream and writes two; 9-12 warps per SM measure the same at 1024 x 64x48, 14 and more lose 1-4 %, 7 loses 7 %)
+    // and maps dealt grid-wide, 80 % of a warp's share interleaved statically and the tail claimed dynamically:
+    // 1024 x 64x48 113.0 -> 108.0 us, 2048: 212.5 -> 204.6 us (0.96 of the HBM peak), 512 x 96x72: 131 -> 125 us,
+    // 384 x 64x48: 51.9 -> 47.3 us. A purely static interleaved assignment loses again (119.8 us with 10 warps).
     const SpTuning& tune = sp_tuning();
-    const bool large = (long long)nmaps >= 3LL * fit * sms;
-    int nwarps = large ? (fit >= 14 ? 8 : (fit + 1) / 2 + (fit >= 6 ? 2 : 0)) : fit;
+    const bool large = 2LL * nmaps >= 3LL * fit * sms;       // more than one and a half rounds of one map per warp
+    int nwarps = large ? (fit >= 14 ? 9 : (fit + 1) / 2 + (fit >= 6 ? 2 : 0)) : fit;
     nwarps = sp_knob(tune.step_warps, nwarps);
     if (nwarps < 1) nwarps = 1;
     if (nwarps > fit) nwarps = fit;
-    // a second stage per warp (the next map's copy in flight while this one is processed) measured SLOWER: 123.5 vs
-    // 114.0 us at 1024 x 64x48 with 8 warps -- more bytes in flight than the memory system wants. Kept as a knob.
-    int stages = sp_knob(tune.step_stages, 1);
-    if (stages < 1) stages = 1;
-    if (stages > 2) stages = 2;
-    while (stages > 1 && (size_t)nwarps * (per_warp1 + (stages - 1) * map_bytes) > budget) --stages;
-    const size_t per_warp = per_warp1 + (size_t)(stages - 1) * map_bytes;
     int grid = sms;
     const int need = (nmaps + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
-    const size_t smem = kHeadBytes + kWtsBytes + (size_t)nwarps * per_warp;
+    const size_t smem = kHeadBytes + kWtsBytes + (size_t)nwarps * per_warp1;
+    // large launches: maps dealt grid-wide; SP_STEP_STATIC_PCT % of a warp's expected share is fixed up front (no atomic),
+    // the rest is claimed dynamically. Tried and dropped for this kernel (numbers in DESIGN.md section 4): a second stage per
+    // warp (123.5 vs 114.0 us at 1024 x 64x48) and the period-tiled loss pass of the fused training kernel (123 vs 113 us).
+    int static_maps = 0;
+    if (large || sp_knob(tune.step_static_pct, -1) >= 0) {
+        static_maps = (int)((long long)nmaps * sp_knob(tune.step_static_pct, 80) / 100 / ((long long)grid * nwarps));
+        if (static_maps < 1) static_maps = 1;
+    }
 
     sp_dec::DecodeArgs A;
     A.hm = pred; A.hm_flip = nullptr; A.perm = nullptr; A.trans_inv = trans_inv; A.blur_w = blur_w;
@@ -298,37 +208,8 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MseWorkspace* ws = static_cast<MseWorkspace*>(workspace);
     const int sel = (grad ? 4 : 0) | (targets ? 2 : 0) | (pred_xy ? 1 : 0);
-    // period-tiled loss pass for large launches of 64x48 / 96x72-shaped maps (stages == 1, <= 9 warps)
-    const int qpr = W >> 2;
-    // (opt-in, SP_STEP_TILE=1: measured 123 vs 113 us at 1024 x 64x48 with 8 warps, 111 us with 7; 139 vs 131 us at
-    // 512 x 96x72 -- the step kernel is bound by the memory system and its per-map tail, not by instruction count)
-    if (large && stages == 1 && nwarps <= 9 && (qpr == 12 || qpr == 18) && sp_knob(tune.step_tile, 0) == 1) {
-        const int rows = (qpr == 12) ? sp_trn::Tile<12>::ROWS : sp_trn::Tile<18>::ROWS;
-        const int period = (qpr == 12) ? sp_trn::Tile<12>::PERIOD : sp_trn::Tile<18>::PERIOD;
-        const int ppc = (qpr == 12) ? 2 : 1;
-        const int nq = (H * W) >> 2;
-        if (H % rows == 0 && nq % (32 * period * ppc) == 0) {
-#define SP_LAUNCH_STEP_TILE(Q, P, G, T, AC) \
-    SP_CUDA(sp_launch_smem(step_tile_kernel<Q, P, G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps))
-#define SP_STEP_TILE_SEL(Q, P)                                                  \
-    switch (sel) {                                                              \
-        case 0: SP_LAUNCH_STEP_TILE(Q, P, false, false, false); break;          \
-        case 1: SP_LAUNCH_STEP_TILE(Q, P, false, false, true); break;           \
-        case 2: SP_LAUNCH_STEP_TILE(Q, P, false, true, false); break;           \
-        case 3: SP_LAUNCH_STEP_TILE(Q, P, false, true, true); break;            \
-        case 4: SP_LAUNCH_STEP_TILE(Q, P, true, false, false); break;           \
-        case 5: SP_LAUNCH_STEP_TILE(Q, P, true, false, true); break;            \
-        case 6: SP_LAUNCH_STEP_TILE(Q, P, true, true, false); break;            \
-        default: SP_LAUNCH_STEP_TILE(Q, P, true, true, true); break;            \
-    }
-            if (qpr == 12) { SP_STEP_TILE_SEL(12, 2) } else { SP_STEP_TILE_SEL(18, 1) }
-#undef SP_STEP_TILE_SEL
-#undef SP_LAUNCH_STEP_TILE
-            return 0;
-        }
-    }
 #define SP_LAUNCH_STEP(G, T, AC) \
-    SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps, stages))
+    SP_CUDA(sp_launch_smem(step_kernel<G, T, AC>, dim3(grid), dim3(nwarps * 32), smem, st, A, io, loss, ws, 1.0 / count, nwarps, static_maps))
     switch (sel) {
         case 0: SP_LAUNCH_STEP(false, false, false); break;
         case 1: SP_LAUNCH_STEP(false, false, true); break;

@@ -1112,14 +1112,20 @@ def test_decode_grid_wide_dealing_equals_equal_ranges(api, b, hw, flip):
     tinv = synth.inverse_affines(b, height=h, width=w, seed=91)[0].to(DEV)
     dec = api.metrics.GaussTaylorKeyPointDecoder()
     run = (lambda: dec.flip_call(hm, hf, tinv)) if flip else (lambda: dec(hm, tinv))
-    os.environ["SP_DECODE_GRID_WIDE"] = "1"              # by default only items >= 40 KB are dealt grid-wide
+    os.environ["SP_DECODE_GRID_WIDE"] = "1"              # by default only large launches and items >= 40 KB are dealt grid-wide
     api.abi.reload_tuning()
     try:
         got = [run() for _ in range(6)]
+        for pct in ("0", "40", "85", "100", "300"):        # static interleaved share of a warp's maps, the rest claimed dynamically
+            os.environ["SP_DECODE_STATIC_PCT"] = pct
+            api.abi.reload_tuning()
+            got.append(run())
+        del os.environ["SP_DECODE_STATIC_PCT"]
         os.environ["SP_DECODE_GRID_WIDE"] = "0"
         api.abi.reload_tuning()
         want = run()
     finally:
+        os.environ.pop("SP_DECODE_STATIC_PCT", None)
         del os.environ["SP_DECODE_GRID_WIDE"]
         api.abi.reload_tuning()
     got.append(run())                                    # the default policy

@@ -302,11 +302,12 @@ def test_one_launch_step_equals_the_three_kernels(b, hw):
 
 
 @pytest.mark.parametrize("b,hw", [(520, (64, 48)), (200, (96, 72))])
-@pytest.mark.parametrize("env", [{}, {"SP_STEP_TILE": "1"}, {"SP_STEP_TILE": "1", "SP_STEP_WARPS": "7"}, {"SP_STEP_STAGES": "2"},
-                                 {"SP_STEP_WARPS": "3", "SP_STEP_STAGES": "2"}])
+@pytest.mark.parametrize("env", [{}, {"SP_STEP_STATIC_PCT": "0"}, {"SP_STEP_STATIC_PCT": "100"}, {"SP_STEP_WARPS": "3", "SP_STEP_STATIC_PCT": "30"},
+                                 {"SP_STEP_WARPS": "5"}])
 def test_one_launch_step_large_launch_layouts(b, hw, env):
-    """Launches large enough for the few-warps configuration of sp_step_f32, its two-stage ring and the opt-in
-    period-tiled loss pass: all write the bits of the stand-alone kernels."""
+    """Launches large enough for the few-warps configuration of sp_step_f32 with maps dealt grid-wide (every split
+    between statically assigned and dynamically claimed maps): all write the bits of the stand-alone kernels, every
+    map exactly once, and the work counter is back at zero."""
     from simple_pose_b200 import _abi
     from simple_pose_b200.pipeline import HeatmapHotPath
     h, w = hw
@@ -330,6 +331,7 @@ def test_one_launch_step_large_launch_layouts(b, hw, env):
     eq = lambda x, y: torch.equal(x.nan_to_num(nan=7.5), y.nan_to_num(nan=7.5))
     for key in ("targets", "weights", "grad", "coords", "maxval", "pred_xy", "label_xy"):
         assert eq(getattr(one, key), want[key]), key
+    assert int(one.ws[:2].abs().sum().item()) == 0
 
 
 def test_one_launch_step_vs_oracle_and_graph_replay():
