@@ -190,7 +190,12 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
     // warp (123.5 vs 114.0 us at 1024 x 64x48) and the period-tiled loss pass of the fused training kernel (123 vs 113 us).
     int static_maps = 0;
     if (large || sp_knob(tune.step_static_pct, -1) >= 0) {
-        static_maps = (int)((long long)nmaps * sp_knob(tune.step_static_pct, 80) / 100 / ((long long)grid * nwarps));
+        const long long share = (long long)nmaps / ((long long)grid * nwarps);
+        int pct = sp_knob(tune.step_static_pct, 80);
+        if (pct > 100) pct = 100;
+        long long dynamic = share * (100 - pct) / 100;
+        if (dynamic > 8) dynamic = 8;              // the tail to even out is a few maps per warp whatever the launch size
+        static_maps = (int)(share - dynamic);
         if (static_maps < 1) static_maps = 1;
     }
 

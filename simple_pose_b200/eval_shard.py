@@ -213,6 +213,7 @@ class ShardedPoseEvaluator(object):
         self.transport = transport       # after the first run: the transport in use ('fanout', 'fanout-unicast', 'nccl', 'local')
         self.seg = self.cuts = self.ccuts = None
         self._dev_state = {}
+        self._cur = None
 
     def _world_rank(self):
         if dist.is_available() and dist.is_initialized():
@@ -268,6 +269,123 @@ class ShardedPoseEvaluator(object):
                 st["images"].append(i1 - i0)
             self._dev_state[dev] = st
         return st
+
+    # ---- incremental form: what an eval loop does (reference eval.py:133-149: the backbone emits a batch of heatmaps,
+    # the decoder turns it into keypoints, nothing else is kept). begin() -> add_batch() per batch -> finish().
+    def begin(self, device):
+        """Start a run on ``device``: picks the transport buffer the rows of this run are written into."""
+        if self.ccuts.shape[1] - 1 != 1:
+            raise ValueError("the incremental form needs chunks == 1 (the NCCL transport's chunk pipeline is run()'s)")
+        dev = torch.device(device)
+        st = self._state(dev)
+        symm = None
+        if st["symm"] is not None:
+            symm = st["symm"][st["runs"] & 1]
+            st["runs"] += 1
+        self._cur = {"dev": dev, "st": st, "symm": symm, "buf": symm["buffer"] if symm is not None else st["buffer"],
+                     "area32": False}
+
+    @torch.no_grad()
+    def add_batch(self, start, heat_map, trans_inv=None, boxes=None, heat_map_flip=None, joint_pairs=None,
+                  input_shape=(192, 256)):
+        """Decode persons [start, start + b) of THIS rank's shard (0-based within the shard) straight into their result
+        rows: one launch of ``sp_decode_rows_f32`` (preceded by ``sp_box_affine_f64`` when detection ``boxes`` [b,4]
+        float64 are given instead of ``trans_inv`` [b,2,3]; the box areas are then kept for the NMS)."""
+        from . import _abi
+        cur = self._cur
+        dev, st, buf = cur["dev"], cur["st"], cur["buf"]
+        world, rank = self._world_rank()
+        n = self.counts[rank][0]
+        b = int(heat_map.shape[0])
+        if heat_map.dim() != 4 or heat_map.shape[1] != self.num_joints or start < 0 or start + b > n:
+            raise ValueError("heat_map must be [b, %d, H, W] with persons [start, start + b) inside this rank's %d" % (self.num_joints, n))
+        if b == 0:
+            return
+        _abi.require_cuda(heat_map, heat_map_flip, trans_inv)
+        k, h, w = self.num_joints, int(heat_map.shape[2]), int(heat_map.shape[3])
+        hm = heat_map if (heat_map.dtype == torch.float32 and heat_map.is_contiguous()) else _abi.dense(heat_map, torch.float32)
+        hf = perm = None
+        if heat_map_flip is not None:
+            if tuple(heat_map_flip.shape) != tuple(heat_map.shape):
+                raise ValueError("heat_map_flip must have the shape of heat_map")
+            hf = _abi.dense(heat_map_flip, torch.float32)
+            perm = self.decoder._perm_on(dev, k, joint_pairs)
+        width = buf.shape[-1]
+        lib = _abi.lib()
+        stream = _abi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            if boxes is not None:
+                bx = boxes if (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype == torch.float64
+                               and boxes.is_contiguous()) else _abi.to_device(boxes, torch.float64, dev)
+                if tuple(bx.shape) != (b, 4):
+                    raise ValueError("boxes must be [%d, 4]" % b)
+                if "tinv" not in st:
+                    st["tinv"] = torch.empty((max(n, 1), 2, 3), dtype=torch.float32, device=dev)
+                    st["area"] = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
+                tinv_ptr = st["tinv"].data_ptr() + 24 * start
+                _abi.check(lib.sp_box_affine_f64(bx.data_ptr(), _abi.SP_BOX_XYXY, None, None, st["area"].data_ptr() + 4 * start,
+                                                 tinv_ptr, None, None, b, float(input_shape[0]) / float(input_shape[1]), w, h, 1.25,
+                                                 stream))
+                cur["area32"] = True
+                keep_alive = bx
+            else:
+                ti = _abi.dense(_abi.to_device(trans_inv, torch.float32, dev), torch.float32)
+                if tuple(ti.shape) != (b, 2, 3):
+                    raise ValueError("trans_inv must be [%d, 2, 3]" % b)
+                tinv_ptr = ti.data_ptr()
+                keep_alive = ti
+            blur = self.decoder._weights_on(dev)
+            ws = _abi.scratch(dev, stream, 16, "decode")
+            slot = buf[0, rank]
+            _abi.check_ws(lib.sp_decode_rows_f32(
+                hm.data_ptr(), _abi.ptr(hf), _abi.ptr(perm), tinv_ptr, blur.data_ptr(), slot.data_ptr() + 4 * width * start, width,
+                None, None, b, k, h, w, int(self.decoder.kernel_size), _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
+                stream), dev, stream)
+        cur["keep_alive"] = (keep_alive, hm, hf)       # until the next call: the launches above are asynchronous
+
+    @torch.no_grad()
+    def finish(self, box_scores, areas=None, compact=True):
+        """Rescoring + OKS-NMS of this rank's images on the rows written by ``add_batch`` and the exchange with the other
+        ranks (fan-out from the kernel + barrier, or the in-place NCCL all-gather). ``areas`` [n] are needed unless every
+        batch came with ``boxes``. Returns the table as ``run`` does."""
+        from . import _abi
+        cur = self._cur
+        dev, st, buf, symm = cur["dev"], cur["st"], cur["buf"], cur["symm"]
+        world, rank = self._world_rank()
+        n = self.counts[rank][0]
+        k, width = self.num_joints, buf.shape[-1]
+        lib = _abi.lib()
+        stream = _abi.stream_ptr(dev)
+        handle = None
+        with torch.cuda.device(dev):
+            if n > 0:
+                bs = _abi.to_device(box_scores, torch.float64, dev).reshape(-1)
+                area32 = st["area"] if (cur["area32"] and areas is None) else None
+                area64 = None if area32 is not None else _abi.to_device(areas, torch.float64, dev).reshape(-1)
+                if bs.shape[0] != n or (area64 is not None and area64.shape[0] != n):
+                    raise ValueError("box_scores / areas must describe this rank's %d persons" % n)
+                slot = buf[0, rank]
+                args = (slot.data_ptr(), width, bs.data_ptr(), _abi.ptr(area64), _abi.ptr(area32), st["seg"][0].data_ptr(), None, None,
+                        n, st["images"][0], k, st["max_seg"][0], self.in_vis_thre, self.oks_thre)
+                if symm is None:
+                    _abi.check(lib.sp_eval_rows_nms_f32(*args, stream))
+                else:
+                    # the kernel stores every completed row into the same slot of every rank's buffer (NVLS multicast
+                    # when the fabric offers it, else peer by peer): the all-gather is its epilogue
+                    _abi.check(lib.sp_eval_rows_nms_fanout_f32(*args, symm["multicast"] or None, symm["peer_ptrs_dev"], world, rank,
+                                                               rank * self.chunk_len * width, stream))
+            if world > 1:
+                if symm is not None:
+                    symm["handle"].barrier(channel=0)        # every rank's rows have landed in every rank's buffer
+                else:
+                    handle = gather_chunk(buf[0], rank, self.group, async_op=True)
+        if handle is not None:
+            handle.wait()
+        table = ShardedTable(buf, self.counts)
+        if not compact:
+            return table
+        rows = table.rows()
+        return rows.clone() if rows.data_ptr() == buf.data_ptr() and rows.numel() else rows
 
     @torch.no_grad()
     def run(self, heat_map, trans_inv, box_scores, areas, heat_map_flip=None, joint_pairs=None, boxes=None,

@@ -645,6 +645,38 @@ def test_sharded_evaluator_single_rank_fused_rows(api, chunks, use_boxes, flip):
         ev.run(hm[:-1].to(DEV), tinv[:-1], es.box_scores[:-1], torch.from_numpy(area_np[:-1]).double())
 
 
+def test_sharded_evaluator_incremental_batches(api):
+    """begin / add_batch / finish (the shape of the reference's eval loop, eval.py:133-149: heatmaps arrive batch by
+    batch) returns the table of one run() over all heatmaps, with boxes or with ready-made affines."""
+    from simple_pose_b200 import eval_shard
+    es = synth.EvalSet(persons=700, mean_group=6.0, seed=41)
+    n = es.persons
+    hm = es.heatmaps(0, n, DEV)
+    boxes = es.boxes.to(DEV)
+    ev = eval_shard.ShardedPoseEvaluator(chunks=1)
+    ev.plan(es.seg)
+    want = ev.run(hm, None, es.box_scores, None, boxes=boxes)
+    cuts = [0, 1, 130, 131, 400, n]
+    ev.begin(DEV)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ev.add_batch(a, hm[a:b], boxes=boxes[a:b])
+    ev.add_batch(n, hm[:0], boxes=boxes[:0])                      # an empty last batch is a no-op
+    got = ev.finish(es.box_scores)
+    assert eval_shard.rows_equal(got, want)
+    aff = api.naive.box_affines(boxes)
+    ev.begin(DEV)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ev.add_batch(a, hm[a:b], trans_inv=aff["trans_inv"][a:b])
+    got2 = ev.finish(es.box_scores, areas=aff["area"].double())
+    assert eval_shard.rows_equal(got2, want)
+    with pytest.raises(ValueError):
+        ev.add_batch(n - 3, hm[:5], boxes=boxes[:5])
+    ev3 = eval_shard.ShardedPoseEvaluator(chunks=2)
+    ev3.plan(es.seg)
+    with pytest.raises(ValueError):
+        ev3.begin(DEV)
+
+
 def test_kps_to_dict_on_device(api):
     """A10 (metrics/pose_metrics.py:172-179) with CUDA tensors: one kernel + one D2H; keypoints are the
     decoder's floats exactly, the score mean(conf) + max(conf) agrees with the reference's float32 torch
