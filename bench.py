@@ -319,6 +319,8 @@ def time_ops(device, height, width, persons, batch, peak_gbs, only=None):
     flips = [synth.heatmaps(batch, height=height, width=width, seed=900 + i, noise=0.01, device=device) for i in range(nb)]
     paths = [HeatmapHotPath(batch, 17, height, width, device=device) for _ in range(nb)]
     perm = paths[0].decoder._perm_on(device, 17, None)
+    from simple_pose_b200.commons.transforms import encode_heat_maps_basic
+    input_joints = [torch.cat([s[0][..., :2] * 4.0, s[0][..., 2:]], dim=-1).contiguous() for s in sets]
     ops = {
         "encode": lambda i: paths[i].encode(sets[i][0]),
         "loss": lambda i: paths[i].loss_fwd_bwd(sets[i][1]),
@@ -326,6 +328,8 @@ def time_ops(device, height, width, persons, batch, peak_gbs, only=None):
         "decode": lambda i: paths[i].decode(sets[i][1], sets[i][2]),
         "flip_decode": lambda i: paths[i].decode(sets[i][1], sets[i][2], flips[i], perm),
         "step": lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2]),
+        # BasicSimpleTransform.get_heat_map (the ResNet solvers' quantised 13x13 encoder), joints in input pixels
+        "encode_basic": lambda i: encode_heat_maps_basic(input_joints[i], 2.0, (width, height), 4, out=(paths[i].targets, paths[i].weights)),
     }
     if only is not None:
         ops = {k: v for k, v in ops.items() if k in only}
@@ -344,7 +348,7 @@ def time_ops(device, height, width, persons, batch, peak_gbs, only=None):
             b.synchronize()
             times.append(a.elapsed_time(b) / nb)
         ms = statistics.median(times)
-        bytes_per_launch = ALGO_BYTES[name](17, height, width) * batch
+        bytes_per_launch = ALGO_BYTES["encode" if name == "encode_basic" else name](17, height, width) * batch
         gbs = bytes_per_launch / (ms * 1e-3) / 1e9
         out[name] = {"persons_per_s": batch / (ms * 1e-3), "ms_per_launch": ms, "GBps": gbs, "frac": gbs / peak_gbs,
                      "persons_per_launch": batch}

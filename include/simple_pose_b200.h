@@ -148,7 +148,7 @@ int sp_encode_mse_fwd_bwd(const float* joints, const void* pred, int pred_dtype,
  * shared memory once and read from HBM once.
  *   joints [B,K,3] f32 heatmap px; pred [B,K,H,W] f32; trans_inv [B,2,3] f32 (NULL = heatmap-space coords);
  *   blur_w [121] f32 (ksize must be 11); outputs: targets [B,K,H,W] (NULL = not materialised), weights [B,K]
- *   (NULL ok), grad [B,K,H,W] (NULL = no backward), loss (1 f32), coords [B,K,2], maxval [B,K],
+ *   (NULL ok), grad [B,K,H,W] (NULL = no backward), loss (1 f32), coords [B,K,2], maxval [B,K] (both NULL = no decode pass),
  *   pred_xy / label_xy [B,K,2] (both NULL = skip). Workspace as sp_mse_fwd_bwd_f32.
  * coords / maxval / targets / weights / grad / pred_xy / label_xy are bit-identical to the stand-alone entry points,
  * the loss up to the float64 summation order. W % 4 != 0, ksize != 11 or maps too large for shared memory:

@@ -127,6 +127,17 @@ def masked_mse_loss_and_grad(pred, target, mask):
     return loss.detach(), p.grad.detach()
 
 
+def masked_mse_loss_and_grad_scaled(pred, target, mask, scale=1.0):
+    """The AMP branch, processors/dp_pose_hrnet_solver.py:111-120: ``pred`` is the autocast output (float16 or
+    bfloat16), ``pred.mul(mask)`` promotes to float32 (as it does under autocast; ``mse_loss`` is on autocast's
+    float32 list anyway), the loss is float32, and ``scaler.scale(loss).backward()`` sends ``scale`` as the upstream
+    gradient: d loss / d pred comes back in ``pred``'s dtype, cast once after the scale has been applied in float32."""
+    p = pred.detach().clone().requires_grad_(True)
+    loss = masked_mse_loss(p, target, mask)
+    (loss * scale).backward()
+    return loss.detach(), p.grad.detach()
+
+
 # --------------------------------------------------------------------------- decode
 def argmax_coords(heat_map):
     """``BasicKeyPointDecoder.heat_map_to_axis`` (metrics/pose_metrics.py:11-24).

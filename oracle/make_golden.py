@@ -185,6 +185,51 @@ def negative_step_maps(h=64, w=48, want=17):
     return np.stack(keep)[None]
 
 
+def round2_fixtures(ref):
+    """Round-2 rows: the solvers' loss expression on float16 / bfloat16 predictions with a GradScaler-style upstream
+    gradient (processors/dp_pose_hrnet_solver.py:111-120: the half x float32 product promotes to float32 exactly as under
+    autocast, the gradient comes back in the prediction's dtype), the reference's own ``kps_to_dict_``
+    (metrics/pose_metrics.py:172-179) and ``oks_nms`` on tied scores made explicit by ``oracle.detie_scores``. Written to
+    a file of its own so that the round-1 fixtures stay byte-identical."""
+    from oracle import heatmap_oracle as O
+    out = {}
+    jl = synth.joints(5, height=16, width=12, seed=61).numpy()
+    tl, wl = zip(*[ref.get_heat_map(j, 2.0, (12, 16)) for j in jl])
+    target = torch.from_numpy(np.stack(tl))
+    mask = torch.from_numpy(np.stack(wl))
+    mask[0, 0] = 2.0
+    pred32 = synth.predictions_like(target, seed=62)
+    for name, dtype, scale in (("f16", torch.float16, 65536.0), ("bf16", torch.bfloat16, 1024.0)):
+        pred = pred32.to(dtype).requires_grad_(True)
+        crit = torch.nn.MSELoss()
+        loss = 0.5 * crit(pred.mul(mask[[..., None, None]]), target.mul(mask[[..., None, None]]))
+        (loss * scale).backward()
+        assert pred.grad.dtype == dtype and loss.dtype == torch.float32
+        out["amp_%s_pred_bits" % name] = pred.detach().view(torch.int16).numpy()
+        out["amp_%s_grad_bits" % name] = pred.grad.view(torch.int16).numpy()
+        out["amp_%s_loss" % name] = np.float32(loss.item())
+        out["amp_%s_scale" % name] = np.float32(scale)
+    out["amp_target"], out["amp_mask"] = target.numpy(), mask.numpy()
+    # kps_to_dict_
+    g = torch.Generator().manual_seed(63)
+    coords = torch.randn(11, 17, 2, generator=g) * 100
+    conf = torch.rand(11, 17, 1, generator=g)
+    records = []
+    ref.kps_to_dict_(coords, conf, list(range(700, 711)), records)
+    out["dict_coords"], out["dict_conf"] = coords.numpy(), conf.numpy()
+    out["dict_score"] = np.array([r["score"] for r in records], dtype=np.float64)
+    out["dict_keypoints"] = np.array([r["keypoints"] for r in records], dtype=np.float64)
+    out["dict_image_id"] = np.array([r["image_id"] for r in records], dtype=np.int64)
+    # oks_nms with ties, de-tied "higher index first"
+    kps, _, area, _ = synth.nms_groups(1, mean_group=40.0, seed=64)
+    kps, area = kps.numpy(), area.numpy()
+    tied = np.random.RandomState(65).choice([0.2, 0.4, 0.6], size=kps.shape[0])
+    detied = O.detie_scores(tied)
+    out["tie_kps"], out["tie_area"], out["tie_scores"], out["tie_detied"] = kps, area, tied, detied
+    out["tie_keep"] = np.array([int(i) for i in ref.oks_nms(kps, detied, area, 0.9)], dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "round2.npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(GOLDEN, exist_ok=True)
@@ -320,6 +365,7 @@ def main():
                         basic_hsp=bhsp.numpy(), basic_max=bmax.numpy(), basic_edge_hsp=beimg.numpy(),
                         joints_q=jq, targets_q=np.stack(tq), weights_q=np.stack(wq),
                         acc_pred=prd.numpy(), acc_value=np.float32(float(acc_val)))
+    round2_fixtures(ref)
     total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print("wrote fixtures to", GOLDEN, "(%.1f KB)" % (total / 1024))
 

@@ -52,6 +52,7 @@ for hw in args.hw.split(","):
             "decode": lambda i: paths[i].decode(sets[i][1], sets[i][2]),
             "flip_decode": lambda i: paths[i].decode(sets[i][1], sets[i][2], flips[i], perm),
             "step": lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], sets[i][2]),
+            "step_train": lambda i: paths[i].step_one_launch(sets[i][0], sets[i][1], None, want_targets=False, with_acc=True, want_decode=False),
         }
         for i in range(nb):
             paths[i].encode(sets[i][0])      # targets for the loss
@@ -78,7 +79,7 @@ for hw in args.hw.split(","):
                     times.append(a.elapsed_time(b) / nb)
                 ms = statistics.median(times)
                 best = min(times)
-                by = ALGO_BYTES[name](17, H, W) * batch
+                by = ALGO_BYTES[{'step_train': 'train_fused'}.get(name, name)](17, H, W) * batch
                 gbs = by / (ms * 1e-3) / 1e9
                 print("%-12s %dx%d B=%-6d nb=%-2d env=[%s]  %8.2f us (best %8.2f)  %7.1f GB/s  frac %.3f" %
                       (name, H, W, batch, nb, env, ms * 1e3, best * 1e3, gbs, gbs / args.peak), flush=True)

@@ -157,7 +157,7 @@ def basic_gaussian_table(sigma=2.0):
 _table_cache = {}
 
 
-def encode_heat_maps_basic(joints, sigma=2.0, shape=(48, 64), stride=4):
+def encode_heat_maps_basic(joints, sigma=2.0, shape=(48, 64), stride=4, out=None):
     """Batched ``BasicSimpleTransform.get_heat_map``: joints [B,K,3] in INPUT pixels ->
     (targets [B,K,H,W] float32, weights [B,K] float32) on the CUDA device."""
     j = _abi.to_device(joints, torch.float32)
@@ -171,8 +171,16 @@ def encode_heat_maps_basic(joints, sigma=2.0, shape=(48, 64), stride=4):
     if table is None:
         table = torch.from_numpy(basic_gaussian_table(sigma)).to(dev)
         _table_cache[key] = table
-    targets = torch.empty((b, k, height, width), dtype=torch.float32, device=dev)
-    weights = torch.empty((b, k), dtype=torch.float32, device=dev)
+    if out is None:
+        targets = torch.empty((b, k, height, width), dtype=torch.float32, device=dev)
+        weights = torch.empty((b, k), dtype=torch.float32, device=dev)
+    else:
+        targets, weights = out
+        _abi.require_cuda(j, targets, weights)
+        if tuple(targets.shape) != (b, k, height, width) or tuple(weights.shape) != (b, k) \
+                or targets.dtype != torch.float32 or weights.dtype != torch.float32 \
+                or not targets.is_contiguous() or not weights.is_contiguous():
+            raise ValueError("out buffers have the wrong shape/dtype/layout")
     with torch.cuda.device(dev):
         _abi.check(_abi.lib().sp_encode_basic_f32(j.data_ptr(), table.data_ptr(), targets.data_ptr(), weights.data_ptr(),
                                                   b, k, height, width, float(sigma), int(stride), int(table.shape[0]),

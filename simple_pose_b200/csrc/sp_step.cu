@@ -125,7 +125,7 @@ step_kernel(const sp_dec::DecodeArgs A, const sp_trn::MapIo io, float* __restric
                                                                         ex, ey, st, lane, io.half_scale);
                 if (ACC) sp_trn::end_map_acc(io, m, jv, ex, ey, st, lane);
                 sum_sq += (double)st.acc;
-            } else {
+            } else if (A.coords != nullptr) {
                 // ---- decode (argmax on the raw map, blur at the 13 stencil points, Taylor step, affine)
                 const sp_dec::Peak pk = sp_dec::argmax_smem<false>(a, a, hw, A.W, lane);
                 sp_dec::DirectView view{a};
@@ -150,14 +150,15 @@ extern "C" int sp_step_f32(const float* joints, const float* pred, const float* 
                            float* targets, float* weights, float* grad, float* loss, float* coords, float* maxval,
                            float* pred_xy, float* label_xy, void* workspace, size_t workspace_bytes,
                            int B, int K, int H, int W, double sigma, int ksize, float grad_scale, void* stream) {
-    SP_RETURN_IF(!joints || !pred || !blur_w || !loss || !coords || !maxval || !workspace, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF(!joints || !pred || !blur_w || !loss || !workspace, SP_ERR_BAD_ARGUMENT);
+    SP_RETURN_IF((coords == nullptr) != (maxval == nullptr), SP_ERR_BAD_ARGUMENT);      // both NULL: no decode pass
     SP_RETURN_IF(B <= 0 || K <= 0 || H <= 0 || W <= 0 || !(sigma > 0.0), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF((pred_xy == nullptr) != (label_xy == nullptr), SP_ERR_BAD_ARGUMENT);
     SP_RETURN_IF((long long)B * K > 0x7fffffffLL || (long long)H * W > (1 << 24), SP_ERR_UNSUPPORTED);
     SP_RETURN_IF(W % 4 != 0 || ksize != 11, SP_ERR_UNSUPPORTED);      // callers compose the stand-alone kernels instead
     SP_RETURN_IF(workspace_bytes < sizeof(MseWorkspace), SP_ERR_WORKSPACE);
     SP_RETURN_IF(!sp_aligned16(workspace) || !sp_aligned16(pred) || (grad && !sp_aligned16(grad)) || (targets && !sp_aligned16(targets)) ||
-                 !sp_aligned16(coords) || (pred_xy && (!sp_aligned16(pred_xy) || !sp_aligned16(label_xy))), SP_ERR_BAD_ALIGNMENT);
+                 (coords && !sp_aligned16(coords)) || (pred_xy && (!sp_aligned16(pred_xy) || !sp_aligned16(label_xy))), SP_ERR_BAD_ALIGNMENT);
     const int nmaps = B * K;
     const size_t map_bytes = (size_t)H * W * 4;
     const int wpad = (W + 1) & ~1;

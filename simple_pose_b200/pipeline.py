@@ -113,7 +113,7 @@ class HeatmapHotPath(object):
                                                      self.ksize, _abi.SP_DECODE_GAUSS_TAYLOR, ws.data_ptr(), ws.numel() * 8,
                                                      stream), self.device, stream, self)
 
-    def step_one_launch(self, joints, pred, trans_inv, want_targets=True, want_grad=True, with_acc=False):
+    def step_one_launch(self, joints, pred, trans_inv, want_targets=True, want_grad=True, with_acc=False, want_decode=True):
         """encode + loss fwd/bwd (+ HeatMapAcc argmaxes) + GaussTaylor decode of ``pred`` in ONE launch
         (``sp_step_f32``): every map is staged in shared memory once, pred is read from HBM once and the
         targets are written but not read back. Same outputs as ``step`` (loss up to summation order)."""
@@ -130,8 +130,9 @@ class HeatmapHotPath(object):
             _abi.check_ws(self._lib.sp_step_f32(
                 joints.data_ptr(), pred.data_ptr(), _abi.ptr(trans_inv), self.blur_w.data_ptr(),
                 self.targets.data_ptr() if want_targets else None, self.weights.data_ptr(),
-                self.grad.data_ptr() if want_grad else None, self.loss.data_ptr(), self.coords.data_ptr(),
-                self.maxval.data_ptr(), _abi.ptr(self.pred_xy) if with_acc else None,
+                self.grad.data_ptr() if want_grad else None, self.loss.data_ptr(),
+                self.coords.data_ptr() if want_decode else None, self.maxval.data_ptr() if want_decode else None,
+                _abi.ptr(self.pred_xy) if with_acc else None,
                 _abi.ptr(self.label_xy) if with_acc else None, ws.data_ptr(), ws.numel() * 8,
                 self.batch, self.k, self.h, self.w, self.sigma, self.ksize, 1.0, stream), self.device, stream, self)
         return self.loss, self.coords, self.maxval

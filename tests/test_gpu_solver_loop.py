@@ -18,14 +18,9 @@ DEV = "cuda:0"
 
 
 def reference_loss_and_grad(pred, target, mask, scale=1.0):
-    """The solvers' expression on host tensors, differentiated by torch autograd; ``pred`` may be
-    float16 / bfloat16 (then the product promotes to float32 exactly as under autocast and the gradient comes
-    back in pred's dtype)."""
-    p = pred.detach().clone().requires_grad_(True)
-    m = mask[..., None, None]
-    loss = 0.5 * torch.nn.MSELoss()(p.mul(m), target.mul(m))
-    (loss * scale).backward()
-    return loss.detach(), p.grad
+    """The solvers' expression on host tensors (oracle restatement of dp_pose_hrnet_solver.py:106-107 / :111-120),
+    differentiated by torch autograd; ``pred`` may be float16 / bfloat16."""
+    return O.masked_mse_loss_and_grad_scaled(pred, target, mask, scale)
 
 
 def half_ulp_distance(a, b):
@@ -78,6 +73,31 @@ def test_loss_native_half_precision_pred(dtype, b, hw, scale):
     none, g = mse_forward_backward(pred.to(DEV), tgt.to(DEV), msk.to(DEV), need_loss=False,
                                    grad_scale_dev=torch.tensor(scale, device=DEV))
     assert none is None and torch.equal(g, p.grad)
+
+
+def test_round2_golden_fixtures(golden):
+    """The CUDA path against outputs of the reference itself frozen in tests/golden/round2.npz: float16 / bfloat16 loss and
+    gradient (the solvers' AMP expression), kps_to_dict_, NMS with tied scores de-tied by the documented rule."""
+    from simple_pose_b200.datasets.naive_data import oks_nms
+    from simple_pose_b200.metrics.pose_metrics import kps_to_dict_
+    from simple_pose_b200.processors.loss import JointsMSELoss
+    g = golden("round2")
+    target, mask = torch.from_numpy(g["amp_target"]).to(DEV), torch.from_numpy(g["amp_mask"]).to(DEV)
+    for name, dtype in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        p = torch.from_numpy(g["amp_%s_pred_bits" % name]).view(dtype).to(DEV).requires_grad_(True)
+        loss = JointsMSELoss()(p, target, mask)
+        (loss * float(g["amp_%s_scale" % name])).backward()
+        want_loss = float(g["amp_%s_loss" % name])
+        assert abs(loss.item() - want_loss) <= 1e-5 * abs(want_loss)
+        want = torch.from_numpy(g["amp_%s_grad_bits" % name]).view(dtype)
+        d = half_ulp_distance(p.grad.cpu(), want)
+        assert p.grad.dtype == dtype and int(d.max()) <= 1 and float((d != 0).float().mean()) < 1e-3
+    out = []
+    kps_to_dict_(torch.from_numpy(g["dict_coords"]).to(DEV), torch.from_numpy(g["dict_conf"]).to(DEV), g["dict_image_id"].tolist(), out)
+    assert [r["keypoints"] for r in out] == g["dict_keypoints"].tolist()
+    assert [r["image_id"] for r in out] == g["dict_image_id"].tolist()
+    assert np.allclose([r["score"] for r in out], g["dict_score"], rtol=2.4e-7, atol=0)
+    assert oks_nms(g["tie_kps"], g["tie_scores"], g["tie_area"], 0.9) == g["tie_keep"].tolist()
 
 
 def test_float32_loss_node_is_single_use_unless_deferred():
