@@ -932,7 +932,7 @@ def run_e2e(args, device, world, rank, P, B, H, W):
     h2d = P * (17 * 3 * 4 + 17 * H * W * 4 + 24)
     d2h = P * 17 * 3 * 4 + nb * 4
     return {"value": world * P * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "h2d_GBps_per_gpu": h2d * steps / dt / 1e9,
             "note": "public API (encode_heat_maps, JointsMSELoss+backward, GaussTaylorKeyPointDecoder) on pinned host "
                     "inputs incl. the predicted heatmaps; PCIe-bound"}
 
