@@ -5,18 +5,21 @@
     python bench.py --impl reference [...]                        # the reference's CPU algorithm
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N  # one rank per GPU (N > 1)
 
-A step = one pass of the hot path over PERSONS persons per GPU (K = 17, 64x48 float32 maps):
-encode (joints -> targets, weights), masked-MSE forward+backward (pred, targets, weights ->
-loss, grad) and GaussTaylor decode (pred, trans_inv -> keypoints, scores), issued as BATCH-sized
-launches over distinct buffers (working set >> the 126 MB L2, so every launch streams from HBM).
-With N > 1 every rank does the same amount of work on its own persons (weak scaling) and the
-decoded keypoints are all-gathered over NCCL inside the step.
+A step = DarkPose target encoding (joints -> targets, weights), masked-MSE forward+backward (pred, targets, weights ->
+loss, grad) and GaussTaylor decode (pred, trans_inv -> keypoints, scores) of the same predicted heatmaps (K = 17, 64x48
+float32), issued as BATCH-sized launches of the one-launch step kernel (sp_step_f32) over distinct buffer sets (working
+set >> the 126 MB L2, so every launch streams from HBM); ceil(500 / --steps) passes over the buffer sets make one step, so
+that the timed region lasts about half a second whatever --steps is. With N > 1 every rank does the same amount of work
+on its own persons (weak scaling) and the decoded keypoints of a step are all-gathered over NCCL (double-buffered,
+overlapped with the next step).
 
-Prints ONE JSON line (rank 0). `value` = persons/s with inputs resident in HBM; `e2e` = the same
-path fed from pinned host buffers through the public Python API (H2D of joints, predicted
-heatmaps and affines, D2H of loss and keypoints, all inside the timed region); `roofline` = the
-dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the oracle (a CPU
-restatement of the reference's algorithm, pinned bit-exact to it) timed on this box's host.
+Prints ONE JSON line (rank 0). `value` = persons/s with inputs resident in HBM; `e2e` = the same path fed from pinned
+host buffers through the public Python API (H2D of joints, predicted heatmaps and affines, D2H of loss and keypoints,
+all inside the timed region; `e2e_device_heatmaps` = the same with the heatmaps resident, as a backbone leaves them);
+`roofline` = the step kernel against the measured HBM copy bandwidth; `ops` / `small_batch` = every kernel at 64x48 and
+96x72 and at the reference's literal batch sizes; `eval_job` = BASELINE config 5 through the sharded evaluator with a
+bit-for-bit check against a single-device recompute; `cpu_baseline` = the oracle (a CPU restatement of the reference's
+algorithm, pinned bit-exact to it) timed on this box's host. Both arms print the same `config`.
 """
 import argparse
 import json

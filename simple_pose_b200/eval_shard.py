@@ -162,10 +162,14 @@ def _symmetric_buffer(shape, device, group, required=False):
         if os.environ.get("SP_EVAL_NO_MULTICAST"):
             multicast = 0
         return {"buffer": buf, "handle": handle, "peer_ptrs_dev": int(handle.buffer_ptrs_dev), "multicast": multicast}
-    except Exception:
+    except Exception as exc:
         if required:
             raise
+        _symmetric_buffer.last_error = "%s: %s" % (type(exc).__name__, exc)      # why the NCCL transport was taken instead
         return None
+
+
+_symmetric_buffer.last_error = None
 
 
 class ShardedTable(object):

@@ -99,6 +99,24 @@ def test_argument_errors_without_gpu(lib):
     assert lib.sp_person_rows_f32(None, 16, 16, 1, 17, None) == -1
     assert lib.sp_person_rows_f32(None, None, None, 0, 17, None) == 0
     assert lib.sp_reload_tuning() == 0
+    # one-launch step, autocast-dtype loss, fan-out NMS: argument errors are caught before any CUDA call
+    step_ok = [16, 16, 16, 16, 16, 16, 16, 16, 16, 16, None, None, 16, 1 << 16, 1, 17, 64, 48, 2.0, 11, 1.0, None]
+    assert lib.sp_step_f32(*([None] + step_ok[1:])) == -1                                     # no joints
+    assert lib.sp_step_f32(*(step_ok[:8] + [16, None] + step_ok[10:])) == -1                  # coords without maxval
+    assert lib.sp_step_f32(*(step_ok[:10] + [16, None] + step_ok[12:])) == -1                 # pred_xy without label_xy
+    assert lib.sp_step_f32(*(step_ok[:17] + [50] + step_ok[18:])) == -4                       # W % 4 != 0
+    assert lib.sp_step_f32(*(step_ok[:19] + [9] + step_ok[20:])) == -4                        # only the 11 x 11 blur
+    assert lib.sp_step_f32(*(step_ok[:13] + [8] + step_ok[14:])) == -3                        # workspace too small
+    assert lib.sp_step_f32(*(step_ok[:1] + [24] + step_ok[2:])) == -2                         # misaligned pred
+    assert lib.sp_mse_fwd_bwd(16, 7, 16, 16, 16, 16, 16, 1 << 16, 1, 17, 3072, 1.0, None, 0, None) == -1      # unknown dtype
+    assert lib.sp_mse_fwd_bwd(16, 1, 16, 16, None, None, 16, 1 << 16, 1, 17, 3072, 1.0, None, 0, None) == -1  # nothing to compute
+    assert lib.sp_mse_fwd_bwd(16, 1, 16, 16, 16, 16, 16, 8, 1, 17, 3072, 1.0, None, 0, None) == -3            # workspace too small
+    assert lib.sp_encode_mse_fwd_bwd(16, 16, 9, 16, None, 16, 16, None, None, 16, 1 << 16, 1, 17, 64, 48, 2.0, 1.0, None, None) == -1
+    fan = [16, 54, 16, 16, None, 16, None, None, 4, 1, 17, 4, 0.2, 0.9]
+    assert lib.sp_eval_rows_nms_fanout_f32(*(fan + [None, None, 2, 0, 0, None])) == -1        # world 2 without any peer mapping
+    assert lib.sp_eval_rows_nms_fanout_f32(*(fan + [16, None, 2, 2, 0, None])) == -1          # rank outside the world
+    assert lib.sp_eval_rows_nms_fanout_f32(*(fan + [16, None, 2, 0, 7, None])) == -2          # odd slot offset: rows must stay 8-byte aligned
+    assert lib.sp_eval_rows_nms_fanout_f32(*([16, 55] + fan[2:] + [16, None, 2, 0, 0, None])) == -2   # odd row stride
     # empty batches are a no-op success
     assert lib.sp_encode_f32(None, None, None, 0, 17, 64, 48, 2.0, None) == 0
     assert lib.sp_decode_f32(16, None, None, None, 16, 16, 16, None, 0, 17, 64, 48, 11, 0, None) == 0
