@@ -302,7 +302,7 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
         const int need = (A.nmaps + nwarps - 1) / nwarps;
         if (grid > need) grid = need;
         // Work distribution (needs the caller's workspace, sp_decode_ws_f32 / sp_decode_rows_f32):
-        //  * launches of >= 4 maps per warp slot: maps dealt GRID-WIDE, 85 % of a warp's share interleaved statically
+        //  * launches of 4 ... 256 maps per warp slot: maps dealt GRID-WIDE, 85 % of a warp's share interleaved statically
         //    (no atomic), the tail claimed from the workspace counter one map ahead. Against equal per-CTA ranges:
         //    1024 x 64x48 36.3 -> 36.0 us, flip 67.8 -> 66.4 us (0.986 of the HBM peak); 4096 x 64x48 130.7 -> 127.2 us;
         //    512 x 96x72 40.1 -> 39.5 us, flip 83.3 -> 80.8 us. Without the static share every map costs a global atomic
@@ -313,7 +313,10 @@ static int decode_launch(const float* hm, const float* hm_flip, const int* perm,
         int static_pct = 0;
         {
             const int force = sp_knob(tune.decode_grid_wide, -1);
-            const bool large = (long long)A.nmaps >= 4LL * nwarps * sp_sm_count();
+            // ... and <= 256 maps per warp slot: the 104 k-person decode of cfg 5 (852 maps per slot) measured 3.09 ms
+            // dealt grid-wide against 3.01 ms with contiguous per-CTA ranges, an eighth of it 0.377 against 0.387 ms
+            const long long slots = (long long)nwarps * sp_sm_count();
+            const bool large = (long long)A.nmaps >= 4LL * slots && (long long)A.nmaps <= 256LL * slots;
             if (force == 0 || (force < 0 && !large && stage_bytes < 40 * 1024)) A.work = nullptr;
             if (large) static_pct = 85;
             static_pct = sp_knob(tune.decode_static_pct, static_pct);
