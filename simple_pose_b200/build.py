@@ -34,9 +34,10 @@ def _fingerprint():
     h = hashlib.sha256()
     files = _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
         [os.path.join(os.path.dirname(PKG), "include", "simple_pose_b200.h")]
+    root = os.path.dirname(PKG)
     for f in files:
-        with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+        with open(f, "rb") as fh:       # path relative to the checkout: the same sources hash the same wherever the tree lives
+            h.update(os.path.relpath(f, root).encode() + b"\0" + fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

@@ -39,3 +39,20 @@ def test_product_arm_needs_cuda():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
     assert not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_source_fingerprint_does_not_depend_on_where_the_tree_lives(tmp_path, monkeypatch):
+    """bench.py trusts profiles/*_traffic.json only when its fingerprint equals the one of the sources in use; the GPU box
+    runs from a scratch path, so the hash must cover relative names and contents, not absolute paths."""
+    import shutil
+    from simple_pose_b200 import build
+    here = build._fingerprint()
+    root = tmp_path / "elsewhere"
+    shutil.copytree(build.CSRC, root / "simple_pose_b200" / "csrc")
+    shutil.copytree(os.path.join(os.path.dirname(build.PKG), "include"), root / "include")
+    monkeypatch.setattr(build, "PKG", str(root / "simple_pose_b200"))
+    monkeypatch.setattr(build, "CSRC", str(root / "simple_pose_b200" / "csrc"))
+    assert build._fingerprint() == here
+    with open(root / "simple_pose_b200" / "csrc" / "sp_step.cu", "a") as fh:
+        fh.write("// changed\n")
+    assert build._fingerprint() != here
