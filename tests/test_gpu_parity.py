@@ -1308,3 +1308,39 @@ def test_train_geometry_drop_ins_and_edges(api):
     assert lib.sp_train_geometry_f32(d.data_ptr(), None, f.data_ptr(), None, None, u8.data_ptr(), None, f.data_ptr(), None,
                                      None, None, None, None, None, 1, 1, 192, 256, 48, 64, 1.25, None) == -1
     assert lib.sp_transform_joints_f32(f.data_ptr(), None, None, None, None, f.data_ptr(), 1, 1, None) == -1
+
+
+# ------------------------------------------------------------------------------------ entry points without a Python caller
+def test_center_scale_affine_entry_point_and_device_info(api, golden):
+    """sp_center_scale_affine_f64 (get_affine_transform with rot = 0 for given centre/scale pairs) is what a host that already
+    holds centres and scales binds; the Python mirror goes through the rotation entry point, so this one is called directly:
+    float64 matrices bit-identical to the reference fixtures, the float32 inverse = the float64 one rounded once.
+    sp_device_info must describe the device the kernels were built for."""
+    import ctypes
+    g = golden("affine")
+    lib = api.abi.lib()
+    for tag, outp in (("a", (48, 64)), ("b", (72, 96))):
+        c = torch.from_numpy(g["center_" + tag]).to(DEV).contiguous()
+        s = torch.from_numpy(g["scale_" + tag]).to(DEV).contiguous()
+        n = int(c.shape[0])
+        inv32 = torch.empty((n, 2, 3), dtype=torch.float32, device=DEV)
+        inv64 = torch.empty((n, 2, 3), dtype=torch.float64, device=DEV)
+        fwd64 = torch.empty((n, 2, 3), dtype=torch.float64, device=DEV)
+        with torch.cuda.device(DEV):
+            api.abi.check(lib.sp_center_scale_affine_f64(c.data_ptr(), s.data_ptr(), inv32.data_ptr(), inv64.data_ptr(),
+                                                        fwd64.data_ptr(), n, outp[0], outp[1], api.abi.stream_ptr(c.device)))
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(fwd64.cpu().numpy()), bits(g["fwd64_" + tag])), tag
+        assert np.array_equal(bits(inv64.cpu().numpy()), bits(g["tinv64_" + tag])), tag
+        assert np.array_equal(bits(inv32.cpu().numpy()), bits(g["tinv_" + tag])), tag
+        only = torch.empty((n, 2, 3), dtype=torch.float32, device=DEV)         # any subset of the outputs
+        with torch.cuda.device(DEV):
+            api.abi.check(lib.sp_center_scale_affine_f64(c.data_ptr(), s.data_ptr(), only.data_ptr(), None, None, n,
+                                                        outp[0], outp[1], api.abi.stream_ptr(c.device)))
+        assert torch.equal(only, inv32)
+    assert lib.sp_center_scale_affine_f64(c.data_ptr(), s.data_ptr(), None, None, None, n, 48, 64, None) != 0      # no output asked for
+    info = api.abi.device_info()
+    props = torch.cuda.get_device_properties(0)
+    assert info["sm_count"] == props.multi_processor_count and info["cc"] == (props.major, props.minor) == (10, 0)
+    sm = ctypes.c_int()
+    assert lib.sp_device_info(ctypes.byref(sm), None, None) == 0 and sm.value == info["sm_count"]      # outputs are optional
