@@ -873,7 +873,10 @@ def run_e2e(args, device, world, rank, P, B, H, W):
         h_joints[i * B:(i + 1) * B].copy_(synth.joints(B, height=H, width=W, seed=s, device=device))
         h_pred[i * B:(i + 1) * B].copy_(synth.heatmaps(B, height=H, width=W, seed=s, device=device))
         h_tinv[i * B:(i + 1) * B].copy_(synth.inverse_affines(B, height=H, width=W, seed=s, device=device)[0])
-    h_kp = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    # contiguous destinations: a device -> host copy into a strided slice goes through a staging tensor and a host-side
+    # copy that waits for the stream, which would serialise the batches
+    h_xy = torch.empty((P, 17, 2), dtype=torch.float32).pin_memory()
+    h_conf = torch.empty((P, 17, 1), dtype=torch.float32).pin_memory()
     h_loss = torch.empty((nb,), dtype=torch.float32).pin_memory()
     torch.cuda.synchronize(device)
 
@@ -908,8 +911,8 @@ def run_e2e(args, device, world, rank, P, B, H, W):
             xy, conf = dec(pred.detach(), s["t"])
             pred.grad = None
             s["p"].requires_grad_(False)
-            h_kp[i * B:(i + 1) * B, :, :2].copy_(xy, non_blocking=True)
-            h_kp[i * B:(i + 1) * B, :, 2:].copy_(conf, non_blocking=True)
+            h_xy[i * B:(i + 1) * B].copy_(xy, non_blocking=True)
+            h_conf[i * B:(i + 1) * B].copy_(conf.reshape(B, 17, 1), non_blocking=True)
             h_loss[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
             s["free"].record(compute)
         torch.cuda.synchronize(device)
@@ -952,7 +955,8 @@ def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
     for i in range(nb):
         h_joints[i * B:(i + 1) * B].copy_(sets[i][0])
         h_tinv[i * B:(i + 1) * B].copy_(sets[i][2])
-    h_kp = torch.empty((P, 17, 3), dtype=torch.float32).pin_memory()
+    h_xy = torch.empty((P, 17, 2), dtype=torch.float32).pin_memory()         # contiguous destinations, see run_e2e
+    h_conf = torch.empty((P, 17, 1), dtype=torch.float32).pin_memory()
     h_loss = torch.empty((nb,), dtype=torch.float32).pin_memory()
     hp = [HeatmapHotPath(B, 17, H, W, device=device) for _ in range(2)]          # double-buffered outputs
     d_joints = [torch.empty((B, 17, 3), device=device) for _ in range(2)]
@@ -965,8 +969,8 @@ def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
             d_joints[s].copy_(h_joints[i * B:(i + 1) * B], non_blocking=True)
             d_tinv[s].copy_(h_tinv[i * B:(i + 1) * B], non_blocking=True)
             loss, xy, conf = hp[s].step(d_joints[s], sets[i][1], d_tinv[s])
-            h_kp[i * B:(i + 1) * B, :, :2].copy_(xy, non_blocking=True)
-            h_kp[i * B:(i + 1) * B, :, 2:].copy_(conf, non_blocking=True)
+            h_xy[i * B:(i + 1) * B].copy_(xy, non_blocking=True)
+            h_conf[i * B:(i + 1) * B].copy_(conf.reshape(B, 17, 1), non_blocking=True)
             h_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.synchronize(device)
         return float(h_loss.sum())
