@@ -963,15 +963,42 @@ def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
     d_tinv = [torch.empty((B, 2, 3), device=device) for _ in range(2)]
     torch.cuda.synchronize(device)
 
-    def step():
-        for i in range(nb):
-            s = i & 1
+    replays = None
+    # three streams, two slots: the upload of batch i+1 and the read-back of batch i-1 run beside the kernel of batch i
+    compute = torch.cuda.current_stream(device)
+    up, down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    ev_in = [torch.cuda.Event() for _ in range(2)]        # slot's inputs are on the device
+    ev_done = [torch.cuda.Event() for _ in range(2)]      # slot's kernel has finished: inputs reusable, outputs readable
+    ev_out = [torch.cuda.Event() for _ in range(2)]       # slot's outputs are on the host: outputs reusable
+
+    def upload(i):
+        s = i & 1
+        with torch.cuda.stream(up):
+            up.wait_event(ev_done[s])
             d_joints[s].copy_(h_joints[i * B:(i + 1) * B], non_blocking=True)
             d_tinv[s].copy_(h_tinv[i * B:(i + 1) * B], non_blocking=True)
-            loss, xy, conf = hp[s].step(d_joints[s], sets[i][1], d_tinv[s])
-            h_xy[i * B:(i + 1) * B].copy_(xy, non_blocking=True)
-            h_conf[i * B:(i + 1) * B].copy_(conf.reshape(B, 17, 1), non_blocking=True)
-            h_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+            ev_in[s].record(up)
+
+    def step():
+        upload(0)
+        for i in range(nb):
+            s = i & 1
+            if i + 1 < nb:
+                upload(i + 1)
+            compute.wait_event(ev_in[s])
+            compute.wait_event(ev_out[s])
+            if replays is None:
+                loss, xy, conf = hp[s].step(d_joints[s], sets[i][1], d_tinv[s])
+            else:                                   # the same step replayed from the graph HeatmapHotPath.capture made
+                replays[i]()
+                loss, xy, conf = hp[s].loss, hp[s].coords, hp[s].maxval
+            ev_done[s].record(compute)
+            with torch.cuda.stream(down):
+                down.wait_event(ev_done[s])
+                h_xy[i * B:(i + 1) * B].copy_(xy, non_blocking=True)
+                h_conf[i * B:(i + 1) * B].copy_(conf.reshape(B, 17, 1), non_blocking=True)
+                h_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+                ev_out[s].record(down)
         torch.cuda.synchronize(device)
         return float(h_loss.sum())
 
@@ -985,15 +1012,32 @@ def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
+    check_eager = (float(h_loss.sum()), h_xy.clone(), h_conf.clone())
+    # the same loop with the per-batch step replayed from a captured graph (one graph per input buffer set)
+    replays = [hp[i & 1].capture(d_joints[i & 1], sets[i][1], d_tinv[i & 1]) for i in range(nb)]
+    for _ in range(2):
+        step()
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt_graph = time.perf_counter() - t0
+    # keypoints bit-identical; the loss to its float64 summation order (maps of the dynamic tail go to whichever warp asks first)
+    same = abs(float(h_loss.sum()) - check_eager[0]) <= 1e-6 * abs(check_eager[0]) and torch.equal(h_xy, check_eager[1]) \
+        and torch.equal(h_conf, check_eager[2])
+    if world > 1:
+        t = torch.tensor([dt, dt_graph], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt, dt_graph = float(t[0].item()), float(t[1].item())
     return {"value": world * P * steps / dt, "unit": UNIT, "h2d_bytes_per_step": P * (17 * 3 * 4 + 24),
             "d2h_bytes_per_step": P * 17 * 3 * 4 + nb * 4, "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "persons_per_step": P,
+            "persons_per_step": P, "graph_replay_value": world * P * steps / dt_graph,
+            "graph_replay_ms_per_step": 1e3 * dt_graph / steps, "graph_replay_same_results": bool(same),
             "note": "joints + affines H2D from pinned memory, heatmaps resident on the device (backbone output), loss + keypoints "
-                    "D2H; HeatmapHotPath.step per batch, host wall clock incl. the final synchronize"}
+                    "D2H; HeatmapHotPath.step per batch (upload, kernel and read-back on three streams, two slots), host wall clock incl. "
+                    "the final synchronize; graph_replay_* = the same loop with the step replayed from HeatmapHotPath.capture's graph"}
 
 
 def main():
