@@ -1013,28 +1013,40 @@ def run_e2e_device_heatmaps(args, device, world, rank, P, B, H, W, sets):
         step()
     dt = time.perf_counter() - t0
     check_eager = (float(h_loss.sum()), h_xy.clone(), h_conf.clone())
-    # the same loop with the per-batch step replayed from a captured graph (one graph per input buffer set)
-    replays = [hp[i & 1].capture(d_joints[i & 1], sets[i][1], d_tinv[i & 1]) for i in range(nb)]
-    for _ in range(2):
-        step()
+    # the same loop with the per-batch step replayed from a captured graph (one graph per input buffer set). An extra, not the
+    # leg's number: if the capture fails on a box, say so and keep the collectives of the ranks matched
+    dt_graph = same = graph_error = None
+    try:
+        replays = [hp[i & 1].capture(d_joints[i & 1], sets[i][1], d_tinv[i & 1]) for i in range(nb)]
+        for _ in range(2):
+            step()
+    except RuntimeError as exc:
+        graph_error, replays = repr(exc)[:200], None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(device)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt_graph = time.perf_counter() - t0
-    # keypoints bit-identical; the loss to its float64 summation order (maps of the dynamic tail go to whichever warp asks first)
-    same = abs(float(h_loss.sum()) - check_eager[0]) <= 1e-6 * abs(check_eager[0]) and torch.equal(h_xy, check_eager[1]) \
-        and torch.equal(h_conf, check_eager[2])
+    if graph_error is None:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt_graph = time.perf_counter() - t0
+        # keypoints bit-identical; the loss to its float64 summation order (maps of the dynamic tail go to whichever warp asks first)
+        same = abs(float(h_loss.sum()) - check_eager[0]) <= 1e-6 * abs(check_eager[0]) and torch.equal(h_xy, check_eager[1]) \
+            and torch.equal(h_conf, check_eager[2])
     if world > 1:
-        t = torch.tensor([dt, dt_graph], dtype=torch.float64, device=device)
+        t = torch.tensor([dt, dt_graph or 0.0, 0.0 if graph_error is None else 1.0, 0.0 if same else 1.0],
+                         dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_graph = float(t[0].item()), float(t[1].item())
+        dt = float(t[0].item())
+        if float(t[2].item()) > 0.0:                 # some rank could not capture
+            dt_graph, graph_error = None, graph_error or "graph capture failed on another rank"
+        else:
+            dt_graph, same = float(t[1].item()), float(t[3].item()) == 0.0
     return {"value": world * P * steps / dt, "unit": UNIT, "h2d_bytes_per_step": P * (17 * 3 * 4 + 24),
             "d2h_bytes_per_step": P * 17 * 3 * 4 + nb * 4, "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "persons_per_step": P, "graph_replay_value": world * P * steps / dt_graph,
-            "graph_replay_ms_per_step": 1e3 * dt_graph / steps, "graph_replay_same_results": bool(same),
+            "persons_per_step": P, "graph_replay_value": (world * P * steps / dt_graph) if dt_graph else None,
+            "graph_replay_ms_per_step": (1e3 * dt_graph / steps) if dt_graph else None,
+            "graph_replay_same_results": bool(same) if dt_graph else None, "graph_replay_error": graph_error,
             "note": "joints + affines H2D from pinned memory, heatmaps resident on the device (backbone output), loss + keypoints "
                     "D2H; HeatmapHotPath.step per batch (upload, kernel and read-back on three streams, two slots), host wall clock incl. "
                     "the final synchronize; graph_replay_* = the same loop with the step replayed from HeatmapHotPath.capture's graph"}
